@@ -1,0 +1,1045 @@
+// engine.cu — host side of libfi_epp: the C ABI of include/fi_epp.h.
+//
+// Owns the device buffers, three CUDA streams (compute, index maintenance, copies),
+// the pinned op ring that keeps the GPU index live (async H2D on the side stream,
+// ordered before the next pick), the host LRU, the per-batch score tables, and the
+// optional NCCL communicator for endpoint-range sharded pools.  No CPU fallback:
+// creation fails without a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/fi_epp.h"
+#include "kernels.cuh"
+#include "lru.h"
+#include "xxh64.cuh"
+
+using namespace fi;
+
+namespace {
+
+// ---- minimal NCCL binding through dlopen (the torch-bundled or the system libnccl.so.2) ----
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt8 = 0, ncclChar = 0, ncclUint8 = 1 };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string* err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      *err = std::string("dlopen libnccl.so.2 failed: ") + dlerror();
+      return false;
+    }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather) {
+      *err = "libnccl is missing a required symbol";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+struct PairKey {
+  uint64_t hash;
+  uint32_t endpoint;
+  bool operator==(const PairKey& o) const { return hash == o.hash && endpoint == o.endpoint; }
+};
+struct PairHash {
+  size_t operator()(const PairKey& k) const {
+    uint64_t x = k.hash ^ ((uint64_t)k.endpoint * 0x9E3779B97F4A7C15ULL);
+    x ^= x >> 29;
+    return (size_t)(x * 0xBF58476D1CE4E5B9ULL);
+  }
+};
+
+constexpr uint64_t kOpChunk = 1ull << 20;  // ops per pinned staging buffer
+enum KernelKind { K_HASH = 0, K_CHAIN = 1, K_MATCH = 2, K_INDEX = 3, K_OTHER = 4, K_KINDS = 5 };
+
+uint32_t pow2_ceil32(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+uint64_t pow2_ceil64(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+struct fi_epp {
+  fi_epp_config cfg;
+  std::mutex mu;
+  std::string err;
+  int sm_count = 148;
+  uint32_t MP = 0;  // chain pitch
+  uint32_t W = 0;   // words per index row
+  uint32_t P = 0;   // profiles
+  bool fast_hash = false;
+
+  cudaStream_t s_main = nullptr, s_index = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_index = nullptr, ev_user = nullptr, ev_done = nullptr, ev_ctr = nullptr, ev_copy = nullptr;
+
+  // request buffers (device)
+  uint8_t* d_prompts = nullptr;
+  uint64_t* d_offsets = nullptr;
+  uint64_t* d_h0 = nullptr;
+  uint64_t* d_pre = nullptr;
+  uint64_t* d_chain = nullptr;
+  uint32_t* d_nblocks = nullptr;
+  fi_pick* d_picks = nullptr;   // [R][P] final
+  fi_pick* d_local = nullptr;   // [R][P] this rank's picks (sharded)
+  fi_pick* d_gather = nullptr;  // [world][R][P]
+  uint32_t* d_mask = nullptr;   // [R][mask_words]
+  uint32_t* d_gmask = nullptr;  // [world][R][mask_words]
+  unsigned long long* d_probed = nullptr;
+  // pinned host mirrors
+  fi_pick* h_picks = nullptr;
+  uint64_t* h_offsets = nullptr;
+  uint64_t* h_h0 = nullptr;
+  uint32_t* h_nblocks = nullptr;
+
+  // index
+  IndexView ix{};
+  IndexCounters* d_ctr = nullptr;
+  IndexCounters* h_ctr = nullptr;  // pinned
+  bool ctr_pending = false;
+  uint64_t rebuilds = 0, ops_applied = 0;
+  fi_index_op* h_sets[2] = {nullptr, nullptr};
+  fi_index_op* h_clears[2] = {nullptr, nullptr};
+  fi_index_op* d_sets[2] = {nullptr, nullptr};
+  fi_index_op* d_clears[2] = {nullptr, nullptr};
+  cudaEvent_t ev_buf[2] = {nullptr, nullptr};
+  int cur_buf = 0;
+  uint64_t n_sets = 0, n_clears = 0;
+  std::unordered_set<PairKey, PairHash> cleared;
+  std::vector<LruSet> lrus;
+
+  // endpoints / score tables
+  std::vector<EndpointDev> eps;  // global pool
+  bool eps_dirty = true;
+  EndpointDev* d_eps = nullptr;
+  double* d_sc = nullptr;
+  uint32_t* d_elig = nullptr;
+  ZeroBest* d_zero = nullptr;
+  ScoreTables st{};
+
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  uint32_t rank = 0, world = 1;
+
+  // stats / profiling
+  fi_epp_stats stats{};
+  bool profiling = false;
+  struct Ev {
+    cudaEvent_t a, b;
+    int kind;
+  };
+  std::vector<Ev> pending_ev;
+  std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace {
+
+#define FI_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                     \
+      return FI_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+int fail(fi_epp* h, int code, const std::string& m) {
+  h->err = m;
+  return code;
+}
+
+cudaEvent_t get_event(fi_epp* h) {
+  if (!h->ev_pool.empty()) {
+    cudaEvent_t e = h->ev_pool.back();
+    h->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// wraps one kernel launch: counts it and, when profiling, brackets it with events
+struct LaunchScope {
+  fi_epp* h;
+  cudaStream_t s;
+  int kind;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(fi_epp* h_, cudaStream_t s_, int kind_) : h(h_), s(s_), kind(kind_) {
+    h->stats.kernel_launches++;
+    if (h->profiling) {
+      a = get_event(h);
+      b = get_event(h);
+      cudaEventRecord(a, s);
+    }
+  }
+  ~LaunchScope() {
+    if (h->profiling) {
+      cudaEventRecord(b, s);
+      h->pending_ev.push_back({a, b, kind});
+    }
+  }
+};
+
+void drain_profile(fi_epp* h) {
+  for (auto& e : h->pending_ev) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+      switch (e.kind) {
+        case K_HASH: h->stats.ms_hash_blocks += ms; h->stats.n_hash_blocks++; break;
+        case K_CHAIN: h->stats.ms_chain_probe += ms; h->stats.n_chain_probe++; break;
+        case K_MATCH: h->stats.ms_match_pick += ms; h->stats.n_match_pick++; break;
+        case K_INDEX: h->stats.ms_index_apply += ms; h->stats.n_index_apply++; break;
+        default: h->stats.ms_other += ms; h->stats.n_other++; break;
+      }
+    }
+    h->ev_pool.push_back(e.a);
+    h->ev_pool.push_back(e.b);
+  }
+  h->pending_ev.clear();
+}
+
+int alloc_index(fi_epp* h, uint64_t slots, IndexView* out) {
+  IndexView v{};
+  v.C = slots;
+  v.bmask = slots / BUCKET_KEYS - 1;
+  v.W = h->W;
+  v.logW = 0;
+  while ((1u << v.logW) < v.W) ++v.logW;
+  const uint64_t total = slots + 2;
+  FI_CUDA(cudaMalloc(&v.keys, total * sizeof(uint64_t)));
+  FI_CUDA(cudaMalloc(&v.rows, total * v.W * sizeof(uint32_t)));
+  FI_CUDA(cudaMalloc(&v.cnt, total * sizeof(uint32_t)));
+  FI_CUDA(cudaMemsetAsync(v.keys, 0, total * sizeof(uint64_t), h->s_index));
+  FI_CUDA(cudaMemsetAsync(v.rows, 0, total * v.W * sizeof(uint32_t), h->s_index));
+  FI_CUDA(cudaMemsetAsync(v.cnt, 0, total * sizeof(uint32_t), h->s_index));
+  *out = v;
+  return FI_OK;
+}
+
+void free_index(IndexView& v) {
+  cudaFree(v.keys);
+  cudaFree(v.rows);
+  cudaFree(v.cnt);
+  v.keys = nullptr;
+  v.rows = nullptr;
+  v.cnt = nullptr;
+}
+
+int rebuild_index(fi_epp* h) {
+  IndexView nv{};
+  int rc = alloc_index(h, h->ix.C, &nv);
+  if (rc != FI_OK) {
+    free_index(nv);
+    return rc;
+  }
+  FI_CUDA(cudaMemsetAsync(h->d_ctr, 0, sizeof(IndexCounters), h->s_index));
+  {
+    LaunchScope ls(h, h->s_index, K_INDEX);
+    FI_CUDA(launch_index_rebuild(h->ix, nv, h->d_ctr, h->s_index));
+  }
+  FI_CUDA(cudaStreamSynchronize(h->s_index));
+  // the compute stream may still be reading the old table
+  FI_CUDA(cudaStreamSynchronize(h->s_main));
+  free_index(h->ix);
+  h->ix = nv;
+  h->rebuilds++;
+  return FI_OK;
+}
+
+// look at the counters copied back after the previous flush; rebuild if the table is
+// clogged with tombstones, fail if it is genuinely full
+int check_counters(fi_epp* h) {
+  if (!h->ctr_pending) return FI_OK;
+  FI_CUDA(cudaEventSynchronize(h->ev_ctr));
+  h->ctr_pending = false;
+  if (h->h_ctr->overflow) return fail(h, FI_ERR_CAPACITY, "index full: raise index_slots");
+  const uint64_t used = h->h_ctr->used, tomb = h->h_ctr->tombstones;
+  if (used * 10 > h->ix.C * 7) {
+    if ((used - tomb) * 10 > h->ix.C * 6) return fail(h, FI_ERR_CAPACITY, "index above 60% live keys: raise index_slots");
+    int rc = rebuild_index(h);
+    if (rc != FI_OK) return rc;
+  }
+  return FI_OK;
+}
+
+// launch the staged SET then CLEAR ops of the current group on the index stream
+int flush_ops(fi_epp* h) {
+  if (h->n_sets == 0 && h->n_clears == 0) return FI_OK;
+  const int b = h->cur_buf;
+  if (h->n_sets) {
+    FI_CUDA(cudaMemcpyAsync(h->d_sets[b], h->h_sets[b], h->n_sets * sizeof(fi_index_op), cudaMemcpyHostToDevice, h->s_index));
+    h->stats.h2d_bytes += h->n_sets * sizeof(fi_index_op);
+    LaunchScope ls(h, h->s_index, K_INDEX);
+    FI_CUDA(launch_index_set(h->ix, h->d_ctr, h->d_sets[b], h->n_sets, h->cfg.endpoint_begin, h->cfg.endpoint_count, h->s_index));
+  }
+  if (h->n_clears) {
+    FI_CUDA(cudaMemcpyAsync(h->d_clears[b], h->h_clears[b], h->n_clears * sizeof(fi_index_op), cudaMemcpyHostToDevice, h->s_index));
+    h->stats.h2d_bytes += h->n_clears * sizeof(fi_index_op);
+    LaunchScope ls(h, h->s_index, K_INDEX);
+    FI_CUDA(launch_index_clear(h->ix, h->d_ctr, h->d_clears[b], h->n_clears, h->cfg.endpoint_begin, h->cfg.endpoint_count, h->s_index));
+  }
+  h->ops_applied += h->n_sets + h->n_clears;
+  FI_CUDA(cudaEventRecord(h->ev_buf[b], h->s_index));
+  FI_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(IndexCounters), cudaMemcpyDeviceToHost, h->s_index));
+  FI_CUDA(cudaEventRecord(h->ev_ctr, h->s_index));
+  h->ctr_pending = true;
+  FI_CUDA(cudaEventRecord(h->ev_index, h->s_index));
+  h->n_sets = h->n_clears = 0;
+  h->cleared.clear();
+  h->cur_buf ^= 1;
+  // the buffer we are about to fill must have been consumed
+  FI_CUDA(cudaEventSynchronize(h->ev_buf[h->cur_buf]));
+  // a rebuild swaps tables; do it between groups only
+  return check_counters(h);
+}
+
+// stage one op (already filtered to this shard).  Within a launch group SETs run
+// before CLEARs, so a SET that follows a CLEAR of the same pair starts a new group.
+int submit_op(fi_epp* h, uint64_t hash, uint32_t endpoint, uint32_t op) {
+  if (op == FI_OP_SET) {
+    if (!h->cleared.empty() && h->cleared.count(PairKey{hash, endpoint})) {
+      int rc = flush_ops(h);
+      if (rc != FI_OK) return rc;
+    }
+    h->h_sets[h->cur_buf][h->n_sets++] = fi_index_op{hash, endpoint, FI_OP_SET};
+  } else {
+    h->cleared.insert(PairKey{hash, endpoint});
+    h->h_clears[h->cur_buf][h->n_clears++] = fi_index_op{hash, endpoint, FI_OP_CLEAR};
+  }
+  if (h->n_sets == kOpChunk || h->n_clears == kOpChunk) return flush_ops(h);
+  return FI_OK;
+}
+
+int upload_endpoints(fi_epp* h) {
+  if (!h->eps_dirty) return FI_OK;
+  FI_CUDA(cudaMemcpyAsync(h->d_eps, h->eps.data(), h->eps.size() * sizeof(EndpointDev), cudaMemcpyHostToDevice, h->s_main));
+  h->stats.h2d_bytes += h->eps.size() * sizeof(EndpointDev);
+  {
+    LaunchScope ls(h, h->s_main, K_OTHER);
+    FI_CUDA(launch_prepare_endpoints(h->d_eps, h->cfg.num_endpoints, h->cfg.endpoint_begin, h->cfg.endpoint_count, h->st,
+                                     h->d_sc, h->d_elig, h->d_zero, h->s_main));
+  }
+  // eps is pageable host memory: the copy above has been staged by the time the call returns
+  h->eps_dirty = false;
+  return FI_OK;
+}
+
+// hash kernels: prompts → chain (device buffers), on s_main
+int run_hash(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0, uint32_t R) {
+  if (h->fast_hash) {
+    {
+      LaunchScope ls(h, h->s_main, K_HASH);
+      FI_CUDA(launch_hash_blocks(d_prompts, d_offsets, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, h->d_pre,
+                                 h->d_nblocks, h->s_main));
+    }
+    LaunchScope ls(h, h->s_main, K_CHAIN);
+    FI_CUDA(launch_chain_finalize(h->d_pre, h->d_nblocks, d_h0, R, h->MP, h->d_chain, h->s_main));
+  } else {
+    LaunchScope ls(h, h->s_main, K_HASH);
+    FI_CUDA(launch_hash_generic(d_prompts, d_offsets, d_h0, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, h->d_chain,
+                                h->d_nblocks, h->s_main));
+  }
+  return FI_OK;
+}
+
+int nccl_allgather(fi_epp* h, const void* send, void* recv, size_t bytes) {
+  int rc = g_nccl.AllGather(send, recv, bytes, ncclInt8, h->comm, h->s_main);
+  if (rc != ncclSuccess)
+    return fail(h, FI_ERR_COMM, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+  return FI_OK;
+}
+
+// the whole pick on device buffers; result in d_out ([R][P])
+int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0, uint32_t R,
+             fi_pick* d_out) {
+  int rc = flush_ops(h);
+  if (rc != FI_OK) return rc;
+  rc = check_counters(h);
+  if (rc != FI_OK) return rc;
+  FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_index, 0));  // every submitted op is visible
+  rc = upload_endpoints(h);
+  if (rc != FI_OK) return rc;
+  rc = run_hash(h, d_prompts, d_offsets, d_h0, R);
+  if (rc != FI_OK) return rc;
+
+  const bool sharded = h->world > 1;
+  MatchParams mp{};
+  mp.chain = h->d_chain;
+  mp.nblocks = h->d_nblocks;
+  mp.offsets = d_offsets;
+  mp.R = R;
+  mp.MP = h->MP;
+  mp.ix = h->ix;
+  mp.st = h->st;
+  mp.ep_begin = h->cfg.endpoint_begin;
+  mp.lpm = h->cfg.match_mode;
+  mp.apply_pd = (h->cfg.pd_enabled && !sharded) ? 1 : 0;
+  mp.pd_decode = h->cfg.pd_decode_profile;
+  mp.pd_prefill = h->cfg.pd_prefill_profile;
+  mp.pd_threshold = h->cfg.pd_threshold;
+  mp.mask_words = (h->MP + 31) / 32;
+  mp.gmask = nullptr;
+  mp.gmask_ranks = 0;
+  mp.out = sharded ? h->d_local : d_out;
+  mp.probed_blocks = h->profiling ? h->d_probed : nullptr;
+
+  if (sharded && h->cfg.match_mode == FI_MATCH_UPSTREAM) {
+    // exact upstream semantics need the global first miss: exchange presence masks
+    {
+      LaunchScope ls(h, h->s_main, K_OTHER);
+      FI_CUDA(launch_probe_mask(mp, h->d_mask, h->sm_count, h->s_main));
+    }
+    const size_t bytes = (size_t)R * mp.mask_words * sizeof(uint32_t);
+    // gathered layout must be [rank][R][words] with the *call's* R
+    rc = nccl_allgather(h, h->d_mask, h->d_gmask, bytes);
+    if (rc != FI_OK) return rc;
+    mp.gmask = h->d_gmask;
+    mp.gmask_ranks = h->world;
+  }
+  {
+    LaunchScope ls(h, h->s_main, K_MATCH);
+    FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
+  }
+  if (sharded) {
+    rc = nccl_allgather(h, h->d_local, h->d_gather, (size_t)R * h->P * sizeof(fi_pick));
+    if (rc != FI_OK) return rc;
+    MergeParams mg{};
+    mg.gathered = h->d_gather;
+    mg.ranks = h->world;
+    mg.R = R;
+    mg.P = h->P;
+    mg.nblocks = h->d_nblocks;
+    mg.offsets = d_offsets;
+    mg.apply_pd = h->cfg.pd_enabled;
+    mg.pd_decode = h->cfg.pd_decode_profile;
+    mg.pd_prefill = h->cfg.pd_prefill_profile;
+    mg.pd_threshold = h->cfg.pd_threshold;
+    mg.out = d_out;
+    LaunchScope ls(h, h->s_main, K_OTHER);
+    FI_CUDA(launch_merge_picks(mg, h->s_main));
+  }
+  h->stats.pick_calls++;
+  h->stats.requests += R;
+  return FI_OK;
+}
+
+int validate_config(const fi_epp_config& c, std::string* err) {
+  auto bad = [&](const char* m) {
+    *err = m;
+    return FI_ERR_INVALID;
+  };
+  if (c.struct_size != sizeof(fi_epp_config)) return bad("struct_size mismatch");
+  if (c.abi_version != FI_EPP_ABI_VERSION) return bad("abi_version mismatch");
+  if (c.block_bytes == 0 || c.block_bytes > (1u << 20)) return bad("block_bytes out of range");
+  if (c.max_blocks == 0 || c.max_blocks > FI_EPP_MAX_BLOCKS) return bad("max_blocks out of range");
+  if (c.num_endpoints == 0) return bad("num_endpoints == 0");
+  if (c.endpoint_count == 0 || (uint64_t)c.endpoint_begin + c.endpoint_count > c.num_endpoints)
+    return bad("endpoint shard out of range");
+  if (c.endpoint_count > 4096) return bad("more than 4096 local endpoints: shard the pool by endpoint range");
+  if (c.match_mode != FI_MATCH_UPSTREAM && c.match_mode != FI_MATCH_LPM) return bad("bad match_mode");
+  if (c.max_batch == 0) return bad("max_batch == 0");
+  if (c.n_profiles == 0 || c.n_profiles > FI_EPP_MAX_PROFILES) return bad("n_profiles out of range");
+  for (uint32_t p = 0; p < c.n_profiles; ++p) {
+    if (c.profiles[p].n_scorers > FI_EPP_MAX_SCORERS) return bad("n_scorers out of range");
+    for (uint32_t s = 0; s < c.profiles[p].n_scorers; ++s) {
+      const uint32_t k = c.profiles[p].scorers[s].kind;
+      if (k == FI_SCORER_LORA) return bad("lora-affinity-scorer is not implemented yet (SURVEY.md §8f)");
+      if (k != FI_SCORER_PREFIX && k != FI_SCORER_KV_UTIL && k != FI_SCORER_QUEUE) return bad("unknown scorer kind");
+      if (c.profiles[p].scorers[s].weight < 0) return bad("scorer weights must be >= 0");
+    }
+  }
+  if (c.pd_enabled) {
+    if (c.pd_decode_profile >= c.n_profiles || c.pd_prefill_profile >= c.n_profiles) return bad("pd profile index out of range");
+    if (!(c.pd_threshold == c.pd_threshold)) return bad("pd_threshold is NaN");
+  }
+  if (c.index_slots) {
+    if (c.index_slots < 64 || (c.index_slots & (c.index_slots - 1))) return bad("index_slots must be a power of two >= 64");
+    if (c.index_slots > 0xFFFFFF00ull) return bad("index_slots too large");
+  }
+  return FI_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+uint32_t fi_epp_abi_version(void) { return FI_EPP_ABI_VERSION; }
+
+const char* fi_epp_status_string(int s) {
+  switch (s) {
+    case FI_OK: return "ok";
+    case FI_ERR_INVALID: return "invalid argument";
+    case FI_ERR_CUDA: return "CUDA error (no CPU fallback exists)";
+    case FI_ERR_NOMEM: return "out of memory";
+    case FI_ERR_CAPACITY: return "capacity exceeded";
+    case FI_ERR_STATE: return "invalid state";
+    case FI_ERR_COMM: return "communicator error";
+    case FI_ERR_CONFIG: return "EndpointPickerConfig rejected";
+    default: return "unknown status";
+  }
+}
+
+int fi_epp_config_default(fi_epp_config* c) {
+  if (!c) return FI_ERR_INVALID;
+  std::memset(c, 0, sizeof(*c));
+  c->struct_size = sizeof(*c);
+  c->abi_version = FI_EPP_ABI_VERSION;
+  c->device = 0;
+  c->block_bytes = 64;     // 16 uint32 tokens; the reference YAML overrides it (strategy.go:57)
+  c->max_blocks = 256;     // strategy.go:58
+  c->lru_capacity = 31250; // strategy.go:59
+  c->num_endpoints = 1;
+  c->endpoint_begin = 0;
+  c->endpoint_count = 1;
+  c->match_mode = FI_MATCH_UPSTREAM;
+  c->max_batch = 1024;
+  c->max_prompt_bytes = 0;  // 0 = max_batch * block_bytes * max_blocks
+  c->index_slots = 0;
+  c->n_profiles = 1;  // generatePrefixCacheConfig: profile "default" = picker + prefix scorer weight 100
+  std::snprintf(c->profiles[0].name, sizeof(c->profiles[0].name), "default");
+  c->profiles[0].n_scorers = 1;
+  c->profiles[0].scorers[0].kind = FI_SCORER_PREFIX;
+  c->profiles[0].scorers[0].weight = 100;  // strategy.go:66
+  return FI_OK;
+}
+
+int fi_epp_model_seed(const void* model, size_t model_len, const void* salt, size_t salt_len, uint64_t* h0) {
+  if (!h0 || (!model && model_len) || (!salt && salt_len)) return FI_ERR_INVALID;
+  if (model_len + salt_len > 0x7FFFFFFFull) return FI_ERR_INVALID;
+  std::vector<uint8_t> buf(model_len + salt_len);
+  if (model_len) std::memcpy(buf.data(), model, model_len);
+  if (salt_len) std::memcpy(buf.data() + model_len, salt, salt_len);
+  *h0 = xxh64_bytes(buf.data(), (uint32_t)buf.size());
+  return FI_OK;
+}
+
+void* fi_epp_pinned_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void fi_epp_pinned_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+const char* fi_epp_last_error(const fi_epp* h) { return h ? h->err.c_str() : "null handle"; }
+
+void fi_epp_destroy(fi_epp* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->s_main) cudaStreamSynchronize(h->s_main);
+  if (h->s_index) cudaStreamSynchronize(h->s_index);
+  if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  drain_profile(h);
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  cudaFree(h->d_prompts);
+  cudaFree(h->d_offsets);
+  cudaFree(h->d_h0);
+  cudaFree(h->d_pre);
+  cudaFree(h->d_chain);
+  cudaFree(h->d_nblocks);
+  cudaFree(h->d_picks);
+  cudaFree(h->d_local);
+  cudaFree(h->d_gather);
+  cudaFree(h->d_mask);
+  cudaFree(h->d_gmask);
+  cudaFree(h->d_probed);
+  cudaFree(h->d_ctr);
+  cudaFree(h->d_eps);
+  cudaFree(h->d_sc);
+  cudaFree(h->d_elig);
+  cudaFree(h->d_zero);
+  free_index(h->ix);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(h->d_sets[b]);
+    cudaFree(h->d_clears[b]);
+    if (h->h_sets[b]) cudaFreeHost(h->h_sets[b]);
+    if (h->h_clears[b]) cudaFreeHost(h->h_clears[b]);
+    if (h->ev_buf[b]) cudaEventDestroy(h->ev_buf[b]);
+  }
+  if (h->h_picks) cudaFreeHost(h->h_picks);
+  if (h->h_offsets) cudaFreeHost(h->h_offsets);
+  if (h->h_h0) cudaFreeHost(h->h_h0);
+  if (h->h_nblocks) cudaFreeHost(h->h_nblocks);
+  if (h->h_ctr) cudaFreeHost(h->h_ctr);
+  for (cudaEvent_t e : {h->ev_index, h->ev_user, h->ev_done, h->ev_ctr, h->ev_copy})
+    if (e) cudaEventDestroy(e);
+  for (cudaStream_t s : {h->s_main, h->s_index, h->s_copy})
+    if (s) cudaStreamDestroy(s);
+  delete h;
+}
+
+int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
+  if (!cfg || !out) return FI_ERR_INVALID;
+  *out = nullptr;
+  std::unique_ptr<fi_epp> up(new fi_epp());
+  fi_epp* h = up.get();
+  h->cfg = *cfg;
+  {
+    std::string e;
+    int rc = validate_config(*cfg, &e);
+    if (rc != FI_OK) {
+      std::fprintf(stderr, "fi_epp_create: %s\n", e.c_str());
+      return rc;
+    }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    std::fprintf(stderr, "fi_epp_create: no CUDA device — libfi_epp has no CPU fallback\n");
+    return FI_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    std::fprintf(stderr, "fi_epp_create: device %d out of range (%d devices)\n", cfg->device, ndev);
+    return FI_ERR_INVALID;
+  }
+  auto die = [&](int rc) {
+    std::fprintf(stderr, "fi_epp_create: %s\n", h->err.c_str());
+    fi_epp_destroy(up.release());
+    return rc;
+  };
+#define FI_TRY(call)                                                    \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) {                                           \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);     \
+      return die(e__ == cudaErrorMemoryAllocation ? FI_ERR_NOMEM : FI_ERR_CUDA); \
+    }                                                                   \
+  } while (0)
+  FI_TRY(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  FI_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  h->sm_count = prop.multiProcessorCount;
+  h->P = cfg->n_profiles;
+  h->MP = (cfg->max_blocks + 3) & ~3u;
+  h->W = pow2_ceil32((cfg->endpoint_count + 31) / 32);
+  h->fast_hash = (cfg->block_bytes % 32) == 0;
+  if (h->cfg.max_prompt_bytes == 0)
+    h->cfg.max_prompt_bytes = (uint64_t)cfg->max_batch * cfg->block_bytes * cfg->max_blocks;
+  if (h->cfg.index_slots == 0) {
+    uint64_t want = 2ull * cfg->endpoint_count * (cfg->lru_capacity ? cfg->lru_capacity : 1024);
+    if (want < 4096) want = 4096;
+    h->cfg.index_slots = pow2_ceil64(want);
+    if (h->cfg.index_slots > 0x80000000ull) h->cfg.index_slots = 0x80000000ull;
+  }
+
+  FI_TRY(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+  FI_TRY(cudaStreamCreateWithFlags(&h->s_index, cudaStreamNonBlocking));
+  FI_TRY(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&h->ev_index, &h->ev_user, &h->ev_done, &h->ev_ctr, &h->ev_copy})
+    FI_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  FI_TRY(cudaEventRecord(h->ev_index, h->s_index));
+
+  const uint64_t R = cfg->max_batch;
+  const uint32_t mask_words = (h->MP + 31) / 32;
+  FI_TRY(cudaMalloc(&h->d_prompts, h->cfg.max_prompt_bytes + 64));
+  FI_TRY(cudaMalloc(&h->d_offsets, (R + 1) * sizeof(uint64_t)));
+  FI_TRY(cudaMalloc(&h->d_h0, R * sizeof(uint64_t)));
+  FI_TRY(cudaMalloc(&h->d_pre, R * h->MP * sizeof(uint64_t)));
+  FI_TRY(cudaMalloc(&h->d_chain, R * h->MP * sizeof(uint64_t)));
+  FI_TRY(cudaMalloc(&h->d_nblocks, R * sizeof(uint32_t)));
+  FI_TRY(cudaMalloc(&h->d_picks, R * h->P * sizeof(fi_pick)));
+  FI_TRY(cudaMalloc(&h->d_probed, sizeof(unsigned long long)));
+  FI_TRY(cudaMemset(h->d_probed, 0, sizeof(unsigned long long)));
+  FI_TRY(cudaMallocHost(&h->h_picks, R * h->P * sizeof(fi_pick)));
+  FI_TRY(cudaMallocHost(&h->h_offsets, (R + 1) * sizeof(uint64_t)));
+  FI_TRY(cudaMallocHost(&h->h_h0, R * sizeof(uint64_t)));
+  FI_TRY(cudaMallocHost(&h->h_nblocks, R * sizeof(uint32_t)));
+  (void)mask_words;
+
+  // index
+  FI_TRY(cudaMalloc(&h->d_ctr, sizeof(IndexCounters)));
+  FI_TRY(cudaMemset(h->d_ctr, 0, sizeof(IndexCounters)));
+  FI_TRY(cudaMallocHost(&h->h_ctr, sizeof(IndexCounters)));
+  std::memset(h->h_ctr, 0, sizeof(IndexCounters));
+  {
+    int rc = alloc_index(h, h->cfg.index_slots, &h->ix);
+    if (rc != FI_OK) return die(rc == FI_ERR_CUDA ? FI_ERR_NOMEM : rc);
+  }
+  for (int b = 0; b < 2; ++b) {
+    FI_TRY(cudaMallocHost(&h->h_sets[b], kOpChunk * sizeof(fi_index_op)));
+    FI_TRY(cudaMallocHost(&h->h_clears[b], kOpChunk * sizeof(fi_index_op)));
+    FI_TRY(cudaMalloc(&h->d_sets[b], kOpChunk * sizeof(fi_index_op)));
+    FI_TRY(cudaMalloc(&h->d_clears[b], kOpChunk * sizeof(fi_index_op)));
+    FI_TRY(cudaEventCreateWithFlags(&h->ev_buf[b], cudaEventDisableTiming));
+    FI_TRY(cudaEventRecord(h->ev_buf[b], h->s_index));
+  }
+  if (cfg->lru_capacity) h->lrus.assign(cfg->endpoint_count, LruSet(cfg->lru_capacity));
+
+  // endpoints + score tables
+  h->eps.assign(cfg->num_endpoints, EndpointDev{0.0, 0, 0, 0, 0});
+  const uint32_t Epad = h->W * 32;
+  FI_TRY(cudaMalloc(&h->d_eps, (size_t)cfg->num_endpoints * sizeof(EndpointDev)));
+  FI_TRY(cudaMalloc(&h->d_sc, (size_t)FI_EPP_MAX_PROFILES * FI_EPP_MAX_SCORERS * Epad * sizeof(double)));
+  FI_TRY(cudaMalloc(&h->d_elig, (size_t)FI_EPP_MAX_PROFILES * h->W * sizeof(uint32_t)));
+  FI_TRY(cudaMalloc(&h->d_zero, FI_EPP_MAX_PROFILES * sizeof(ZeroBest)));
+  FI_TRY(cudaMemset(h->d_sc, 0, (size_t)FI_EPP_MAX_PROFILES * FI_EPP_MAX_SCORERS * Epad * sizeof(double)));
+  FI_TRY(cudaMemset(h->d_elig, 0, (size_t)FI_EPP_MAX_PROFILES * h->W * sizeof(uint32_t)));
+  h->st.n_profiles = h->P;
+  h->st.Epad = Epad;
+  h->st.sc = h->d_sc;
+  h->st.elig = h->d_elig;
+  h->st.zero = h->d_zero;
+  for (uint32_t p = 0; p < h->P; ++p) {
+    ProfileDev& d = h->st.prof[p];
+    d.n_scorers = cfg->profiles[p].n_scorers;
+    d.role_mask = cfg->profiles[p].role_mask;
+    for (uint32_t s = 0; s < d.n_scorers; ++s) {
+      d.kind[s] = cfg->profiles[p].scorers[s].kind;
+      d.weight[s] = (double)cfg->profiles[p].scorers[s].weight;
+    }
+  }
+  FI_TRY(cudaStreamSynchronize(h->s_index));
+  FI_TRY(cudaDeviceSynchronize());
+#undef FI_TRY
+  *out = up.release();
+  return FI_OK;
+}
+
+int fi_epp_endpoints_update(fi_epp* h, const fi_endpoint_state* s, uint32_t n) {
+  if (!h || (!s && n)) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (s[i].endpoint >= h->cfg.num_endpoints) return fail(h, FI_ERR_INVALID, "endpoint index out of range");
+    if (!std::isfinite(s[i].kv_util)) return fail(h, FI_ERR_INVALID, "kv_util must be finite");
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    EndpointDev& e = h->eps[s[i].endpoint];
+    e.kv_util = s[i].kv_util;
+    e.queue_depth = s[i].queue_depth;
+    e.role_mask = s[i].role_mask;
+    e.flags = s[i].flags;
+  }
+  h->eps_dirty = true;
+  return FI_OK;
+}
+
+int fi_epp_index_apply(fi_epp* h, const fi_index_op* ops, uint64_t n) {
+  if (!h || (!ops && n)) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  int rc = check_counters(h);
+  if (rc != FI_OK) return rc;
+  const uint32_t lo = h->cfg.endpoint_begin, cnt = h->cfg.endpoint_count;
+  for (uint64_t i = 0; i < n; ++i) {
+    const fi_index_op& op = ops[i];
+    if (op.op != FI_OP_SET && op.op != FI_OP_CLEAR) return fail(h, FI_ERR_INVALID, "bad index opcode");
+    if (op.endpoint >= h->cfg.num_endpoints) return fail(h, FI_ERR_INVALID, "index op endpoint out of range");
+    if (op.endpoint - lo >= cnt) continue;  // another rank's shard
+    rc = submit_op(h, op.hash, op.endpoint, op.op);
+    if (rc != FI_OK) return rc;
+  }
+  return flush_ops(h);
+}
+
+int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes, uint32_t n) {
+  if (!h || (!hashes && n)) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  if (!h->cfg.lru_capacity) return fail(h, FI_ERR_STATE, "lru_capacity is 0: the host LRU is disabled");
+  if (endpoint >= h->cfg.num_endpoints) return fail(h, FI_ERR_INVALID, "endpoint out of range");
+  const uint32_t e = endpoint - h->cfg.endpoint_begin;
+  if (e >= h->cfg.endpoint_count) return FI_OK;  // another rank's shard
+  int rc = check_counters(h);
+  if (rc != FI_OK) return rc;
+  LruSet& l = h->lrus[e];
+  for (uint32_t i = 0; i < n; ++i) {
+    uint64_t ev = 0;
+    bool did = false;
+    const bool inserted = l.touch(hashes[i], &ev, &did);
+    if (did) {
+      rc = submit_op(h, ev, endpoint, FI_OP_CLEAR);
+      if (rc != FI_OK) return rc;
+    }
+    if (inserted) {
+      rc = submit_op(h, hashes[i], endpoint, FI_OP_SET);
+      if (rc != FI_OK) return rc;
+    }
+  }
+  return flush_ops(h);
+}
+
+int fi_epp_index_sync(fi_epp* h) {
+  if (!h) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  int rc = flush_ops(h);
+  if (rc != FI_OK) return rc;
+  FI_CUDA(cudaStreamSynchronize(h->s_index));
+  return check_counters(h);
+}
+
+int fi_epp_index_stats(fi_epp* h, fi_index_stats* out) {
+  if (!h || !out) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  int rc = flush_ops(h);
+  if (rc != FI_OK) return rc;
+  FI_CUDA(cudaStreamSynchronize(h->s_index));
+  IndexCounters c;
+  FI_CUDA(cudaMemcpy(&c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost));
+  out->slots = h->ix.C;
+  out->used = c.used;
+  out->tombstones = c.tombstones;
+  out->rebuilds = h->rebuilds;
+  out->ops_applied = h->ops_applied;
+  uint64_t l = 0;
+  for (auto& s : h->lrus) l += s.size();
+  out->lru_entries = l;
+  return FI_OK;
+}
+
+// diagnostics for tests: out[i] = 1 iff (ops[i].endpoint, ops[i].hash) is in the GPU index
+int fi_epp_index_contains(fi_epp* h, const fi_index_op* q, uint64_t n, uint8_t* out) {
+  if (!h || (!q && n) || (!out && n)) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  int rc = flush_ops(h);
+  if (rc != FI_OK) return rc;
+  if (n == 0) return FI_OK;
+  fi_index_op* dq = nullptr;
+  uint8_t* dout = nullptr;
+  FI_CUDA(cudaMalloc(&dq, n * sizeof(fi_index_op)));
+  if (cudaMalloc(&dout, n) != cudaSuccess) {
+    cudaFree(dq);
+    return fail(h, FI_ERR_NOMEM, "cudaMalloc failed");
+  }
+  cudaError_t e = cudaMemcpyAsync(dq, q, n * sizeof(fi_index_op), cudaMemcpyHostToDevice, h->s_index);
+  if (e == cudaSuccess) {
+    LaunchScope ls(h, h->s_index, K_OTHER);
+    e = launch_index_contains(h->ix, dq, n, h->cfg.endpoint_begin, h->cfg.endpoint_count, dout, h->s_index);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, n, cudaMemcpyDeviceToHost, h->s_index);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_index);
+  cudaFree(dq);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(h, FI_ERR_CUDA, cudaGetErrorString(e));
+  return FI_OK;
+}
+
+static int check_batch(fi_epp* h, const uint64_t* offsets, uint32_t R, uint64_t* total) {
+  if (R > h->cfg.max_batch) return fail(h, FI_ERR_CAPACITY, "batch larger than max_batch");
+  if (offsets[0] != 0) return fail(h, FI_ERR_INVALID, "offsets[0] must be 0");
+  for (uint32_t r = 0; r < R; ++r)
+    if (offsets[r + 1] < offsets[r]) return fail(h, FI_ERR_INVALID, "offsets must be non-decreasing");
+  *total = offsets[R];
+  if (*total > h->cfg.max_prompt_bytes) return fail(h, FI_ERR_CAPACITY, "prompt bytes larger than max_prompt_bytes");
+  return FI_OK;
+}
+
+static int stage_inputs(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
+                        uint64_t total) {
+  std::memcpy(h->h_offsets, offsets, (size_t)(R + 1) * sizeof(uint64_t));
+  std::memcpy(h->h_h0, h0, (size_t)R * sizeof(uint64_t));
+  FI_CUDA(cudaMemcpyAsync(h->d_offsets, h->h_offsets, (size_t)(R + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->s_main));
+  FI_CUDA(cudaMemcpyAsync(h->d_h0, h->h_h0, (size_t)R * sizeof(uint64_t), cudaMemcpyHostToDevice, h->s_main));
+  if (total) FI_CUDA(cudaMemcpyAsync(h->d_prompts, prompts, total, cudaMemcpyHostToDevice, h->s_main));
+  h->stats.h2d_bytes += total + (size_t)(2 * R + 1) * sizeof(uint64_t);
+  return FI_OK;
+}
+
+static int copy_chains_out(fi_epp* h, uint64_t* chains_out, uint32_t R, cudaMemcpyKind kind, cudaStream_t s) {
+  const size_t row = (size_t)h->cfg.max_blocks * sizeof(uint64_t);
+  FI_CUDA(cudaMemcpy2DAsync(chains_out, row, h->d_chain, (size_t)h->MP * sizeof(uint64_t), row, R, kind, s));
+  if (kind == cudaMemcpyDeviceToHost) h->stats.d2h_bytes += row * R;
+  return FI_OK;
+}
+
+int fi_epp_hash_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
+                      uint64_t* chains_out, uint32_t* nblocks_out) {
+  if (!h || !offsets || (!h0 && R) || (!prompts && R && offsets[R])) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  if (R == 0) return FI_OK;
+  uint64_t total = 0;
+  int rc = check_batch(h, offsets, R, &total);
+  if (rc != FI_OK) return rc;
+  rc = stage_inputs(h, prompts, offsets, h0, R, total);
+  if (rc != FI_OK) return rc;
+  rc = run_hash(h, h->d_prompts, h->d_offsets, h->d_h0, R);
+  if (rc != FI_OK) return rc;
+  if (chains_out) {
+    rc = copy_chains_out(h, chains_out, R, cudaMemcpyDeviceToHost, h->s_main);
+    if (rc != FI_OK) return rc;
+  }
+  if (nblocks_out) {
+    FI_CUDA(cudaMemcpyAsync(h->h_nblocks, h->d_nblocks, (size_t)R * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_main));
+    h->stats.d2h_bytes += (size_t)R * sizeof(uint32_t);
+  }
+  FI_CUDA(cudaStreamSynchronize(h->s_main));
+  if (nblocks_out) std::memcpy(nblocks_out, h->h_nblocks, (size_t)R * sizeof(uint32_t));
+  return FI_OK;
+}
+
+int fi_epp_pick_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
+                      fi_pick* out, uint64_t* chains_out) {
+  if (!h || !offsets || (!h0 && R) || (!out && R) || (!prompts && R && offsets[R])) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  if (R == 0) return FI_OK;
+  uint64_t total = 0;
+  int rc = check_batch(h, offsets, R, &total);
+  if (rc != FI_OK) return rc;
+  rc = stage_inputs(h, prompts, offsets, h0, R, total);
+  if (rc != FI_OK) return rc;
+  rc = run_pick(h, h->d_prompts, h->d_offsets, h->d_h0, R, h->d_picks);
+  if (rc != FI_OK) return rc;
+  const size_t pb = (size_t)R * h->P * sizeof(fi_pick);
+  FI_CUDA(cudaMemcpyAsync(h->h_picks, h->d_picks, pb, cudaMemcpyDeviceToHost, h->s_main));
+  h->stats.d2h_bytes += pb;
+  if (chains_out) {
+    rc = copy_chains_out(h, chains_out, R, cudaMemcpyDeviceToHost, h->s_main);
+    if (rc != FI_OK) return rc;
+  }
+  FI_CUDA(cudaStreamSynchronize(h->s_main));
+  std::memcpy(out, h->h_picks, pb);
+  return FI_OK;
+}
+
+int fi_epp_pick_batch_device(fi_epp* h, const void* d_prompts, const void* d_offsets, const void* d_h0, uint32_t R,
+                             uint64_t total_prompt_bytes, void* d_out, void* d_chains_out, void* stream) {
+  if (!h || !d_offsets || (!d_h0 && R) || (!d_out && R)) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  if (R == 0) return FI_OK;
+  if (R > h->cfg.max_batch) return fail(h, FI_ERR_CAPACITY, "batch larger than max_batch");
+  (void)total_prompt_bytes;  // inputs stay where they are: no staging copy, no capacity limit
+  cudaStream_t us = (cudaStream_t)stream;
+  FI_CUDA(cudaEventRecord(h->ev_user, us));
+  FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_user, 0));
+  int rc = run_pick(h, (const uint8_t*)d_prompts, (const uint64_t*)d_offsets, (const uint64_t*)d_h0, R, (fi_pick*)d_out);
+  if (rc != FI_OK) return rc;
+  if (d_chains_out) {
+    rc = copy_chains_out(h, (uint64_t*)d_chains_out, R, cudaMemcpyDeviceToDevice, h->s_main);
+    if (rc != FI_OK) return rc;
+  }
+  FI_CUDA(cudaEventRecord(h->ev_done, h->s_main));
+  FI_CUDA(cudaStreamWaitEvent(us, h->ev_done, 0));
+  return FI_OK;
+}
+
+int fi_epp_comm_unique_id(uint8_t out[FI_EPP_UNIQUE_ID_BYTES]) {
+  if (!out) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  std::string e;
+  if (!g_nccl.load(&e)) {
+    std::fprintf(stderr, "fi_epp_comm_unique_id: %s\n", e.c_str());
+    return FI_ERR_COMM;
+  }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return FI_ERR_COMM;
+  static_assert(sizeof(ncclUniqueId) == FI_EPP_UNIQUE_ID_BYTES, "unique id size");
+  std::memcpy(out, &id, sizeof(id));
+  return FI_OK;
+}
+
+int fi_epp_comm_init(fi_epp* h, const uint8_t id_bytes[FI_EPP_UNIQUE_ID_BYTES], uint32_t rank, uint32_t world) {
+  if (!h || !id_bytes || world == 0 || rank >= world) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  if (h->comm) return fail(h, FI_ERR_STATE, "communicator already initialised");
+  if (world == 1) {
+    h->rank = 0;
+    h->world = 1;
+    return FI_OK;
+  }
+  {
+    std::lock_guard<std::mutex> lk2(g_nccl_mu);
+    std::string e;
+    if (!g_nccl.load(&e)) return fail(h, FI_ERR_COMM, e);
+  }
+  ncclUniqueId id;
+  std::memcpy(&id, id_bytes, sizeof(id));
+  int rc = g_nccl.CommInitRank(&h->comm, (int)world, id, (int)rank);
+  if (rc != ncclSuccess) {
+    h->comm = nullptr;
+    return fail(h, FI_ERR_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+  }
+  const uint64_t R = h->cfg.max_batch;
+  const uint32_t mask_words = (h->MP + 31) / 32;
+  FI_CUDA(cudaMalloc(&h->d_local, R * h->P * sizeof(fi_pick)));
+  FI_CUDA(cudaMalloc(&h->d_gather, (size_t)world * R * h->P * sizeof(fi_pick)));
+  FI_CUDA(cudaMalloc(&h->d_mask, R * mask_words * sizeof(uint32_t)));
+  FI_CUDA(cudaMalloc(&h->d_gmask, (size_t)world * R * mask_words * sizeof(uint32_t)));
+  h->rank = rank;
+  h->world = world;
+  return FI_OK;
+}
+
+int fi_epp_set_profiling(fi_epp* h, int on) {
+  if (!h) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaSetDevice(h->cfg.device);
+  drain_profile(h);
+  h->profiling = on != 0;
+  return FI_OK;
+}
+
+int fi_epp_get_stats(fi_epp* h, fi_epp_stats* out) {
+  if (!h || !out) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  drain_profile(h);
+  if (h->profiling) {
+    FI_CUDA(cudaStreamSynchronize(h->s_main));
+    unsigned long long pb = 0;
+    FI_CUDA(cudaMemcpy(&pb, h->d_probed, sizeof(pb), cudaMemcpyDeviceToHost));
+    h->stats.probed_blocks = pb;
+  }
+  *out = h->stats;
+  return FI_OK;
+}
+
+int fi_epp_reset_stats(fi_epp* h) {
+  if (!h) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaSetDevice(h->cfg.device);
+  drain_profile(h);
+  cudaStreamSynchronize(h->s_main);
+  cudaMemset(h->d_probed, 0, sizeof(unsigned long long));
+  h->stats = fi_epp_stats{};
+  return FI_OK;
+}
+
+}  // extern "C"

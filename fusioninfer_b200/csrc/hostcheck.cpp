@@ -1,0 +1,96 @@
+// hostcheck.cpp — host build of the arithmetic the kernels share with the CPU
+// (xxh64.cuh, bitslice.cuh) and of the host LRU, exported for CPU unit tests
+// (tests/test_host_logic.py).  Not part of libfi_epp.so and never used to serve a pick.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "bitslice.cuh"
+#include "lru.h"
+#include "xxh64.cuh"
+
+extern "C" {
+
+uint64_t fihc_xxh64(const uint8_t* p, uint32_t len) { return fi::xxh64_bytes(p, len); }
+
+// chain via the generic virtual-message path (any block size)
+uint32_t fihc_chain_generic(const uint8_t* p, uint64_t len, uint64_t h0, uint32_t B, uint32_t M, uint64_t* out) {
+  uint64_t nb = len / B;
+  if (nb > M) nb = M;
+  uint64_t h = h0;
+  for (uint64_t i = 0; i < nb; ++i) {
+    fi::ChainMsg m{p + i * B, B, h, true};
+    h = fi::xxh64_msg(m);
+    out[i] = h;
+  }
+  return (uint32_t)nb;
+}
+
+// chain via the split pre-state / chain_step path (B % 32 == 0), as the GPU fast path does
+uint32_t fihc_chain_split(const uint8_t* p, uint64_t len, uint64_t h0, uint32_t B, uint32_t M, uint64_t* out) {
+  if (B % 32) return 0;
+  uint64_t nb = len / B;
+  if (nb > M) nb = M;
+  uint64_t h = h0;
+  for (uint64_t i = 0; i < nb; ++i) {
+    fi::XAcc a = fi::xacc_init();
+    for (uint32_t s = 0; s < B / 32; ++s) {
+      uint64_t w[4];
+      std::memcpy(w, p + i * B + 32 * s, 32);
+      fi::xacc_stripe(a, w[0], w[1], w[2], w[3]);
+    }
+    const uint64_t pre = fi::xacc_finish(a, (uint64_t)B + 8);
+    h = fi::chain_step(pre, h);
+    out[i] = h;
+  }
+  return (uint32_t)nb;
+}
+
+// bit-sliced counting: add n words K at a time (zero padded), return the 32 counts
+void fihc_bitcount(const uint32_t* words, uint32_t n, uint32_t K, uint32_t* counts) {
+  fi::BitCounter b;
+  fi::bc_clear(b);
+  for (uint32_t i = 0; i < n; i += K) {
+    uint32_t w[16] = {0};
+    for (uint32_t j = 0; j < K && i + j < n; ++j) w[j] = words[i + j];
+    switch (K) {
+      case 1: { uint32_t t[1] = {w[0]}; fi::bc_add<1>(b, t); break; }
+      case 2: { uint32_t t[2] = {w[0], w[1]}; fi::bc_add<2>(b, t); break; }
+      case 4: { uint32_t t[4]; std::memcpy(t, w, sizeof(t)); fi::bc_add<4>(b, t); break; }
+      case 8: { uint32_t t[8]; std::memcpy(t, w, sizeof(t)); fi::bc_add<8>(b, t); break; }
+      default: { uint32_t t[16]; std::memcpy(t, w, sizeof(t)); fi::bc_add<16>(b, t); break; }
+    }
+  }
+  for (uint32_t bit = 0; bit < 32; ++bit) counts[bit] = fi::bc_get(b, bit);
+}
+
+// merge of two counters built from two word streams
+void fihc_bitcount_merge(const uint32_t* wa, uint32_t na, const uint32_t* wb, uint32_t nb, uint32_t* counts,
+                         uint32_t* nonzero) {
+  fi::BitCounter a, b;
+  fi::bc_clear(a);
+  fi::bc_clear(b);
+  for (uint32_t i = 0; i < na; ++i) { uint32_t t[1] = {wa[i]}; fi::bc_add<1>(a, t); }
+  for (uint32_t i = 0; i < nb; ++i) { uint32_t t[1] = {wb[i]}; fi::bc_add<1>(b, t); }
+  fi::bc_merge(a, b);
+  for (uint32_t bit = 0; bit < 32; ++bit) counts[bit] = fi::bc_get(a, bit);
+  *nonzero = fi::bc_nonzero(a);
+}
+
+// LRU trace: for each key report (inserted, did_evict, evicted)
+void* fihc_lru_new(uint32_t cap) { return new fi::LruSet(cap); }
+void fihc_lru_free(void* l) { delete (fi::LruSet*)l; }
+uint32_t fihc_lru_size(void* l) { return ((fi::LruSet*)l)->size(); }
+int fihc_lru_contains(void* l, uint64_t k) { return ((fi::LruSet*)l)->contains(k) ? 1 : 0; }
+void fihc_lru_touch(void* l, const uint64_t* keys, uint32_t n, uint8_t* inserted, uint8_t* did_evict, uint64_t* evicted) {
+  fi::LruSet* s = (fi::LruSet*)l;
+  for (uint32_t i = 0; i < n; ++i) {
+    bool d = false;
+    uint64_t ev = 0;
+    inserted[i] = s->touch(keys[i], &ev, &d) ? 1 : 0;
+    did_evict[i] = d ? 1 : 0;
+    evicted[i] = ev;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+// kernels.cuh — device-side data layout and launcher declarations of libfi_epp.
+//
+// HBM layout (DESIGN.md "Data layout"):
+//   prompts   concatenated prompt bytes, request r = [offsets[r], offsets[r+1])
+//   pre       [R][MP] u64   block pre-states (hash_blocks → chain_finalize)
+//   chain     [R][MP] u64   chained block hashes h_1..h_n
+//   index     keys  [C+2]   u64, buckets of 4 keys = one 32 B sector; 0 = empty,
+//                           ~0 = tombstone; slots C, C+1 hold hashes 0 and ~0
+//             rows  [C+2][W] u32, row s = membership bitset of key s over the
+//                           local endpoints (bit e%32 of word e/32)
+//             cnt   [C+2]   u32 popcount of the row (key present ⇔ cnt > 0)
+//   picks     [R][P]        fi_pick
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fi_epp.h"
+
+namespace fi {
+
+constexpr uint32_t SLOT_MISS = 0xFFFFFFFFu;
+constexpr uint64_t KEY_EMPTY = 0ull;
+constexpr uint64_t KEY_TOMB = ~0ull;
+constexpr int BUCKET_KEYS = 4;
+
+struct IndexView {
+  uint64_t* keys;
+  uint32_t* rows;
+  uint32_t* cnt;
+  uint64_t bmask;  // buckets - 1
+  uint64_t C;      // regular slots = buckets * 4
+  uint32_t W;      // words per row (power of two)
+  uint32_t logW;
+};
+
+// device-side counters of the index (one cache line)
+struct IndexCounters {
+  unsigned long long used;        // slots claimed (keys + tombstones)
+  unsigned long long tombstones;  // keys retired because their row emptied
+  unsigned long long overflow;    // != 0: an insert found no free slot
+  unsigned long long pad;
+};
+
+struct ProfileDev {
+  uint32_t n_scorers;
+  uint32_t role_mask;
+  uint32_t kind[FI_EPP_MAX_SCORERS];
+  double weight[FI_EPP_MAX_SCORERS];
+};
+
+// best endpoint of a profile when no prefix block matches (per batch constant)
+struct ZeroBest {
+  double score;
+  uint32_t e_local;  // FI_NO_ENDPOINT if no eligible local endpoint
+  uint32_t pad;
+};
+
+struct EndpointDev {  // raw state of one endpoint of the GLOBAL pool
+  double kv_util;
+  int32_t queue_depth;
+  uint32_t role_mask;
+  uint32_t flags;
+  uint32_t pad;
+};
+
+struct ScoreTables {
+  ProfileDev prof[FI_EPP_MAX_PROFILES];
+  uint32_t n_profiles;
+  uint32_t Epad;        // W * 32
+  const double* sc;     // [P][S][Epad] clamp01'd per-endpoint scores of the non-prefix scorers
+  const uint32_t* elig; // [P][W] eligibility bit words
+  const ZeroBest* zero; // [P]
+};
+
+struct MatchParams {
+  const uint64_t* chain;
+  const uint32_t* nblocks;
+  const uint64_t* offsets;  // [R+1], prompt byte offsets (PD threshold); may be null if !apply_pd
+  uint32_t R;
+  uint32_t MP;  // pitch of chain rows (multiple of 4)
+  IndexView ix;
+  ScoreTables st;
+  uint32_t ep_begin;
+  uint32_t lpm;  // fi_match_mode
+  // pd-profile-handler
+  uint32_t apply_pd, pd_decode, pd_prefill;
+  double pd_threshold;
+  // sharded exact-upstream mode: presence masks of all ranks [ranks][R][mask_words]
+  const uint32_t* gmask;
+  uint32_t gmask_ranks;
+  uint32_t mask_words;
+  fi_pick* out;                       // [R][P]
+  unsigned long long* probed_blocks;  // optional Σ N_probe
+};
+
+struct MergeParams {
+  const fi_pick* gathered;  // [ranks][R][P]
+  uint32_t ranks, R, P;
+  const uint32_t* nblocks;
+  const uint64_t* offsets;
+  uint32_t apply_pd, pd_decode, pd_prefill;
+  double pd_threshold;
+  fi_pick* out;  // [R][P]
+};
+
+// ---- launchers (each returns the cudaGetLastError() of its launch) -----------
+cudaError_t launch_hash_blocks(const uint8_t* prompts, const uint64_t* offsets, uint32_t R, uint32_t B,
+                               uint32_t M, uint32_t MP, uint64_t* pre, uint32_t* nblocks, cudaStream_t s);
+cudaError_t launch_chain_finalize(const uint64_t* pre, const uint32_t* nblocks, const uint64_t* h0,
+                                  uint32_t R, uint32_t MP, uint64_t* chain, cudaStream_t s);
+cudaError_t launch_hash_generic(const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
+                                uint32_t R, uint32_t B, uint32_t M, uint32_t MP, uint64_t* chain,
+                                uint32_t* nblocks, cudaStream_t s);
+
+cudaError_t launch_index_set(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n,
+                             uint32_t ep_begin, uint32_t ep_count, cudaStream_t s);
+cudaError_t launch_index_clear(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n,
+                               uint32_t ep_begin, uint32_t ep_count, cudaStream_t s);
+cudaError_t launch_index_rebuild(IndexView from, IndexView to, IndexCounters* ctr, cudaStream_t s);
+cudaError_t launch_index_contains(IndexView ix, const fi_index_op* q, uint64_t n, uint32_t ep_begin,
+                                  uint32_t ep_count, uint8_t* out, cudaStream_t s);
+
+cudaError_t launch_prepare_endpoints(const EndpointDev* eps, uint32_t E_global, uint32_t ep_begin,
+                                     uint32_t ep_count, ScoreTables st, double* sc, uint32_t* elig,
+                                     ZeroBest* zero, cudaStream_t s);
+
+cudaError_t launch_match_pick(const MatchParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_probe_mask(const MatchParams& p, uint32_t* mask_out, int sm_count, cudaStream_t s);
+cudaError_t launch_merge_picks(const MergeParams& p, cudaStream_t s);
+
+}  // namespace fi

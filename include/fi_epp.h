@@ -1,0 +1,250 @@
+/*
+ * fi_epp.h — C ABI of the B200-native prefix-cache-aware Endpoint Picker.
+ *
+ * This is the drop-in boundary for the ONE hot path this repo implements
+ * (BASELINE.json north_star): per request, hash the prompt into
+ * chained fixed-size block keys, look the chain up against every candidate
+ * endpoint's cached-prefix set, combine the match length with KV-cache /
+ * queue load into a weighted fp64 score, and argmax to choose a pod.
+ *
+ * What it replaces.  FusionInfer (the reference, /root/reference) does not
+ * contain this loop: its router role only *configures and deploys* the
+ * Gateway-API-Inference-Extension EPP image
+ *   pkg/router/epp.go:46        DefaultEPPImage  …/epp:v1.2.1
+ *   pkg/router/epp.go:125-129   args --pool-name --pool-namespace --config-file
+ *   pkg/router/strategy.go:51-68,115-165  the EndpointPickerConfig YAML
+ * and the loop itself runs inside that image (upstream Go packages
+ * pkg/epp/scheduling/framework/plugins/{multi/prefix,scorer,picker}).  There
+ * is no cgo/FFI in the reference (Dockerfile:24 builds CGO_ENABLED=0), so the
+ * entry points below are shaped after the upstream plugin seams a Go EPP
+ * would bind through cgo:
+ *
+ *   upstream seam (Go, module sigs.k8s.io/gateway-api-inference-extension v1.2.1,
+ *   go.mod:16)                                      → entry point here
+ *   ------------------------------------------------------------------------
+ *   config loader for the YAML of strategy.go:52-67 → fi_epp_config_from_yaml
+ *   prefix.Plugin hashPrompt (xxhash chain)         → fi_epp_hash_batch
+ *   prefix indexer.Add / LRU eviction (PreRequest)  → fi_epp_index_add_chain,
+ *                                                     fi_epp_index_apply
+ *   datastore pod metrics refresh (kv, queue, role) → fi_epp_endpoints_update
+ *   SchedulerProfile.Run: filter → scorers → picker → fi_epp_pick_batch
+ *   pd-profile-handler (decode then prefill)        → fi_epp_pick_batch with
+ *                                                     cfg.pd_enabled
+ *
+ * Conventions (cgo-safe): every function returns 0 (FI_OK) or a negative
+ * fi_status; nothing throws across the ABI; the caller owns every buffer and
+ * no pointer is retained after a call returns; one fi_epp handle is internally
+ * serialised by a mutex (concurrency comes from batching); library threads
+ * never call back into the host language.  There is NO CPU fallback: without
+ * a CUDA device fi_epp_create fails with FI_ERR_CUDA.
+ */
+#ifndef FI_EPP_H_
+#define FI_EPP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FI_EPP_ABI_VERSION 1u
+#define FI_EPP_MAX_PROFILES 4u
+#define FI_EPP_MAX_SCORERS 4u
+#define FI_EPP_MAX_BLOCKS 1023u /* counts are kept in 10 bit-planes on the GPU */
+#define FI_NO_ENDPOINT 0xFFFFFFFFu
+#define FI_EPP_UNIQUE_ID_BYTES 128u
+
+typedef enum fi_status {
+  FI_OK = 0,
+  FI_ERR_INVALID = -1,  /* bad argument / config */
+  FI_ERR_CUDA = -2,     /* CUDA runtime error, or no device (there is no CPU fallback) */
+  FI_ERR_NOMEM = -3,
+  FI_ERR_CAPACITY = -4, /* batch, prompt bytes or index larger than configured */
+  FI_ERR_STATE = -5,
+  FI_ERR_COMM = -6,     /* NCCL / peer-memory error */
+  FI_ERR_CONFIG = -7    /* EndpointPickerConfig YAML rejected */
+} fi_status;
+
+/* SURVEY.md Appendix A.3.  UPSTREAM: stop at the first block no endpoint holds,
+ * count per endpoint the blocks it holds before that.  LPM: per-endpoint longest
+ * contiguous prefix.  Identical whenever every endpoint's set is prefix-closed. */
+typedef enum fi_match_mode { FI_MATCH_UPSTREAM = 0, FI_MATCH_LPM = 1 } fi_match_mode;
+
+/* plugin `type:` names of pkg/router/strategy.go:55,74,89,104 */
+typedef enum fi_scorer_kind {
+  FI_SCORER_PREFIX = 1,  /* prefix-cache-scorer          */
+  FI_SCORER_KV_UTIL = 2, /* kv-cache-utilization-scorer  */
+  FI_SCORER_QUEUE = 3,   /* queue-scorer                 */
+  FI_SCORER_LORA = 4     /* lora-affinity-scorer         */
+} fi_scorer_kind;
+
+/* role bits: `fusioninfer.io/component-type` values (api/core/v1alpha1/
+ * inferenceservice_types.go:26-33) that the by-label filters of
+ * strategy.go:135-144 key on. */
+#define FI_ROLE_WORKER 1u
+#define FI_ROLE_PREFILLER 2u
+#define FI_ROLE_DECODER 4u
+
+#define FI_ENDPOINT_ALIVE 1u
+
+typedef struct fi_scorer {
+  uint32_t kind;  /* fi_scorer_kind */
+  int32_t weight; /* `weight:` of the pluginRef (strategy.go:66,157,163); >= 0 */
+} fi_scorer;
+
+typedef struct fi_profile {
+  char name[32];      /* schedulingProfiles[].name */
+  uint32_t role_mask; /* by-label filter: endpoint eligible iff role_mask==0 or (ep.role_mask & role_mask) */
+  uint32_t n_scorers;
+  fi_scorer scorers[FI_EPP_MAX_SCORERS]; /* in profile order: fp64 accumulation order */
+} fi_profile;
+
+typedef struct fi_epp_config {
+  uint32_t struct_size; /* sizeof(fi_epp_config), checked */
+  uint32_t abi_version; /* FI_EPP_ABI_VERSION */
+  int32_t device;       /* CUDA ordinal */
+  uint32_t block_bytes; /* blockSize | hashBlockSize (strategy.go:57,147); 64 = 16 u32 tokens */
+  uint32_t max_blocks;  /* maxPrefixBlocksToMatch (strategy.go:58,148) */
+  uint32_t lru_capacity; /* lruCapacityPerServer (strategy.go:59,149); 0 disables the host LRU */
+  uint32_t num_endpoints;  /* global pool size E */
+  uint32_t endpoint_begin; /* this handle's shard [begin, begin+count) of the pool */
+  uint32_t endpoint_count;
+  uint32_t match_mode; /* fi_match_mode */
+  uint32_t max_batch;  /* largest R accepted by one pick/hash call */
+  uint32_t reserved0;
+  uint64_t max_prompt_bytes; /* largest total prompt bytes per call (device staging) */
+  uint64_t index_slots;      /* key slots of the GPU index, power of two; 0 = 2x endpoint_count*lru_capacity */
+  uint32_t n_profiles;
+  uint32_t pd_enabled;        /* pd-profile-handler present (strategy.go:129-133) */
+  uint32_t pd_decode_profile; /* profile index run first */
+  uint32_t pd_prefill_profile;
+  double pd_threshold;        /* `threshold:` — prefill runs iff (1-hit)*len(prompt) >= threshold */
+  fi_profile profiles[FI_EPP_MAX_PROFILES];
+} fi_epp_config;
+
+/* One row of the pod datastore the scorers read (upstream metrics refresh). */
+typedef struct fi_endpoint_state {
+  uint32_t endpoint;   /* global index in [0, num_endpoints) */
+  uint32_t role_mask;  /* FI_ROLE_* */
+  double kv_util;      /* KVCacheUsagePercent in [0,1] */
+  int32_t queue_depth; /* WaitingQueueSize */
+  uint32_t flags;      /* FI_ENDPOINT_ALIVE */
+} fi_endpoint_state;
+
+typedef enum fi_index_opcode { FI_OP_SET = 1, FI_OP_CLEAR = 2 } fi_index_opcode;
+
+/* One membership change of the logical index {(endpoint, block hash)}. */
+typedef struct fi_index_op {
+  uint64_t hash;
+  uint32_t endpoint; /* global index */
+  uint32_t op;       /* fi_index_opcode */
+} fi_index_op;
+
+/* One routing decision (16 bytes). */
+typedef struct fi_pick {
+  uint32_t endpoint;     /* global index, or FI_NO_ENDPOINT */
+  uint16_t match_blocks; /* prefix blocks matched at the picked endpoint */
+  uint16_t n_blocks;     /* blocks hashed for this request */
+  double score;          /* weighted fp64 total of the picked endpoint */
+} fi_pick;
+
+typedef struct fi_index_stats {
+  uint64_t slots;      /* key slots */
+  uint64_t used;       /* slots holding a key or a tombstone */
+  uint64_t tombstones; /* keys whose row became empty */
+  uint64_t rebuilds;
+  uint64_t ops_applied;
+  uint64_t lru_entries; /* host LRU: sum over endpoints */
+} fi_index_stats;
+
+typedef struct fi_epp_stats {
+  uint64_t kernel_launches; /* kernels of this library launched since create/reset */
+  uint64_t pick_calls;
+  uint64_t requests;
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+  /* per-kernel device time, accumulated only while profiling is on */
+  double ms_hash_blocks, ms_chain_probe, ms_match_pick, ms_index_apply, ms_other;
+  uint64_t n_hash_blocks, n_chain_probe, n_match_pick, n_index_apply, n_other;
+  uint64_t probed_blocks; /* sum over requests of N_probe, profiling only */
+} fi_epp_stats;
+
+typedef struct fi_epp fi_epp;
+
+uint32_t fi_epp_abi_version(void);
+const char* fi_epp_status_string(int status);
+
+/* Fill cfg with the defaults of generatePrefixCacheConfig (strategy.go:51-68)
+ * except block_bytes = 64 (16 uint32 tokens). */
+int fi_epp_config_default(fi_epp_config* cfg);
+
+/* Parse an EndpointPickerConfig YAML document (exactly the schema
+ * strategy.go:52-67,126-164 emits, plus custom passthrough strategy.go:29-31)
+ * into cfg's plugin-derived fields (block_bytes, max_blocks, lru_capacity,
+ * profiles, pd_*).  Deployment fields (device, endpoints, sizes) are untouched.
+ * On FI_ERR_CONFIG a message is written to err (NUL-terminated, truncated). */
+int fi_epp_config_from_yaml(const char* yaml, size_t len, fi_epp_config* cfg, char* err, size_t err_len);
+
+int fi_epp_create(const fi_epp_config* cfg, fi_epp** out);
+void fi_epp_destroy(fi_epp* h);
+const char* fi_epp_last_error(const fi_epp* h);
+
+/* h0 = XXH64(seed 0, model ‖ salt): the chain seed of SURVEY.md Appendix A.1. */
+int fi_epp_model_seed(const void* model, size_t model_len, const void* salt, size_t salt_len, uint64_t* h0);
+
+/* Replace the state of the listed endpoints (every rank receives the whole
+ * pool: queue min/max are global).  Unlisted endpoints keep their state;
+ * endpoints never listed are not alive. */
+int fi_epp_endpoints_update(fi_epp* h, const fi_endpoint_state* states, uint32_t n);
+
+/* Asynchronous, ordered: every op submitted before a pick call is visible to
+ * that pick.  Ops for endpoints outside this handle's shard are ignored. */
+int fi_epp_index_apply(fi_epp* h, const fi_index_op* ops, uint64_t n);
+
+/* Upstream indexer.Add(hashes, pod): touch each hash in `endpoint`'s LRU
+ * (capacity lru_capacity), emit SET for new entries and CLEAR for evicted
+ * ones.  Requires lru_capacity > 0. */
+int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes, uint32_t n);
+
+int fi_epp_index_sync(fi_epp* h); /* block until submitted ops are applied */
+
+/* Diagnostics: out[i] = 1 iff (q[i].endpoint, q[i].hash) is in this handle's GPU index. */
+int fi_epp_index_contains(fi_epp* h, const fi_index_op* q, uint64_t n, uint8_t* out);
+int fi_epp_index_stats(fi_epp* h, fi_index_stats* out);
+
+/* Hash only.  prompts: concatenated prompt bytes; offsets: R+1 byte offsets;
+ * h0: R chain seeds.  chains_out: R*max_blocks hashes (row r holds
+ * nblocks_out[r] valid entries); either output may be NULL. */
+int fi_epp_hash_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
+                      uint32_t R, uint64_t* chains_out, uint32_t* nblocks_out);
+
+/* The hot path, host buffers (pinned memory from fi_epp_pinned_alloc avoids a
+ * staging copy).  out: R*n_profiles picks, out[r*n_profiles + p] for profile p.
+ * With pd_enabled the prefill profile's pick is FI_NO_ENDPOINT when the
+ * threshold test skips it.  chains_out optional (R*max_blocks). */
+int fi_epp_pick_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
+                      uint32_t R, fi_pick* out, uint64_t* chains_out);
+
+/* Same, every buffer already in device memory of cfg.device; work is ordered
+ * after `stream` (a cudaStream_t, may be NULL) and `stream` waits for it. */
+int fi_epp_pick_batch_device(fi_epp* h, const void* d_prompts, const void* d_offsets, const void* d_h0,
+                             uint32_t R, uint64_t total_prompt_bytes, void* d_out, void* d_chains_out,
+                             void* stream);
+
+void* fi_epp_pinned_alloc(size_t bytes);
+void fi_epp_pinned_free(void* p);
+
+/* Multi-GPU (one handle per GPU, endpoint-range shards).  Rank 0 makes an id,
+ * the host distributes it out of band, every rank calls comm_init. */
+int fi_epp_comm_unique_id(uint8_t out[FI_EPP_UNIQUE_ID_BYTES]);
+int fi_epp_comm_init(fi_epp* h, const uint8_t id[FI_EPP_UNIQUE_ID_BYTES], uint32_t rank, uint32_t world);
+
+int fi_epp_set_profiling(fi_epp* h, int on);
+int fi_epp_get_stats(fi_epp* h, fi_epp_stats* out);
+int fi_epp_reset_stats(fi_epp* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FI_EPP_H_ */
