@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py — routing decisions/s of the prefix-cache-aware Endpoint Picker hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--cfg 2|3|4|5] [--mode replicas|sharded] [--scale F]
+
+One "step" = one pass of the hot path (hash → index lookup → weighted score → argmax)
+over one batch of synthetic requests.  Default workload = BASELINE.json's headline
+config 3: 16 384 requests × 1 024 endpoints × 4 096-token prompts.
+
+Prints ONE JSON line (rank 0):
+  value     whole-job decisions/s with inputs already resident in HBM (device-timed,
+            CUDA events on the launching stream, max over ranks)
+  e2e       the same metric through the public C-ABI call with HOST (pinned) buffers:
+            H2D of the prompts and D2H of the picks inside the timed region
+  roofline  dominant kernel: algorithmic bytes per launch ÷ its CUDA-event duration,
+            against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  the CPU oracle (C++ restatement of the upstream algorithm; the
+            reference's Go path is neither in /root/reference nor compilable here,
+            SURVEY.md §0 F1/F2) timed on a bounded sample on the host cores
+
+Multi-GPU (torchrun, one rank per GPU): --mode replicas (default: the 1 024-endpoint
+pool fits one GPU, so every GPU is an independent replica serving its own batches —
+SURVEY.md §8e) or --mode sharded (configs 4/5: endpoint-range shards + the library's
+NCCL exchange of presence masks and (score, endpoint) pairs).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "routing decisions/sec (4K-tok prompts x 1024 endpoints); achieved HBM GB/s"
+ORACLE_LABEL = ("C++ restatement of the upstream EPP v1.2.1 algorithm (oracle/epp_oracle.cpp); the reference's Go "
+                "path is not in /root/reference and cannot be compiled here (SURVEY.md F1/F2); parity unpinned by "
+                "reference tests")
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, read+write)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_config(wl, cfg_id, begin, count, device, max_batch, mode):
+    from fusioninfer_b200 import make_config, synth
+
+    profiles, pd = synth.baseline_profiles(cfg_id)
+    slots = 4096
+    while slots < 2 * count * wl.lru_capacity:
+        slots *= 2
+    return make_config(num_endpoints=wl.E, block_bytes=wl.block_bytes, max_blocks=wl.max_blocks, lru_capacity=0,
+                       max_batch=max_batch, max_prompt_bytes=max_batch * wl.T * 4, index_slots=slots, device=device,
+                       endpoint_begin=begin, endpoint_count=count, profiles=profiles, pd=pd)
+
+
+def algorithmic_bytes(wl, picks_nprobe_total, R, E_local):
+    """A = 4·T + N_probe·(8 + E_local/8) + 16 per decision."""
+    return {"hash_blocks": R * 4 * wl.T, "match_pick": picks_nprobe_total * (8 + E_local / 8.0) + 16.0 * R}
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernels from the committed ncu summary, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def run_reference(args, wl, cfg_id):
+    """--impl reference: the CPU restatement on the box's host cores, bounded sample per step."""
+    from fusioninfer_b200 import synth
+    from oracle.epp_oracle import Oracle
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    cfg = build_config(wl, cfg_id, 0, wl.E, 0, max(wl.R, 1), "replicas")
+    t0 = time.time()
+    o = Oracle(cfg)
+    o.update_endpoints(wl.endpoint_states())
+    o.index_reserve(wl.E * wl.lru_capacity)
+    for ops in wl.index_ops(chunk_endpoints=128):
+        o.index_apply(ops)
+    log(f"oracle index built in {time.time() - t0:.1f}s")
+    S = args.cpu_sample
+    sub = synth.Workload(**{**wl.__dict__, "R": S})
+    tok, offs = sub.prompts(batch=100)
+    # calibrate so that every step is a few seconds at most
+    t0 = time.perf_counter()
+    o.pick_batch(tok[:256], offs[:257], wl.h0, nthreads=ncores)
+    per = (time.perf_counter() - t0) / 256
+    S_eff = int(max(256, min(S, 3.0 / max(per, 1e-9))))
+    tok, offs = tok[:S_eff], offs[: S_eff + 1]
+    for _ in range(args.warmup):
+        o.pick_batch(tok, offs, wl.h0, nthreads=ncores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.pick_batch(tok, offs, wl.h0, nthreads=ncores)
+    dt = time.perf_counter() - t0
+    val = S_eff * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "decisions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(wl, cfg_id, "cpu"),
+        "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": ncores, "kind": "port",
+                         "sample": f"{S_eff} requests of the same workload per step, full {wl.E}-endpoint index "
+                                   f"({wl.E * wl.lru_capacity} entries); {ORACLE_LABEL}"},
+        "e2e": {"value": val, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl, cfg_id, parallelism):
+    return {
+        "workload": f"cfg{cfg_id}: {wl.R} req x {wl.E} endpoints x {wl.T}-token prompts (uint32), "
+                    f"{wl.block_bytes} B blocks, <= {wl.max_blocks} blocks, {wl.lru_capacity} index entries/endpoint",
+        "global_batch": wl.R, "endpoints": wl.E, "prompt_tokens": wl.T, "parallelism": parallelism,
+        "l2": f"inputs larger than L2: {wl.R * wl.T * 4 / 2**20:.0f} MiB of prompts per step, rotating batches; "
+              f"index {wl.E * wl.lru_capacity / 1e6:.1f} M entries",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", type=int, default=3, choices=[2, 3, 4, 5])
+    ap.add_argument("--mode", default=None, choices=["replicas", "sharded"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink R (debug only; the JSON line says so)")
+    ap.add_argument("--batches", type=int, default=2, help="distinct request batches rotated through")
+    ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 10)")
+    args = ap.parse_args()
+
+    from fusioninfer_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"note: WORLD_SIZE={world} but --gpus {args.gpus}; using the launched world size")
+        args.gpus = world
+    cfg_id = args.cfg
+    mode = args.mode or ("sharded" if cfg_id in (4, 5) and world > 1 else "replicas")
+    wl = synth.baseline_workload(cfg_id)
+    if args.scale != 1.0:
+        wl.R = max(64, int(wl.R * args.scale))
+
+    if args.impl == "reference":
+        run_reference(args, wl, cfg_id)
+        return
+
+    import torch
+
+    from fusioninfer_b200 import EndpointPicker, PinnedBuffer
+    from fusioninfer_b200 import dist as fdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the pick path has no CPU fallback (use --impl reference "
+                         "for the CPU arm)")
+    if world > 1:
+        fdist.init_process_group("nccl")
+    torch.cuda.set_device(local)
+
+    # ---- set-up (untimed) ----------------------------------------------------------
+    t_setup = time.time()
+    if mode == "sharded":
+        begin, count = fdist.shard_range(wl.E, rank, world)
+    else:
+        begin, count = 0, wl.E
+    cfg = build_config(wl, cfg_id, begin, count, local, wl.R, mode)
+    picker = EndpointPicker(cfg)
+    if mode == "sharded" and world > 1:
+        uid = EndpointPicker.comm_unique_id() if rank == 0 else None
+        picker.comm_init(fdist.broadcast_bytes(uid, 128), rank, world)
+    picker.update_endpoints(wl.endpoint_states())
+    n_ops = 0
+    for ops in wl.index_ops(ep_lo=begin, ep_hi=begin + count, chunk_endpoints=128):
+        picker.index_apply(ops)
+        n_ops += len(ops)
+    picker.index_sync()
+    ist = picker.index_stats()
+    log(f"rank {rank}: index {n_ops} entries -> {ist.used} keys in {ist.slots} slots "
+        f"({time.time() - t_setup:.1f}s)")
+
+    # request batches: replicas serve different batches per rank, shards all see the same requests
+    nb = max(1, args.batches)
+    d_tok, d_off, host_batches = [], [], []
+    for b in range(nb):
+        bid = b if mode == "sharded" else rank * nb + b
+        tok, offs = wl.prompts(batch=bid)
+        d_tok.append(torch.from_numpy(tok.view(np.int32)).cuda())
+        d_off.append(torch.from_numpy(offs.view(np.int64)).cuda())
+        if b == 0:
+            host_batches.append((tok, offs))
+    R = wl.R
+    P = picker.n_profiles
+    d_h0 = torch.full((R,), int(np.uint64(wl.h0).astype(np.int64)), dtype=torch.int64, device="cuda")
+    d_out = torch.zeros(R * P * 16, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    log(f"rank {rank}: {nb} batches of {R} requests resident in HBM ({time.time() - t_setup:.1f}s)")
+
+    def step(i):
+        b = i % nb
+        picker.pick_batch_device(d_tok[b].data_ptr(), d_off[b].data_ptr(), d_h0.data_ptr(), R, R * wl.T * 4,
+                                 d_out.data_ptr(), 0, stream)
+
+    parity = None
+    # ---- warm-up ------------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, device events on the launching stream -----------------
+    fdist.barrier()
+    torch.cuda.synchronize()
+    picker.reset_stats()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    fdist.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    launches = picker.stats().kernel_launches
+    ms_total = fdist.max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    units = R * (world if mode == "replicas" else 1)
+    value = units / (ms_step * 1e-3)
+
+    # ---- per-kernel durations + N_probe (profiled pass, not part of the number above) -----------
+    picker.reset_stats()
+    picker.set_profiling(True)
+    prof_steps = min(args.steps, 8)
+    for i in range(prof_steps):
+        step(i)
+    torch.cuda.synchronize()
+    st = picker.stats()
+    picker.set_profiling(False)
+    kern = {
+        "hash_blocks": (st.ms_hash_blocks, st.n_hash_blocks),
+        "chain_finalize": (st.ms_chain_probe, st.n_chain_probe),
+        "match_pick": (st.ms_match_pick, st.n_match_pick),
+        "other": (st.ms_other, st.n_other),
+    }
+    avg_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in kern.items()}
+    nprobe_per_step = st.probed_blocks / max(prof_steps, 1)
+    alg = algorithmic_bytes(wl, nprobe_per_step, R, count)
+    peak, peak_src = measured_peak_gbs()
+    dom = max(("hash_blocks", "match_pick"), key=lambda k: avg_ms[k])
+    achieved = alg[dom] / (avg_ms[dom] * 1e-3) / 1e9 if avg_ms[dom] else 0.0
+    traffic = load_traffic()
+    step_alg = alg["hash_blocks"] + alg["match_pick"]
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak if peak else None, "traffic": traffic.get(dom),
+        "peak_source": peak_src + " (burst figure: kernel timed alone with CUDA events)",
+        "algorithmic_bytes_per_launch": alg[dom],
+        "kernel_ms": avg_ms, "n_probe_per_decision": nprobe_per_step / R,
+        "step_algorithmic_gbs": step_alg / (ms_step * 1e-3) / 1e9,
+        "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak,
+        "other_kernels": {k: {"achieved": (alg[k] / (avg_ms[k] * 1e-3) / 1e9 if avg_ms[k] else 0.0),
+                              "traffic": traffic.get(k)} for k in ("hash_blocks", "match_pick") if k != dom},
+    }
+
+    # ---- e2e: public C-ABI call with host (pinned) buffers, H2D + D2H inside ---------------------
+    tok0, offs0 = host_batches[0]
+    pin_tok = PinnedBuffer(tok0.nbytes)
+    pin_off = PinnedBuffer(offs0.nbytes)
+    pin_h0 = PinnedBuffer(8 * R)
+    pin_out = PinnedBuffer(16 * R * P)
+    pin_tok.array(np.uint32)[:] = tok0.reshape(-1)
+    pin_off.array(np.uint64)[:] = offs0
+    pin_h0.array(np.uint64)[:] = np.uint64(wl.h0)
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    picker_e2e = picker
+    for _ in range(2):
+        picker_e2e.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr)
+    fdist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        picker_e2e.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dt = fdist.max_over_ranks(dt)
+    e2e = {"value": units * e2e_steps / dt, "unit": "decisions/s",
+           "h2d_bytes_per_step": int(tok0.nbytes + offs0.nbytes + 8 * R), "d2h_bytes_per_step": int(16 * R * P),
+           "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+           "how": "fi_epp_pick_batch on pinned host buffers: H2D prompts+offsets+seeds, kernels, D2H picks, per step"}
+    e2e_picks = pin_out.array(np.uint8).copy().view(np.dtype(
+        [("endpoint", "<u4"), ("match_blocks", "<u2"), ("n_blocks", "<u2"), ("score", "<f8")])).reshape(R, P)
+
+    # ---- cpu_baseline (rank 0, bounded sample) + parity of the e2e picks on that sample ---------------
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle.epp_oracle import Oracle
+
+        ncores = os.cpu_count() or 1
+        t0 = time.time()
+        o = Oracle(build_config(wl, cfg_id, 0, wl.E, 0, max(wl.R, 1), "replicas"))
+        o.update_endpoints(wl.endpoint_states())
+        S = min(args.cpu_sample, R)
+        # the FULL index, not just the sampled requests' hashes: a tiny index would make the CPU
+        # lookups unrealistically cache-friendly
+        o.index_reserve(wl.E * wl.lru_capacity)
+        for ops in wl.index_ops(chunk_endpoints=128):
+            o.index_apply(ops)
+        log(f"oracle index built in {time.time() - t0:.1f}s")
+        t1 = time.perf_counter()
+        want = o.pick_batch(tok0[:S], offs0[: S + 1], wl.h0, nthreads=ncores)
+        tn = time.perf_counter() - t1
+        same = e2e_picks[:S].tobytes() == want.tobytes()
+        parity = {"checked_requests": S, "bit_exact": bool(same)}
+        if not same:
+            log("PARITY FAILURE on the cpu_baseline sample")
+        # single-thread figure on a smaller slice
+        S1 = min(S, 512)
+        t0 = time.perf_counter()
+        o.pick_batch(tok0[:S1], offs0[: S1 + 1], wl.h0, nthreads=1)
+        t1s = time.perf_counter() - t0
+        cpu = {"value": S / tn, "unit": "decisions/s", "cores": ncores, "kind": "port",
+               "single_thread_value": S1 / t1s,
+               "sample": f"first {S} requests of batch 0 (full {wl.E * wl.lru_capacity}-entry index), {ncores} threads "
+                         f"sharded by request; single-thread figure on the first {S1}; {ORACLE_LABEL}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(wl, cfg_id, f"{mode}{world}"),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": int(launches),
+            "parity": parity,
+        }
+        if args.scale != 1.0:
+            line["config"]["workload"] += f" [DEBUG scale={args.scale}: NOT the headline config]"
+        print(json.dumps(line), flush=True)
+    picker.close()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

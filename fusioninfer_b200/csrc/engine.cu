@@ -300,9 +300,13 @@ int check_counters(fi_epp* h) {
   return FI_OK;
 }
 
-// launch the staged SET then CLEAR ops of the current group on the index stream
+// launch the staged SET then CLEAR ops of the current group on the index stream.
+// Asynchronous: the only waits are for the *previous* group's counters (rebuild /
+// overflow decisions lag one group) and for the staging buffer being reused.
 int flush_ops(fi_epp* h) {
   if (h->n_sets == 0 && h->n_clears == 0) return FI_OK;
+  int rc = check_counters(h);  // may rebuild (swaps tables) — only ever between groups
+  if (rc != FI_OK) return rc;
   const int b = h->cur_buf;
   if (h->n_sets) {
     FI_CUDA(cudaMemcpyAsync(h->d_sets[b], h->h_sets[b], h->n_sets * sizeof(fi_index_op), cudaMemcpyHostToDevice, h->s_index));
@@ -327,8 +331,7 @@ int flush_ops(fi_epp* h) {
   h->cur_buf ^= 1;
   // the buffer we are about to fill must have been consumed
   FI_CUDA(cudaEventSynchronize(h->ev_buf[h->cur_buf]));
-  // a rebuild swaps tables; do it between groups only
-  return check_counters(h);
+  return FI_OK;
 }
 
 // stage one op (already filtered to this shard).  Within a launch group SETs run

@@ -67,7 +67,10 @@ def small_workload(**kw):
 
 def config_for(wl, profiles=None, pd=None, match_mode=abi.FI_MATCH_UPSTREAM, **kw):
     profiles = profiles or [{"name": "default", "scorers": [(P, 100)]}]
+    slots = 4096
+    while slots < 4 * wl.E * max(wl.lru_capacity, wl.groups_per_endpoint * wl.n_blocks):
+        slots *= 2
     args = dict(num_endpoints=wl.E, block_bytes=wl.block_bytes, max_blocks=wl.max_blocks, lru_capacity=0,
-                max_batch=max(wl.R, 1), profiles=profiles, pd=pd, match_mode=match_mode)
+                max_batch=max(wl.R, 1), profiles=profiles, pd=pd, match_mode=match_mode, index_slots=slots)
     args.update(kw)
     return make_config(**args)

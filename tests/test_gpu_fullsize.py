@@ -1,0 +1,82 @@
+"""GPU (-m gpu): BASELINE.json's full sizes, checked through size-independent properties
+plus a sampled bit-exact comparison with the oracle.
+
+Config 2 (4 096 × 256 × 2K tokens) and config 3 (16 384 × 1 024 × 4K tokens, 32 M index
+entries).  The oracle sees only the index entries whose hashes occur in the sampled
+requests' chains — for those requests that is exactly equivalent to the full index.
+"""
+import numpy as np
+import pytest
+
+from fusioninfer_b200 import EndpointPicker, synth
+from fusioninfer_b200 import _abi as abi
+from oracle import epp_oracle as eo
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(wl, cfg_id, **kw):
+    profiles, pd = synth.baseline_profiles(cfg_id)
+    slots = 4096
+    while slots < 2 * wl.E * wl.lru_capacity:
+        slots *= 2
+    return H.config_for(wl, profiles=profiles, pd=pd, index_slots=slots, max_prompt_bytes=wl.R * wl.T * 4, **kw)
+
+
+@pytest.mark.parametrize("cfg_id", [2, 3])
+def test_full_size_properties_and_sampled_parity(cfg_id):
+    wl = synth.baseline_workload(cfg_id)
+    cfg = _cfg(wl, cfg_id)
+    gpu = EndpointPicker(cfg)
+    gpu.update_endpoints(wl.endpoint_states())
+    tok, offs = wl.prompts()
+    all_ops = []
+    for ops in wl.index_ops(chunk_endpoints=128):
+        gpu.index_apply(ops)
+        all_ops.append(ops)
+    picks, chains = gpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+    st = gpu.index_stats()
+    assert st.used <= wl.E * wl.lru_capacity and st.used > 0.9 * wl.E * (wl.lru_capacity - 8 * wl.n_blocks)
+
+    # 1. idempotence / batch independence: two halves hashed and picked separately give the same answers
+    half = wl.R // 2
+    p2 = gpu.pick_batch(tok[half:], offs[: wl.R - half + 1], wl.h0)
+    assert H.picks_equal(p2, picks[half:])
+    # 2. chain prefix property: same group ⇒ identical chain up to the common shared length; diverges right after
+    groups, shared = wl.request_params()
+    order = np.argsort(groups, kind="stable")
+    checked = 0
+    for a, b in zip(order[:-1], order[1:]):
+        if groups[a] == groups[b] and shared[a] and shared[b]:
+            k = min(shared[a], shared[b]) // wl.block_tokens
+            assert np.array_equal(chains[a, :k], chains[b, :k])
+            assert chains[a, k] != chains[b, k]
+            checked += 1
+            if checked == 200:
+                break
+    assert checked > 50
+    # 3. a match never exceeds the request's shared prefix, fully unique requests match nothing
+    mb = picks[:, 0]["match_blocks"].astype(np.int64)
+    assert (mb <= shared // wl.block_tokens).all()
+    assert (picks[:, 0]["n_blocks"] == wl.n_blocks).all()
+    assert (mb > 0).mean() > 0.5
+    # 4. the picked endpoint really holds every matched block (membership round trip through the index)
+    sample = np.flatnonzero(mb > 0)[:64]
+    q = []
+    for r in sample:
+        for i in range(mb[r]):
+            q.append((int(chains[r, i]), int(picks[r, 0]["endpoint"]), 0))
+    assert gpu.index_contains(H.ops_array(q)).all()
+    # 5. sampled bit-exact parity with the oracle
+    S = 768
+    idx = np.linspace(0, wl.R - 1, S).astype(np.int64)
+    needed = np.unique(chains[idx])
+    cpu = eo.Oracle(cfg)
+    cpu.update_endpoints(wl.endpoint_states())
+    for ops in all_ops:
+        cpu.index_apply(ops[np.isin(ops["hash"], needed)])
+    sub_offs = np.arange(S + 1, dtype=np.uint64) * np.uint64(wl.T * 4)
+    want = cpu.pick_batch(np.ascontiguousarray(tok[idx]), sub_offs, wl.h0)
+    assert H.picks_equal(picks[idx], want), H.describe_diff(picks[idx], want)
+    gpu.close()

@@ -1,0 +1,346 @@
+"""GPU (-m gpu): parity of the sm_100a path against the CPU oracle, through the C ABI.
+
+Bit-exact for every integer/byte/index output (block hashes, index membership,
+endpoint, match length) and for the fp64 score (compared as raw 64-bit patterns —
+tolerance 0: both sides do the same IEEE-754 round-to-nearest mul/add/div sequence).
+"""
+import numpy as np
+import pytest
+
+from fusioninfer_b200 import EndpointPicker, make_config, synth
+from fusioninfer_b200 import _abi as abi
+from oracle import epp_oracle as eo
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+P, K, Q = H.P, H.K, H.Q
+
+
+def _pair(cfg):
+    return EndpointPicker(cfg), eo.Oracle(cfg)
+
+
+def _load(wl, gpu, cpu, states=None):
+    st = wl.endpoint_states() if states is None else states
+    gpu.update_endpoints(st)
+    cpu.update_endpoints(st)
+    for ops in wl.index_ops():
+        gpu.index_apply(ops)
+        cpu.index_apply(ops)
+
+
+# ---------------------------------------------------------------------------------------
+# block hashing
+# ---------------------------------------------------------------------------------------
+def test_hash_golden_vectors():
+    g = H.golden()
+    h0 = int(g["h0"], 16)
+    for case in g["chains"]:
+        cfg = make_config(num_endpoints=1, block_bytes=case["block_bytes"], max_blocks=case["max_blocks"], max_batch=4,
+                          max_prompt_bytes=1 << 16)
+        with EndpointPicker(cfg) as gpu:
+            data, offs = H.pack_prompts([bytes.fromhex(case["hex"])])
+            chains, nb = gpu.hash_batch(data, offs, h0)
+            want = [int(x, 16) for x in case["chain"]]
+            assert nb[0] == len(want)
+            assert list(chains[0, : nb[0]]) == want, case["block_bytes"]
+            assert not chains[0, nb[0]:].any()
+
+
+@pytest.mark.parametrize("B", [64, 32, 128, 96, 5, 16, 7, 40])
+def test_hash_parity_ragged_unaligned(B):
+    rng = np.random.default_rng(B)
+    M = 24
+    lens = [0, 1, B - 1, B, B + 1, 2 * B, M * B, M * B + 3, (M + 5) * B, 3 * B + B // 2]
+    lens += [int(x) for x in rng.integers(0, (M + 3) * B, size=54)]
+    blobs = [rng.integers(0, 256, size=n, dtype=np.uint8).tobytes() for n in lens]  # offsets end up at every alignment
+    data, offs = H.pack_prompts(blobs)
+    cfg = make_config(num_endpoints=1, block_bytes=B, max_blocks=M, max_batch=len(blobs), max_prompt_bytes=len(data))
+    gpu, cpu = _pair(cfg)
+    h0 = rng.integers(0, 2**63, size=len(blobs), dtype=np.uint64)
+    gc, gn = gpu.hash_batch(data, offs, h0)
+    wc, wn = cpu.hash_batch(data, offs, h0)
+    assert np.array_equal(gn, wn)
+    assert np.array_equal(gc, wc)
+    gpu.close()
+
+
+def test_hash_token_prompts_aligned_fast_path():
+    wl = H.small_workload(R=300, T=2048, max_blocks=128)
+    cfg = H.config_for(wl)
+    gpu, cpu = _pair(cfg)
+    tok, offs = wl.prompts()
+    gc, gn = gpu.hash_batch(tok, offs, wl.h0)
+    wc, wn = cpu.hash_batch(tok, offs, wl.h0)
+    assert np.array_equal(gn, wn) and np.array_equal(gc, wc)
+    # prefix property: requests of the same group share the chain up to their shared length
+    groups, shared = wl.request_params()
+    i, j = 0, None
+    for j in range(1, wl.R):
+        if groups[j] == groups[0] and shared[j] and shared[0]:
+            k = min(shared[0], shared[j]) // wl.block_tokens
+            assert np.array_equal(gc[0, :k], gc[j, :k])
+            break
+    gpu.close()
+
+
+# ---------------------------------------------------------------------------------------
+# index
+# ---------------------------------------------------------------------------------------
+def test_index_set_clear_sequences_match_oracle():
+    rng = np.random.default_rng(11)
+    E = 70
+    cfg = make_config(num_endpoints=E, max_batch=8, index_slots=4096)
+    gpu, cpu = _pair(cfg)
+    universe = np.concatenate([rng.integers(1, 2**63, size=298, dtype=np.uint64),
+                               np.array([0, 0xFFFFFFFFFFFFFFFF], dtype=np.uint64)])  # incl. the sentinel values
+    for step in range(12):
+        n = 700
+        ops = np.zeros(n, dtype=H.OP_DTYPE)
+        ops["hash"] = universe[rng.integers(0, len(universe), size=n)]
+        ops["endpoint"] = rng.integers(0, E, size=n)
+        ops["op"] = rng.choice([abi.FI_OP_SET, abi.FI_OP_SET, abi.FI_OP_CLEAR], size=n)  # conflicts within a call
+        gpu.index_apply(ops)
+        cpu.index_apply(ops)
+        q = np.zeros(len(universe) * E, dtype=H.OP_DTYPE)
+        q["hash"] = np.repeat(universe, E)
+        q["endpoint"] = np.tile(np.arange(E, dtype=np.uint32), len(universe))
+        got = gpu.index_contains(q)
+        want = np.array([cpu.index_contains(int(e), int(h)) for h, e in zip(q["hash"], q["endpoint"])], dtype=np.uint8)
+        assert np.array_equal(got, want), f"step {step}: {int((got != want).sum())} memberships differ"
+    gpu.close()
+
+
+def test_index_tombstones_trigger_rebuild_and_stay_exact():
+    E = 16
+    cfg = make_config(num_endpoints=E, max_batch=8, index_slots=256)
+    gpu, cpu = _pair(cfg)
+    live = []
+    nxt = 1
+    for round_ in range(40):
+        # retire the oldest 20 hashes, add 20 new ones: keys only ever become tombstones
+        ops = []
+        for h in live[:20]:
+            ops.append((h, 3, abi.FI_OP_CLEAR))
+        live = live[20:]
+        for _ in range(20):
+            ops.append((nxt, 3, abi.FI_OP_SET))
+            live.append(nxt)
+            nxt += 1
+        arr = H.ops_array(ops)
+        gpu.index_apply(arr)
+        cpu.index_apply(arr)
+    st = gpu.index_stats()
+    assert st.rebuilds >= 1, "800 retired keys in a 256-slot table must have forced a rebuild"
+    assert st.used - st.tombstones == len(live)
+    q = H.ops_array([(h, 3, 0) for h in range(1, nxt)])
+    got = gpu.index_contains(q)
+    want = np.array([cpu.index_contains(3, h) for h in range(1, nxt)], dtype=np.uint8)
+    assert np.array_equal(got, want)
+    gpu.close()
+
+
+def test_index_overflow_is_reported_not_silent():
+    cfg = make_config(num_endpoints=4, max_batch=8, index_slots=64)
+    gpu = EndpointPicker(cfg)
+    ops = H.ops_array([(h, 1, abi.FI_OP_SET) for h in range(1, 200)])
+    with pytest.raises(Exception) as ei:
+        gpu.index_apply(ops)
+        gpu.index_sync()
+        gpu.index_apply(ops[:1])
+    assert "index" in str(ei.value)
+    gpu.close()
+
+
+# ---------------------------------------------------------------------------------------
+# match + score + pick
+# ---------------------------------------------------------------------------------------
+WEIGHTED = [{"name": "default", "scorers": [(P, 100), (K, 13), (Q, 7)]}]
+
+
+@pytest.mark.parametrize("E", [1, 8, 33, 64, 100, 256, 500, 1024, 2048, 4096])
+@pytest.mark.parametrize("mode", [abi.FI_MATCH_UPSTREAM, abi.FI_MATCH_LPM])
+@pytest.mark.parametrize("holes", [False, True])
+def test_pick_parity_over_pool_sizes(E, mode, holes):
+    wl = H.small_workload(E=E, R=160, holes=holes, lru_capacity=300)
+    cfg = H.config_for(wl, profiles=WEIGHTED, match_mode=mode)
+    gpu, cpu = _pair(cfg)
+    _load(wl, gpu, cpu)
+    tok, offs = wl.prompts()
+    got, gch = gpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+    want, wch = cpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+    assert np.array_equal(gch, wch)
+    assert H.picks_equal(got, want), H.describe_diff(got, want)
+    if E >= 8:
+        assert (want["match_blocks"] > 0).mean() > 0.3  # the case really exercises prefix hits
+    gpu.close()
+
+
+@pytest.mark.parametrize("scorers", [
+    [(P, 100)], [(K, 100)], [(Q, 100)], [(K, 3), (P, 50), (Q, 11)], [(Q, 1), (K, 1), (P, 1)], [(P, 0), (K, 5)],
+    [(P, 100), (P, 1), (K, 2), (Q, 3)],
+])
+def test_pick_parity_over_scorer_mixes(scorers):
+    wl = H.small_workload(E=200, R=200)
+    cfg = H.config_for(wl, profiles=[{"name": "default", "scorers": scorers}])
+    gpu, cpu = _pair(cfg)
+    _load(wl, gpu, cpu)
+    tok, offs = wl.prompts()
+    got = gpu.pick_batch(tok, offs, wl.h0)
+    want = cpu.pick_batch(tok, offs, wl.h0)
+    assert H.picks_equal(got, want), H.describe_diff(got, want)
+    gpu.close()
+
+
+def test_pick_ties_dead_endpoints_and_empty_pool():
+    wl = H.small_workload(E=96, R=64)
+    cfg = H.config_for(wl, profiles=[{"name": "default", "scorers": [(P, 100), (Q, 5)]}])
+    tok, offs = wl.prompts()
+    for alive_fn in (lambda e: e % 3 != 0, lambda e: e >= 64, lambda e: e < 0):
+        gpu, cpu = _pair(cfg)
+        st = wl.endpoint_states()
+        st["flags"] = np.where(alive_fn(np.arange(wl.E)), abi.FI_ENDPOINT_ALIVE, 0)
+        st["queue_depth"] = 4  # all equal → queue score 1.0 everywhere → mass ties → lowest index
+        _load(wl, gpu, cpu, states=st)
+        got = gpu.pick_batch(tok, offs, wl.h0)
+        want = cpu.pick_batch(tok, offs, wl.h0)
+        assert H.picks_equal(got, want), H.describe_diff(got, want)
+        gpu.close()
+    assert (want["endpoint"] == abi.FI_NO_ENDPOINT).all()
+
+
+def test_pick_pd_profiles_and_threshold():
+    wl = H.small_workload(E=128, R=200, pd=True)
+    profiles, _ = synth.baseline_profiles(5)
+    tok, offs = wl.prompts()
+    for thr in (0.0, 600.0, 1500.0, 1e9):
+        cfg = H.config_for(wl, profiles=profiles, pd={"decode": 1, "prefill": 0, "threshold": thr})
+        gpu, cpu = _pair(cfg)
+        _load(wl, gpu, cpu)
+        got = gpu.pick_batch(tok, offs, wl.h0)
+        want = cpu.pick_batch(tok, offs, wl.h0)
+        assert H.picks_equal(got, want), H.describe_diff(got, want)
+        gpu.close()
+        skipped = (want[:, 0]["endpoint"] == abi.FI_NO_ENDPOINT).mean()
+        if thr == 0.0:
+            assert skipped == 0.0
+            assert (want[:, 0]["endpoint"] < 64).all() and (want[:, 1]["endpoint"] >= 64).all()  # role filters
+        if thr == 1e9:
+            assert skipped == 1.0
+
+
+def test_pick_ragged_short_and_truncated_prompts():
+    wl = H.small_workload(E=64, R=64, T=1024, max_blocks=16)  # 64 blocks of text, capped at 16
+    cfg = H.config_for(wl, profiles=WEIGHTED, max_prompt_bytes=1 << 20)
+    gpu, cpu = _pair(cfg)
+    _load(wl, gpu, cpu)
+    tok, _ = wl.prompts()
+    rng = np.random.default_rng(1)
+    blobs = []
+    for r in range(wl.R):
+        n_tok = int(rng.choice([0, 3, 15, 16, 17, 100, 255, 256, 257, 1024]))
+        blobs.append(tok[r, :n_tok].tobytes() + bytes(int(rng.integers(0, 4))))  # + ragged tail bytes
+    data, offs = H.pack_prompts(blobs)
+    got, gch = gpu.pick_batch(data, offs, wl.h0, want_chains=True)
+    want, wch = cpu.pick_batch(data, offs, wl.h0, want_chains=True)
+    assert np.array_equal(gch, wch)
+    assert H.picks_equal(got, want), H.describe_diff(got, want)
+    gpu.close()
+
+
+def test_pick_reference_block_size_5_ascii():
+    """The reference's own config: blockSize 5 over prompt text (strategy.go:57)."""
+    rng = np.random.default_rng(9)
+    E, R = 8, 64
+    cfg = make_config(num_endpoints=E, block_bytes=5, max_blocks=256, max_batch=R, max_prompt_bytes=1 << 20)
+    gpu, cpu = _pair(cfg)
+    st = H.states_array(E)
+    gpu.update_endpoints(st)
+    cpu.update_endpoints(st)
+    alphabet = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz ,.", dtype=np.uint8)
+    system = [alphabet[rng.integers(0, len(alphabet), size=400)].tobytes() for _ in range(4)]
+    blobs = [system[int(rng.integers(0, 4))][: int(rng.integers(50, 400))] + alphabet[rng.integers(0, len(alphabet), size=int(rng.integers(0, 1500)))].tobytes()
+             for _ in range(R)]
+    data, offs = H.pack_prompts(blobs)
+    h0 = synth.xxh64_py(b"meta-llama/Llama-3-8B")
+    # warm the index the way upstream does: route, then Add(chain, picked endpoint)
+    chains, nb = cpu.hash_batch(data, offs, h0)
+    for r in range(0, R, 2):
+        e = int(rng.integers(0, E))
+        ops = H.ops_array([(int(h), e, abi.FI_OP_SET) for h in chains[r, : nb[r]]])
+        gpu.index_apply(ops)
+        cpu.index_apply(ops)
+    got, gch = gpu.pick_batch(data, offs, h0, want_chains=True)
+    want, wch = cpu.pick_batch(data, offs, h0, want_chains=True)
+    assert np.array_equal(gch, wch)
+    assert H.picks_equal(got, want), H.describe_diff(got, want)
+    assert (want["match_blocks"] > 0).sum() >= R // 2
+    gpu.close()
+
+
+def test_lru_add_chain_path_matches_oracle():
+    """Post-pick index maintenance (upstream PreRequest → indexer.Add) through the host LRU."""
+    wl = H.small_workload(E=24, R=96, lru_capacity=0)
+    cfg = H.config_for(wl, profiles=WEIGHTED, lru_capacity=40)  # tiny: constant eviction
+    gpu, cpu = _pair(cfg)
+    st = wl.endpoint_states()
+    gpu.update_endpoints(st)
+    cpu.update_endpoints(st)
+    for batch in range(6):
+        tok, offs = wl.prompts(batch=batch)
+        got, gch = gpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+        want, wch = cpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+        assert np.array_equal(gch, wch)
+        assert H.picks_equal(got, want), f"batch {batch}\n" + H.describe_diff(got, want)
+        for r in range(wl.R):
+            e = int(want[r, 0]["endpoint"])
+            n = int(want[r, 0]["n_blocks"])
+            gpu.index_add_chain(e, gch[r, :n])
+            cpu.index_add_chain(e, wch[r, :n])
+    assert (want["match_blocks"] > 0).any()
+    stx = gpu.index_stats()
+    assert stx.lru_entries <= 24 * 40
+    gpu.close()
+
+
+def test_device_resident_path_equals_host_path():
+    import torch
+
+    wl = H.small_workload(E=256, R=512, T=1024, max_blocks=64)
+    cfg = H.config_for(wl, profiles=WEIGHTED)
+    gpu, cpu = _pair(cfg)
+    _load(wl, gpu, cpu)
+    tok, offs = wl.prompts()
+    want = cpu.pick_batch(tok, offs, wl.h0)
+    host = gpu.pick_batch(tok, offs, wl.h0)
+    d_tok = torch.from_numpy(tok.view(np.int32)).cuda()
+    d_off = torch.from_numpy(offs.view(np.int64)).cuda()
+    d_h0 = torch.full((wl.R,), np.uint64(wl.h0).astype(np.int64), dtype=torch.int64, device="cuda")
+    d_out = torch.zeros(wl.R * 16, dtype=torch.uint8, device="cuda")
+    d_ch = torch.zeros(wl.R * wl.max_blocks, dtype=torch.int64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):  # idempotent
+        gpu.pick_batch_device(d_tok.data_ptr(), d_off.data_ptr(), d_h0.data_ptr(), wl.R, tok.nbytes, d_out.data_ptr(),
+                              d_ch.data_ptr(), s)
+    torch.cuda.synchronize()
+    dev = d_out.cpu().numpy().view(H.PICK_DTYPE).reshape(wl.R, 1)
+    assert H.picks_equal(dev, host) and H.picks_equal(dev, want)
+    gchain = d_ch.cpu().numpy().view(np.uint64).reshape(wl.R, wl.max_blocks)
+    wchain, _ = cpu.hash_batch(tok, offs, wl.h0)
+    assert np.array_equal(gchain, wchain)
+    assert gpu.stats().kernel_launches > 0
+    gpu.close()
+
+
+def test_batch_limits_are_enforced():
+    cfg = make_config(num_endpoints=4, max_batch=4, max_prompt_bytes=1024)
+    gpu = EndpointPicker(cfg)
+    data, offs = H.pack_prompts([bytes(64)] * 5)
+    with pytest.raises(Exception) as ei:
+        gpu.pick_batch(data, offs, 1)
+    assert "max_batch" in str(ei.value)
+    data, offs = H.pack_prompts([bytes(2048)])
+    with pytest.raises(Exception) as ei:
+        gpu.pick_batch(data, offs, 1)
+    assert "max_prompt_bytes" in str(ei.value)
+    gpu.close()

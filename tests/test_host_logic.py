@@ -1,0 +1,305 @@
+"""CPU: the product's host-side logic and the arithmetic its kernels share with the host.
+
+libfi_hostcheck.so is a host build of fusioninfer_b200/csrc/{xxh64.cuh,bitslice.cuh,lru.h}
+— the same headers the sm_100a kernels compile — so the split pre-state/chain-step
+hashing, the bit-plane counters and the LRU are checked here without a GPU.
+"""
+import ctypes as C
+import os
+import random
+
+import numpy as np
+import pytest
+
+from fusioninfer_b200 import _abi as abi
+from fusioninfer_b200 import config_from_yaml, default_config, model_seed
+from fusioninfer_b200.picker import FiEppError
+from oracle import epp_oracle as eo
+from tests import helpers as H
+
+LIB = os.path.join(abi.LIB_DIR, "libfi_hostcheck.so")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    lib = C.CDLL(LIB)
+    lib.fihc_xxh64.restype = C.c_uint64
+    lib.fihc_xxh64.argtypes = [C.c_char_p, C.c_uint32]
+    for f in (lib.fihc_chain_generic, lib.fihc_chain_split):
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.fihc_bitcount.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.fihc_bitcount_merge.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.fihc_lru_new.restype = C.c_void_p
+    lib.fihc_lru_new.argtypes = [C.c_uint32]
+    lib.fihc_lru_free.argtypes = [C.c_void_p]
+    lib.fihc_lru_size.restype = C.c_uint32
+    lib.fihc_lru_size.argtypes = [C.c_void_p]
+    lib.fihc_lru_contains.argtypes = [C.c_void_p, C.c_uint64]
+    lib.fihc_lru_touch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def test_kernel_header_xxh64_matches_golden(hc):
+    g = H.golden()
+    for case in g["xxh64"]:
+        data = bytes.fromhex(case["hex"])
+        assert f"{hc.fihc_xxh64(data, len(data)):016x}" == case["digest"]
+    assert model_seed(g["h0_model"].encode()) == int(g["h0"], 16)
+    assert model_seed(b"synthetic/", b"model") == int(g["h0"], 16)  # h0 = XXH64(model ‖ salt)
+
+
+def test_kernel_header_chains_match_golden(hc):
+    g = H.golden()
+    h0 = int(g["h0"], 16)
+    for case in g["chains"]:
+        data = bytes.fromhex(case["hex"])
+        B, M = case["block_bytes"], case["max_blocks"]
+        want = [int(x, 16) for x in case["chain"]]
+        out = np.zeros(M, dtype=np.uint64)
+        n = hc.fihc_chain_generic(data, len(data), h0, B, M, out.ctypes.data)
+        assert n == len(want) and list(out[:n]) == want
+        if B % 32 == 0:  # the GPU fast path: stripes + merge hoisted out of the serial chain
+            out2 = np.zeros(M, dtype=np.uint64)
+            n2 = hc.fihc_chain_split(data, len(data), h0, B, M, out2.ctypes.data)
+            assert n2 == len(want) and list(out2[:n2]) == want
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 8, 16])
+def test_bitplane_counter_counts_exactly(hc, K):
+    rng = np.random.default_rng(K)
+    for n in (0, 1, 5, 16, 33, 256, 1023):
+        words = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        if n:
+            words[rng.integers(0, n, size=n // 3)] = 0xFFFFFFFF  # push some counters towards the maximum
+        counts = np.zeros(32, dtype=np.uint32)
+        hc.fihc_bitcount(words.ctypes.data, n, K, counts.ctypes.data)
+        want = [int(((words >> b) & 1).sum()) for b in range(32)]
+        assert list(counts) == want
+
+
+def test_bitplane_counter_merge(hc):
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 2**32, size=300, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 2**32, size=500, dtype=np.uint64).astype(np.uint32)
+    counts = np.zeros(32, dtype=np.uint32)
+    nz = C.c_uint32(0)
+    hc.fihc_bitcount_merge(a.ctypes.data, len(a), b.ctypes.data, len(b), counts.ctypes.data, C.byref(nz))
+    want = [int(((a >> i) & 1).sum() + ((b >> i) & 1).sum()) for i in range(32)]
+    assert list(counts) == want
+    assert nz.value == sum((1 << i) for i in range(32) if want[i])
+
+
+def _py_lru_trace(cap, keys):
+    from collections import OrderedDict
+
+    od = OrderedDict()
+    out = []
+    for k in keys:
+        if k in od:
+            od.move_to_end(k)
+            out.append((0, 0, 0))
+            continue
+        ev = (0, 0)
+        if len(od) == cap:
+            old, _ = od.popitem(last=False)
+            ev = (1, old)
+        od[k] = None
+        out.append((1, ev[0], ev[1]))
+    return out, list(od.keys())
+
+
+@pytest.mark.parametrize("cap", [1, 2, 7, 64, 1000])
+def test_host_lru_matches_model(hc, cap):
+    rng = random.Random(cap)
+    keys = [rng.randrange(1, cap * 3 + 2) for _ in range(cap * 20 + 50)]
+    want, final = _py_lru_trace(cap, keys)
+    l = hc.fihc_lru_new(cap)
+    ka = np.array(keys, dtype=np.uint64)
+    ins = np.zeros(len(keys), dtype=np.uint8)
+    did = np.zeros(len(keys), dtype=np.uint8)
+    ev = np.zeros(len(keys), dtype=np.uint64)
+    hc.fihc_lru_touch(l, ka.ctypes.data, len(keys), ins.ctypes.data, did.ctypes.data, ev.ctypes.data)
+    got = [(int(i), int(d), int(e) if d else 0) for i, d, e in zip(ins, did, ev)]
+    assert got == want
+    assert hc.fihc_lru_size(l) == len(final)
+    for k in set(keys):
+        assert bool(hc.fihc_lru_contains(l, k)) == (k in final)
+    hc.fihc_lru_free(l)
+
+
+def test_host_lru_agrees_with_oracle_lru(hc):
+    cap = 16
+    cfg = H.make_config(num_endpoints=1, max_batch=1, lru_capacity=cap)
+    o = eo.Oracle(cfg)
+    l = hc.fihc_lru_new(cap)
+    rng = random.Random(5)
+    live = set()
+    for _ in range(60):
+        chain = np.array([rng.randrange(1, 60) for _ in range(rng.randrange(1, 9))], dtype=np.uint64)
+        o.index_add_chain(0, chain)
+        ins = np.zeros(len(chain), dtype=np.uint8)
+        did = np.zeros(len(chain), dtype=np.uint8)
+        ev = np.zeros(len(chain), dtype=np.uint64)
+        hc.fihc_lru_touch(l, chain.ctypes.data, len(chain), ins.ctypes.data, did.ctypes.data, ev.ctypes.data)
+        for k, i, d, e in zip(chain, ins, did, ev):
+            if d:
+                live.discard(int(e))
+            if i:
+                live.add(int(k))
+        for k in range(1, 60):
+            assert o.index_contains(0, k) == (k in live)
+    hc.fihc_lru_free(l)
+
+
+# ---- EndpointPickerConfig loader -----------------------------------------------------
+# The documents FusionInfer's router role generates
+# (/root/reference/pkg/router/strategy.go:51-68, 70-83, 85-98, 115-165): the drop-in must
+# accept them unchanged.  Reproduced here as test inputs (they are the interface contract).
+PREFIX_YAML = """apiVersion: inference.networking.x-k8s.io/v1alpha1
+kind: EndpointPickerConfig
+plugins:
+- type: prefix-cache-scorer
+  parameters:
+    blockSize: 5
+    maxPrefixBlocksToMatch: 256
+    lruCapacityPerServer: 31250
+- type: max-score-picker
+schedulingProfiles:
+- name: default
+  plugins:
+  - pluginRef: max-score-picker
+  - pluginRef: prefix-cache-scorer
+    weight: 100
+"""
+
+def _single(kind):
+    return f"""apiVersion: inference.networking.x-k8s.io/v1alpha1
+kind: EndpointPickerConfig
+plugins:
+- type: {kind}
+- type: max-score-picker
+schedulingProfiles:
+- name: default
+  plugins:
+  - pluginRef: max-score-picker
+  - pluginRef: {kind}
+    weight: 100
+"""
+
+PD_YAML = """apiVersion: inference.networking.x-k8s.io/v1alpha1
+kind: EndpointPickerConfig
+plugins:
+- type: pd-profile-handler
+  parameters:
+    threshold: 0
+    hashBlockSize: 5
+    primaryPort: 8000
+- type: prefill-header-handler
+- type: by-label
+  name: prefill-pods
+  parameters:
+    label: "fusioninfer.io/component-type"
+    validValues: ["prefiller"]
+- type: by-label
+  name: decode-pods
+  parameters:
+    label: "fusioninfer.io/component-type"
+    validValues: ["decoder"]
+- type: prefix-cache-scorer
+  parameters:
+    hashBlockSize: 5
+    maxPrefixBlocksToMatch: 256
+    lruCapacityPerServer: 31250
+- type: max-score-picker
+schedulingProfiles:
+- name: prefill
+  plugins:
+  - pluginRef: prefill-pods
+  - pluginRef: max-score-picker
+  - pluginRef: prefix-cache-scorer
+    weight: 50
+- name: decode
+  plugins:
+  - pluginRef: decode-pods
+  - pluginRef: max-score-picker
+  - pluginRef: prefix-cache-scorer
+    weight: 50
+"""
+
+
+def test_config_prefix_cache_strategy():
+    cfg = config_from_yaml(PREFIX_YAML)
+    assert (cfg.block_bytes, cfg.max_blocks, cfg.lru_capacity) == (5, 256, 31250)
+    assert cfg.n_profiles == 1 and cfg.pd_enabled == 0
+    p = cfg.profiles[0]
+    assert p.name == b"default" and p.role_mask == 0 and p.n_scorers == 1
+    assert (p.scorers[0].kind, p.scorers[0].weight) == (abi.FI_SCORER_PREFIX, 100)
+
+
+@pytest.mark.parametrize("kind,enum", [("kv-cache-utilization-scorer", abi.FI_SCORER_KV_UTIL),
+                                       ("queue-scorer", abi.FI_SCORER_QUEUE),
+                                       ("lora-affinity-scorer", abi.FI_SCORER_LORA)])
+def test_config_single_scorer_strategies(kind, enum):
+    cfg = config_from_yaml(_single(kind))
+    assert cfg.n_profiles == 1
+    assert (cfg.profiles[0].scorers[0].kind, cfg.profiles[0].scorers[0].weight) == (enum, 100)
+    assert cfg.block_bytes == default_config().block_bytes  # untouched without a prefix scorer
+
+
+def test_config_pd_disaggregation_strategy():
+    cfg = config_from_yaml(PD_YAML)
+    assert cfg.pd_enabled == 1 and cfg.pd_threshold == 0.0
+    assert cfg.n_profiles == 2
+    assert cfg.profiles[cfg.pd_prefill_profile].name == b"prefill"
+    assert cfg.profiles[cfg.pd_decode_profile].name == b"decode"
+    assert cfg.profiles[cfg.pd_prefill_profile].role_mask == abi.FI_ROLE_PREFILLER
+    assert cfg.profiles[cfg.pd_decode_profile].role_mask == abi.FI_ROLE_DECODER
+    for i in range(2):
+        assert (cfg.profiles[i].scorers[0].kind, cfg.profiles[i].scorers[0].weight) == (abi.FI_SCORER_PREFIX, 50)
+    assert (cfg.block_bytes, cfg.max_blocks, cfg.lru_capacity) == (5, 256, 31250)
+
+
+def test_config_custom_passthrough_multi_scorer_and_comments():
+    y = """# custom EndpointPickerConfig (role.EndpointPickerConfig passthrough, strategy.go:29-31)
+apiVersion: inference.networking.x-k8s.io/v1alpha1
+kind: EndpointPickerConfig
+plugins:
+  - type: prefix-cache-scorer   # indented list style
+    name: pfx
+    parameters:
+      hashBlockSize: 64
+      maxPrefixBlocksToMatch: 128
+  - type: kv-cache-utilization-scorer
+  - type: queue-scorer
+  - type: max-score-picker
+schedulingProfiles:
+  - name: default
+    plugins:
+      - pluginRef: max-score-picker
+      - pluginRef: pfx
+        weight: 3
+      - pluginRef: queue-scorer
+        weight: 2
+      - pluginRef: kv-cache-utilization-scorer
+"""
+    cfg = config_from_yaml(y)
+    assert (cfg.block_bytes, cfg.max_blocks) == (64, 128)
+    p = cfg.profiles[0]
+    got = [(p.scorers[i].kind, p.scorers[i].weight) for i in range(p.n_scorers)]
+    assert got == [(abi.FI_SCORER_PREFIX, 3), (abi.FI_SCORER_QUEUE, 2), (abi.FI_SCORER_KV_UTIL, 1)]
+
+
+@pytest.mark.parametrize("bad,frag", [
+    ("kind: Foo\napiVersion: inference.networking.x-k8s.io/v1alpha1\n", "kind"),
+    (PREFIX_YAML.replace("max-score-picker\nschedulingProfiles", "random-picker\nschedulingProfiles"), "unsupported plugin"),
+    (PREFIX_YAML.replace("  - pluginRef: max-score-picker\n", ""), "picker"),
+    (PREFIX_YAML.replace("pluginRef: prefix-cache-scorer", "pluginRef: nope"), "unknown pluginRef"),
+    (PREFIX_YAML.replace("256", "100000"), "maxPrefixBlocksToMatch"),
+    (PD_YAML.replace("- name: decode", "- name: dec"), "prefill' and 'decode'"),
+    ("", "empty"),
+])
+def test_config_rejects_bad_documents(bad, frag):
+    with pytest.raises(FiEppError) as ei:
+        config_from_yaml(bad)
+    assert ei.value.status == abi.FI_ERR_CONFIG and frag in str(ei.value)
