@@ -281,7 +281,7 @@ def test_pick_reference_block_size_5_ascii():
 def test_lru_add_chain_path_matches_oracle():
     """Post-pick index maintenance (upstream PreRequest → indexer.Add) through the host LRU."""
     wl = H.small_workload(E=24, R=96, lru_capacity=0)
-    cfg = H.config_for(wl, profiles=WEIGHTED, lru_capacity=40)  # tiny: constant eviction
+    cfg = H.config_for(wl, profiles=WEIGHTED, lru_capacity=400, index_slots=1 << 16)  # ~12 chains/endpoint: steady eviction
     gpu, cpu = _pair(cfg)
     st = wl.endpoint_states()
     gpu.update_endpoints(st)
@@ -299,7 +299,7 @@ def test_lru_add_chain_path_matches_oracle():
             cpu.index_add_chain(e, wch[r, :n])
     assert (want["match_blocks"] > 0).any()
     stx = gpu.index_stats()
-    assert stx.lru_entries <= 24 * 40
+    assert stx.lru_entries <= 24 * 400 and stx.tombstones > 0  # evictions really happened
     gpu.close()
 
 

@@ -1,8 +1,6 @@
 #!/bin/bash
-# first GPU job: smoke, parity tests, short bench. Everything logged under gpurun_out/.
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-nproc > gpurun_out/nproc.txt; lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket" >> gpurun_out/nproc.txt
-timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
-timeout 1500 python -m pytest tests -m gpu -x -q --timeout 600 -k "not fullsize and not multi" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-tail -30 gpurun_out/smoke.log gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -x -q --timeout 900 -k "lru or fullsize or multi or limits or device_resident" > gpurun_out/pytest_gpu2.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu2.log
+timeout 1200 python bench.py --steps 20 --warmup 3 > gpurun_out/bench1.json 2> gpurun_out/bench1.err; echo "bench rc=$?"
+timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+tail -n 30 gpurun_out/pytest_gpu2.log; tail -n 20 gpurun_out/bench1.err; cat gpurun_out/bench1.json; tail -n 5 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
