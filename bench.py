@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 10)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (tuning runs only)")
     args = ap.parse_args()
 
     from fusioninfer_b200 import synth
@@ -356,6 +357,8 @@ def main():
     pin_off.array(np.uint64)[:] = offs0
     pin_h0.array(np.uint64)[:] = np.uint64(wl.h0)
     e2e_steps = args.e2e_steps or min(args.steps, 10)
+    if args.no_e2e:
+        e2e_steps = 1
     picker_e2e = picker
     for _ in range(2):
         picker_e2e.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr)

@@ -195,12 +195,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("FI_EPP_LIB", LIB_PATH)  # tuning: an alternative build of the same library
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+            f"{path} is missing: build it with `make` (or __graft_entry__.build()). "
             "fusioninfer_b200 has no CPU fallback for the pick path."
         )
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res

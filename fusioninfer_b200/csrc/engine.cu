@@ -82,6 +82,10 @@ struct PairHash {
 };
 
 constexpr uint64_t kOpChunk = 1ull << 20;  // ops per pinned staging buffer
+constexpr uint32_t kSubBatch = 0;        // requests per pipeline slice; 0 = off (measured slower: chain_finalize is a
+                                         // flat ~45 us at any size and small slices pay launch/ramp overheads)
+constexpr uint32_t kMaxSub = 16;         // slices per call (one work counter each)
+
 enum KernelKind { K_HASH = 0, K_CHAIN = 1, K_MATCH = 2, K_INDEX = 3, K_OTHER = 4, K_KINDS = 5 };
 
 uint32_t pow2_ceil32(uint32_t v) {
@@ -108,6 +112,9 @@ struct fi_epp {
   bool fast_hash = false;
 
   cudaStream_t s_main = nullptr, s_index = nullptr, s_copy = nullptr;
+  cudaStream_t s_hash = nullptr, s_chain = nullptr, s_match = nullptr;  // pipeline streams, by kernel type
+  cudaEvent_t ev_fork = nullptr, ev_join[1] = {nullptr};
+  cudaEvent_t ev_h[16] = {}, ev_c[16] = {};
   cudaEvent_t ev_index = nullptr, ev_user = nullptr, ev_done = nullptr, ev_ctr = nullptr, ev_copy = nullptr;
 
   // request buffers (device)
@@ -123,6 +130,9 @@ struct fi_epp {
   uint32_t* d_mask = nullptr;   // [R][mask_words]
   uint32_t* d_gmask = nullptr;  // [world][R][mask_words]
   unsigned long long* d_probed = nullptr;
+  uint32_t* d_work = nullptr;  // [16] dynamic work-queue counters of in-flight match launches
+  uint32_t* d_ready = nullptr; // per (32-request group, chunk) producer counters of the overlapped hashing
+  bool no_overlap = false;     // FI_EPP_NO_OVERLAP=1: hash then walk on one stream (tuning / debugging)
   // pinned host mirrors
   fi_pick* h_picks = nullptr;
   uint64_t* h_offsets = nullptr;
@@ -161,6 +171,9 @@ struct fi_epp {
   // stats / profiling
   fi_epp_stats stats{};
   bool profiling = false;
+  bool tracing = false;       // FI_EPP_TRACE=<call index>: print that call's kernel timeline to stderr
+  long trace_call = -1;
+  cudaEvent_t ev_trace0 = nullptr;
   struct Ev {
     cudaEvent_t a, b;
     int kind;
@@ -204,14 +217,14 @@ struct LaunchScope {
   cudaEvent_t a = nullptr, b = nullptr;
   LaunchScope(fi_epp* h_, cudaStream_t s_, int kind_) : h(h_), s(s_), kind(kind_) {
     h->stats.kernel_launches++;
-    if (h->profiling) {
+    if (h->profiling || h->tracing) {
       a = get_event(h);
       b = get_event(h);
       cudaEventRecord(a, s);
     }
   }
   ~LaunchScope() {
-    if (h->profiling) {
+    if (h->profiling || h->tracing) {
       cudaEventRecord(b, s);
       h->pending_ev.push_back({a, b, kind});
     }
@@ -365,20 +378,49 @@ int upload_endpoints(fi_epp* h) {
   return FI_OK;
 }
 
-// hash kernels: prompts → chain (device buffers), on s_main
-int run_hash(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0, uint32_t R) {
-  if (h->fast_hash) {
-    {
-      LaunchScope ls(h, h->s_main, K_HASH);
-      FI_CUDA(launch_hash_blocks(d_prompts, d_offsets, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, h->d_pre,
-                                 h->d_nblocks, h->s_main));
+// hash kernels for the request slice [r0, r0+R): prompts → chain (device buffers), on stream s
+int run_hash(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0, uint32_t r0,
+             uint32_t R, cudaStream_t s) {
+  uint64_t* pre = h->d_pre + (size_t)r0 * h->MP;
+  uint64_t* chain = h->d_chain + (size_t)r0 * h->MP;
+  uint32_t* nb = h->d_nblocks + r0;
+  if (h->fast_hash && hash_overlap_supported(h->cfg.block_bytes)) {
+    // producers (chunk-major hashing) and the chain walker run concurrently; the walker waits on
+    // per-chunk counters.  Producers are launched first, so a serialising tool just runs them first.
+    const uint32_t B = h->cfg.block_bytes, M = h->cfg.max_blocks;
+    FI_CUDA(cudaMemsetAsync(h->d_ready, 0, (size_t)hash_overlap_flag_words(R, M) * sizeof(uint32_t), s));
+    const bool overlap = !h->profiling && !h->no_overlap;
+    cudaStream_t sp = overlap ? h->s_hash : s, sw = overlap ? h->s_chain : s;
+    if (overlap) {
+      FI_CUDA(cudaEventRecord(h->ev_fork, s));
+      FI_CUDA(cudaStreamWaitEvent(sp, h->ev_fork, 0));
+      FI_CUDA(cudaStreamWaitEvent(sw, h->ev_fork, 0));
     }
-    LaunchScope ls(h, h->s_main, K_CHAIN);
-    FI_CUDA(launch_chain_finalize(h->d_pre, h->d_nblocks, d_h0, R, h->MP, h->d_chain, h->s_main));
+    {
+      LaunchScope ls(h, sp, K_HASH);
+      FI_CUDA(launch_hash_chunks(d_prompts, d_offsets + r0, R, B, M, h->MP, pre, nb, h->d_ready, sp));
+    }
+    {
+      LaunchScope ls(h, sw, K_CHAIN);
+      FI_CUDA(launch_chain_walk(pre, d_offsets + r0, d_h0 + r0, R, B, M, h->MP, h->d_ready, chain, sw));
+    }
+    if (overlap) {
+      FI_CUDA(cudaEventRecord(h->ev_h[0], sp));
+      FI_CUDA(cudaEventRecord(h->ev_c[0], sw));
+      FI_CUDA(cudaStreamWaitEvent(s, h->ev_h[0], 0));
+      FI_CUDA(cudaStreamWaitEvent(s, h->ev_c[0], 0));
+    }
+  } else if (h->fast_hash) {
+    {
+      LaunchScope ls(h, s, K_HASH);
+      FI_CUDA(launch_hash_blocks(d_prompts, d_offsets + r0, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, pre, nb, s));
+    }
+    LaunchScope ls(h, s, K_CHAIN);
+    FI_CUDA(launch_chain_finalize(pre, nb, d_h0 + r0, R, h->MP, chain, s));
   } else {
-    LaunchScope ls(h, h->s_main, K_HASH);
-    FI_CUDA(launch_hash_generic(d_prompts, d_offsets, d_h0, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, h->d_chain,
-                                h->d_nblocks, h->s_main));
+    LaunchScope ls(h, s, K_HASH);
+    FI_CUDA(launch_hash_generic(d_prompts, d_offsets + r0, d_h0 + r0, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP,
+                                chain, nb, s));
   }
   return FI_OK;
 }
@@ -397,12 +439,15 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
   if (rc != FI_OK) return rc;
   rc = check_counters(h);
   if (rc != FI_OK) return rc;
+  h->tracing = !h->profiling && h->trace_call >= 0 && (long)h->stats.pick_calls == h->trace_call;
+  if (h->tracing) {
+    if (!h->ev_trace0) cudaEventCreate(&h->ev_trace0);
+    FI_CUDA(cudaStreamSynchronize(h->s_main));
+    FI_CUDA(cudaEventRecord(h->ev_trace0, h->s_main));
+  }
   FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_index, 0));  // every submitted op is visible
   rc = upload_endpoints(h);
   if (rc != FI_OK) return rc;
-  rc = run_hash(h, d_prompts, d_offsets, d_h0, R);
-  if (rc != FI_OK) return rc;
-
   const bool sharded = h->world > 1;
   MatchParams mp{};
   mp.chain = h->d_chain;
@@ -423,7 +468,44 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
   mp.gmask_ranks = 0;
   mp.out = sharded ? h->d_local : d_out;
   mp.probed_blocks = h->profiling ? h->d_probed : nullptr;
+  mp.work_counter = h->d_work;
+  mp.zero_work_counter = 1;
 
+  if (!sharded) {
+    // (A sub-batch pipeline over several streams was tried and measured slower — DESIGN.md
+    // "What did not work": chain walking costs a flat ~45 us at any batch size and small
+    // slices pay launch/ramp overheads.  The overlap now lives inside run_hash.)
+    const uint32_t nsub = 1;
+    rc = run_hash(h, d_prompts, d_offsets, d_h0, 0, R, h->s_main);
+    if (rc != FI_OK) return rc;
+    {
+      LaunchScope ls(h, h->s_main, K_MATCH);
+      FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
+    }
+    if (h->tracing) {
+      static const char* names[] = {"hash_blocks", "chain_finalize", "match_pick", "index", "other"};
+      cudaStreamSynchronize(h->s_main);
+      std::fprintf(stderr, "[fi_epp trace] call %ld: R=%u slices=%u\n", h->trace_call, R, nsub);
+      for (auto& e : h->pending_ev) {
+        float t0 = 0.f, t1 = 0.f;
+        cudaEventSynchronize(e.b);
+        cudaEventElapsedTime(&t0, h->ev_trace0, e.a);
+        cudaEventElapsedTime(&t1, h->ev_trace0, e.b);
+        std::fprintf(stderr, "[fi_epp trace]   %-15s start %8.1f us  end %8.1f us  (%6.1f us)\n", names[e.kind], t0 * 1e3,
+                     t1 * 1e3, (t1 - t0) * 1e3);
+        h->ev_pool.push_back(e.a);
+        h->ev_pool.push_back(e.b);
+      }
+      h->pending_ev.clear();
+      h->tracing = false;
+    }
+    h->stats.pick_calls++;
+    h->stats.requests += R;
+    return FI_OK;
+  }
+
+  rc = run_hash(h, d_prompts, d_offsets, d_h0, 0, R, h->s_main);
+  if (rc != FI_OK) return rc;
   if (sharded && h->cfg.match_mode == FI_MATCH_UPSTREAM) {
     // exact upstream semantics need the global first miss: exchange presence masks
     {
@@ -589,6 +671,8 @@ void fi_epp_destroy(fi_epp* h) {
   cudaFree(h->d_mask);
   cudaFree(h->d_gmask);
   cudaFree(h->d_probed);
+  cudaFree(h->d_work);
+  cudaFree(h->d_ready);
   cudaFree(h->d_ctr);
   cudaFree(h->d_eps);
   cudaFree(h->d_sc);
@@ -609,6 +693,17 @@ void fi_epp_destroy(fi_epp* h) {
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   for (cudaEvent_t e : {h->ev_index, h->ev_user, h->ev_done, h->ev_ctr, h->ev_copy})
     if (e) cudaEventDestroy(e);
+  for (cudaStream_t s : {h->s_hash, h->s_chain, h->s_match})
+    if (s) {
+      cudaStreamSynchronize(s);
+      cudaStreamDestroy(s);
+    }
+  for (uint32_t i = 0; i < kMaxSub; ++i) {
+    if (h->ev_h[i]) cudaEventDestroy(h->ev_h[i]);
+    if (h->ev_c[i]) cudaEventDestroy(h->ev_c[i]);
+  }
+  if (h->ev_join[0]) cudaEventDestroy(h->ev_join[0]);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (cudaStream_t s : {h->s_main, h->s_index, h->s_copy})
     if (s) cudaStreamDestroy(s);
   delete h;
@@ -658,6 +753,7 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   h->MP = (cfg->max_blocks + 3) & ~3u;
   h->W = pow2_ceil32((cfg->endpoint_count + 31) / 32);
   h->fast_hash = (cfg->block_bytes % 32) == 0;
+  if (const char* e = std::getenv("FI_EPP_TRACE")) h->trace_call = std::strtol(e, nullptr, 10);
   if (h->cfg.max_prompt_bytes == 0)
     h->cfg.max_prompt_bytes = (uint64_t)cfg->max_batch * cfg->block_bytes * cfg->max_blocks;
   if (h->cfg.index_slots == 0) {
@@ -673,6 +769,20 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   for (cudaEvent_t* e : {&h->ev_index, &h->ev_user, &h->ev_done, &h->ev_ctr, &h->ev_copy})
     FI_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   FI_TRY(cudaEventRecord(h->ev_index, h->s_index));
+  FI_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  FI_TRY(cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming));
+  {
+    int lo = 0, hi = 0;  // numerically lower = higher priority
+    FI_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const int mid = (lo + hi) / 2;
+    FI_TRY(cudaStreamCreateWithPriority(&h->s_hash, cudaStreamNonBlocking, lo));
+    FI_TRY(cudaStreamCreateWithPriority(&h->s_match, cudaStreamNonBlocking, mid));
+    FI_TRY(cudaStreamCreateWithPriority(&h->s_chain, cudaStreamNonBlocking, hi));
+  }
+  for (uint32_t i = 0; i < kMaxSub; ++i) {
+    FI_TRY(cudaEventCreateWithFlags(&h->ev_h[i], cudaEventDisableTiming));
+    FI_TRY(cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming));
+  }
 
   const uint64_t R = cfg->max_batch;
   const uint32_t mask_words = (h->MP + 31) / 32;
@@ -685,6 +795,10 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaMalloc(&h->d_picks, R * h->P * sizeof(fi_pick)));
   FI_TRY(cudaMalloc(&h->d_probed, sizeof(unsigned long long)));
   FI_TRY(cudaMemset(h->d_probed, 0, sizeof(unsigned long long)));
+  FI_TRY(cudaMalloc(&h->d_work, 16 * sizeof(uint32_t)));
+  FI_TRY(cudaMemset(h->d_work, 0, 16 * sizeof(uint32_t)));
+  FI_TRY(cudaMalloc(&h->d_ready, (size_t)hash_overlap_flag_words(cfg->max_batch, cfg->max_blocks) * sizeof(uint32_t) + 64));
+  if (const char* e = std::getenv("FI_EPP_NO_OVERLAP")) h->no_overlap = std::atoi(e) != 0;
   FI_TRY(cudaMallocHost(&h->h_picks, R * h->P * sizeof(fi_pick)));
   FI_TRY(cudaMallocHost(&h->h_offsets, (R + 1) * sizeof(uint64_t)));
   FI_TRY(cudaMallocHost(&h->h_h0, R * sizeof(uint64_t)));
@@ -900,7 +1014,7 @@ int fi_epp_hash_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets
   if (rc != FI_OK) return rc;
   rc = stage_inputs(h, prompts, offsets, h0, R, total);
   if (rc != FI_OK) return rc;
-  rc = run_hash(h, h->d_prompts, h->d_offsets, h->d_h0, R);
+  rc = run_hash(h, h->d_prompts, h->d_offsets, h->d_h0, 0, R, h->s_main);
   if (rc != FI_OK) return rc;
   if (chains_out) {
     rc = copy_chains_out(h, chains_out, R, cudaMemcpyDeviceToHost, h->s_main);

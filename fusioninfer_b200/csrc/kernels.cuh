@@ -91,6 +91,8 @@ struct MatchParams {
   uint32_t mask_words;
   fi_pick* out;                       // [R][P]
   unsigned long long* probed_blocks;  // optional Σ N_probe
+  uint32_t* work_counter;             // dynamic request queue of the launch
+  uint32_t zero_work_counter;         // launcher zeroes it first (0: the caller already did)
 };
 
 struct MergeParams {
@@ -111,6 +113,14 @@ cudaError_t launch_chain_finalize(const uint64_t* pre, const uint32_t* nblocks, 
 cudaError_t launch_hash_generic(const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
                                 uint32_t R, uint32_t B, uint32_t M, uint32_t MP, uint64_t* chain,
                                 uint32_t* nblocks, cudaStream_t s);
+
+// overlapped hashing: chunk-major producers + flag-waiting chain walker (hash_kernels.cu)
+bool hash_overlap_supported(uint32_t B);
+uint32_t hash_overlap_flag_words(uint32_t R, uint32_t M);
+cudaError_t launch_hash_chunks(const uint8_t* prompts, const uint64_t* offsets, uint32_t R, uint32_t B, uint32_t M,
+                               uint32_t MP, uint64_t* pre, uint32_t* nblocks, uint32_t* ready, cudaStream_t s);
+cudaError_t launch_chain_walk(const uint64_t* pre, const uint64_t* offsets, const uint64_t* h0, uint32_t R, uint32_t B,
+                              uint32_t M, uint32_t MP, const uint32_t* ready, uint64_t* chain, cudaStream_t s);
 
 cudaError_t launch_index_set(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n,
                              uint32_t ep_begin, uint32_t ep_count, cudaStream_t s);

@@ -35,6 +35,9 @@ namespace fi {
 namespace {
 
 constexpr int kWarps = 8;
+#ifndef FI_MATCH_MIN_BLOCKS
+#define FI_MATCH_MIN_BLOCKS 2
+#endif
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct Best {
@@ -70,6 +73,8 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// fire-and-forget: pull a line into L2, no destination register, no scoreboard wait
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
 // PD rule shared by the single-GPU kernel and the multi-GPU merge kernel
 __device__ __forceinline__ bool pd_prefill_runs(uint32_t dec_endpoint, uint32_t dec_match, uint32_t n, uint64_t len,
@@ -79,21 +84,52 @@ __device__ __forceinline__ bool pd_prefill_runs(uint32_t dec_endpoint, uint32_t 
   return miss_bytes >= threshold;
 }
 
-template <int L, int WPL, bool LPM, bool GMASK>
-__global__ void __launch_bounds__(kWarps * 32) match_pick_kernel(const MatchParams p) {
-  static_assert(L == 32 || WPL == 1, "multi-word lanes only for full-width rows");
-  constexpr int G = 32 / L;                              // rows per load instruction
-  constexpr int BATCH = (L >= 16 ? 16 : L) / WPL > 0 ? (L >= 16 ? 16 : L) / WPL : 1;  // load instrs in flight
+// load VEC consecutive words of a row (16-byte vectors for full rows)
+template <int VEC>
+__device__ __forceinline__ void load_row_words(const uint32_t* __restrict__ p, bool ok, uint32_t (&out)[VEC]) {
+  if (VEC == 4) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ok) v = __ldg(reinterpret_cast<const uint4*>(p));
+    out[0] = v.x;
+    out[1 % VEC] = v.y;
+    out[2 % VEC] = v.z;
+    out[3 % VEC] = v.w;
+  } else if (VEC == 2) {
+    uint2 v = make_uint2(0, 0);
+    if (ok) v = __ldg(reinterpret_cast<const uint2*>(p));
+    out[0] = v.x;
+    out[1 % VEC] = v.y;
+  } else {
+    out[0] = ok ? __ldg(p) : 0u;
+  }
+}
+
+// LPR lanes read one row (VEC words each, LPR*VEC = words per row); a load
+// instruction therefore covers G = 32/LPR rows.  E = 1024 → LPR 8, VEC 4: a 128-byte
+// row is 8 × 16-byte loads and one instruction brings in 4 rows; 32 rows in flight.
+template <int LPR, int VEC, bool LPM, bool GMASK>
+__global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_kernel(const MatchParams p) {
+  constexpr int G = 32 / LPR;                 // rows per load instruction
+  constexpr int BATCH = LPR < 8 ? LPR : 8;    // load instructions in flight
   extern __shared__ __align__(16) uint64_t s_mem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int t = lane % L;  // word within the row
-  const int g = lane / L;  // row group
+  const int t = lane % LPR;  // position within the row
+  const int g = lane / LPR;  // row group
   uint64_t* s_chain = s_mem + (size_t)warp * p.MP;
   const IndexView ix = p.ix;
   const uint32_t P = p.st.n_profiles;
+  const uint32_t* row_base = ix.rows + t * VEC;
 
-  for (uint32_t r = blockIdx.x * kWarps + warp; r < p.R; r += gridDim.x * kWarps) {
+  // dynamic work queue (requests differ a lot in how many rows they touch); the next item is
+  // fetched while the current one is processed so the atomic's round trip is off the critical path
+  uint32_t r_next = 0;
+  if (lane == 0) r_next = atomicAdd(p.work_counter, 1u);
+  r_next = __shfl_sync(FULL, r_next, 0);
+  for (;;) {
+    const uint32_t r = r_next;
+    if (r >= p.R) break;
+    if (lane == 0) r_next = atomicAdd(p.work_counter, 1u);
     const uint32_t n = p.nblocks[r];
     // ---- 1. stage the chain ---------------------------------------------------
     {
@@ -116,10 +152,10 @@ __global__ void __launch_bounds__(kWarps * 32) match_pick_kernel(const MatchPara
       kg = min(n, pos);
     }
 
-    BitCounter cnt[WPL];
-    uint32_t alive[WPL];
+    BitCounter cnt[VEC];
+    uint32_t alive[VEC];
 #pragma unroll
-    for (int x = 0; x < WPL; ++x) {
+    for (int x = 0; x < VEC; ++x) {
       bc_clear(cnt[x]);
       alive[x] = 0xFFFFFFFFu;
     }
@@ -128,18 +164,9 @@ __global__ void __launch_bounds__(kWarps * 32) match_pick_kernel(const MatchPara
 
     // ---- 2./3. probe + row reads, 32 blocks per chunk ---------------------------
     const uint32_t nchunks = (kg + 31) / 32;
-    uint64_t h = 0;
-    bool valid = (uint32_t)lane < kg;
-    BucketRegs br;
-    br.a = make_uint4(0, 0, 0, 0);
-    br.b = br.a;
-    if (valid) {
-      h = s_chain[lane];
-      if (!key_is_special(h)) br = bucket_load(ix, h & ix.bmask);
-    }
+    uint32_t slot = SLOT_MISS;
+    if ((uint32_t)lane < kg) slot = index_find(ix, s_chain[lane]);
     for (uint32_t c = 0; c < nchunks; ++c) {
-      uint32_t slot = SLOT_MISS;
-      if (valid) slot = key_is_special(h) ? index_find(ix, h) : index_resolve(ix, h, br);
       uint32_t rows_here;
       bool stop = false;
       if (GMASK) {
@@ -152,46 +179,62 @@ __global__ void __launch_bounds__(kWarps * 32) match_pick_kernel(const MatchPara
           real_miss = (c * 32 + rows_here) < n;
         }
       }
-      // issue the next chunk's probes before touching this chunk's rows
+      // issue the next chunk's probe before touching this chunk's rows
       uint64_t hn = 0;
-      bool validn = false;
-      BucketRegs brn = br;
+      bool validn = false, plain = false;
+      BucketRegs brn;
+      brn.a = make_uint4(0, 0, 0, 0);
+      brn.b = brn.a;
       if (!stop && c + 1 < nchunks) {
         const uint32_t idx = (c + 1) * 32 + lane;
         validn = idx < kg;
         if (validn) {
           hn = s_chain[idx];
-          if (!key_is_special(hn)) brn = bucket_load(ix, hn & ix.bmask);
+          plain = !key_is_special(hn);
+          if (plain) brn = bucket_load(ix, hn & ix.bmask);
         }
       }
+      uint32_t slot_next = SLOT_MISS;
+      bool resolved = false;
       // rows of this chunk
 #pragma unroll 1
-      for (int q0 = 0; q0 < L; q0 += BATCH) {
+      for (int q0 = 0; q0 < LPR; q0 += BATCH) {
         if ((uint32_t)(q0 * G) >= rows_here) break;
-        uint32_t w[WPL][BATCH];
+        uint32_t w[VEC][BATCH];
 #pragma unroll
         for (int qi = 0; qi < BATCH; ++qi) {
           const int j = (q0 + qi) * G + g;  // row of the chunk this lane helps read
           const uint32_t s = __shfl_sync(FULL, slot, j & 31);
           const bool ok = (uint32_t)j < rows_here && s != SLOT_MISS;
-          const uint32_t* rp = ix.rows + ((uint64_t)s << ix.logW) + t;
+          uint32_t tmp[VEC];
+          load_row_words<VEC>(row_base + ((uint64_t)s << ix.logW), ok, tmp);
 #pragma unroll
-          for (int x = 0; x < WPL; ++x) w[x][qi] = ok ? __ldg(rp + 32 * x) : 0u;
+          for (int x = 0; x < VEC; ++x) w[x][qi] = tmp[x];
+        }
+        if (!resolved) {
+          // resolve the next chunk's probe while this chunk's rows are in flight (a full
+          // home bucket costs a second dependent sector read; it overlaps the row latency)
+          if (validn) slot_next = plain ? index_resolve(ix, hn, brn) : index_find(ix, hn);
+          resolved = true;
+          // the next chunk's rows start moving towards L2 a whole chunk ahead of their loads
+#ifdef FI_MATCH_PREFETCH_ROWS
+          if (slot_next != SLOT_MISS) prefetch_l2(ix.rows + ((uint64_t)slot_next << ix.logW));
+#endif
         }
         if (LPM) {
 #pragma unroll
           for (int qi = 0; qi < BATCH; ++qi) {
 #pragma unroll
-            for (int x = 0; x < WPL; ++x) {
+            for (int x = 0; x < VEC; ++x) {
               uint32_t v = w[x][qi];
               if (G > 1) {  // prefix-AND over the G rows of this instruction
 #pragma unroll
                 for (int d = 1; d < G; d <<= 1) {
-                  const uint32_t o = __shfl_up_sync(FULL, v, d * L);
+                  const uint32_t o = __shfl_up_sync(FULL, v, d * LPR);
                   if (g >= d) v &= o;
                 }
                 v &= alive[x];
-                alive[x] = __shfl_sync(FULL, v, (G - 1) * L + t);
+                alive[x] = __shfl_sync(FULL, v, (G - 1) * LPR + t);
               } else {
                 v &= alive[x];
                 alive[x] = v;
@@ -201,29 +244,31 @@ __global__ void __launch_bounds__(kWarps * 32) match_pick_kernel(const MatchPara
           }
         }
 #pragma unroll
-        for (int x = 0; x < WPL; ++x) bc_add<BATCH>(cnt[x], w[x]);
+        for (int x = 0; x < VEC; ++x) bc_add<BATCH>(cnt[x], w[x]);
       }
+      if (!resolved && validn) slot_next = plain ? index_resolve(ix, hn, brn) : index_find(ix, hn);
       matched_rows += rows_here;
       if (stop) break;
       if (LPM) {  // every local endpoint already dropped out: nothing more can match
         bool any = false;
 #pragma unroll
-        for (int x = 0; x < WPL; ++x) any |= alive[x] != 0;
+        for (int x = 0; x < VEC; ++x) any |= alive[x] != 0;
         if (!__ballot_sync(FULL, any)) break;
       }
-      h = hn;
-      valid = validn;
-      br = brn;
+      slot = slot_next;
     }
 
     // ---- merge the lane groups' counters ---------------------------------------
     if (G > 1) {
 #pragma unroll
-      for (int d = L; d < 32; d <<= 1) {
-        BitCounter o;
+      for (int x = 0; x < VEC; ++x) {
 #pragma unroll
-        for (int pl = 0; pl < NPLANES; ++pl) o.c[pl] = __shfl_xor_sync(FULL, cnt[0].c[pl], d);
-        bc_merge(cnt[0], o);
+        for (int d = LPR; d < 32; d <<= 1) {
+          BitCounter o;
+#pragma unroll
+          for (int pl = 0; pl < NPLANES; ++pl) o.c[pl] = __shfl_xor_sync(FULL, cnt[x].c[pl], d);
+          bc_merge(cnt[x], o);
+        }
       }
     }
 
@@ -240,8 +285,8 @@ __global__ void __launch_bounds__(kWarps * 32) match_pick_kernel(const MatchPara
         b.m = 0;
         if (g == 0) {
 #pragma unroll
-          for (int x = 0; x < WPL; ++x) {
-            const uint32_t wi = t + 32 * x;
+          for (int x = 0; x < VEC; ++x) {
+            const uint32_t wi = t * VEC + x;
             uint32_t cand = bc_nonzero(cnt[x]) & p.st.elig[(uint64_t)pi * ix.W + wi];
             while (cand) {
               const uint32_t bit = __ffs(cand) - 1;
@@ -303,9 +348,10 @@ __global__ void __launch_bounds__(kWarps * 32) match_pick_kernel(const MatchPara
       }
       if (p.probed_blocks) atomicAdd(p.probed_blocks, (unsigned long long)(matched_rows + (real_miss ? 1 : 0)));
     }
-    __syncwarp();  // s_chain is rewritten by the next request
+    r_next = __shfl_sync(FULL, r_next, 0);  // also orders this request's s_chain reads before the next staging
   }
 }
+
 
 // presence mask of every block of every request on this rank (sharded upstream mode)
 __global__ void __launch_bounds__(kWarps * 32) probe_mask_kernel(const MatchParams p, uint32_t* __restrict__ mask_out) {
@@ -473,44 +519,59 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointD
   }
 }
 
-template <int L, int WPL>
+template <int LPR, int VEC>
 cudaError_t launch_match_t(const MatchParams& p, int sm_count, cudaStream_t s) {
   const size_t smem = (size_t)kWarps * p.MP * sizeof(uint64_t);
   auto go = [&](auto kern) -> cudaError_t {
-    cudaError_t e = cudaSuccess;
-    if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-    }
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarps * 32, smem);
+    // occupancy is a property of (kernel, smem): query once per distinct smem size
+    static size_t cached_smem_dev[64];
+    static int cached_per_sm_dev[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
+    dev &= 63;
+    size_t& cached_smem = cached_smem_dev[dev];
+    int& cached_per_sm = cached_per_sm_dev[dev];
+    if (cached_smem != smem + 1) {  // +1: zero-initialised statics mean "not cached"
+      if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+      }
+      int per_sm = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarps * 32, smem);
+      if (e != cudaSuccess) return e;
+      cached_per_sm = per_sm < 1 ? 1 : per_sm;
+      cached_smem = smem + 1;
+    }
     uint32_t grid = (p.R + kWarps - 1) / kWarps;
-    const uint32_t cap = (uint32_t)sm_count * (uint32_t)per_sm;
+    const uint32_t cap = (uint32_t)sm_count * (uint32_t)cached_per_sm;
     if (grid > cap) grid = cap;
     if (grid == 0) grid = 1;
+    if (p.zero_work_counter) {
+      e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
+      if (e != cudaSuccess) return e;
+    }
     kern<<<grid, kWarps * 32, smem, s>>>(p);
     return cudaGetLastError();
   };
   const bool lpm = p.lpm == FI_MATCH_LPM;
   const bool gm = p.gmask != nullptr;
-  if (lpm) return gm ? go(match_pick_kernel<L, WPL, true, true>) : go(match_pick_kernel<L, WPL, true, false>);
-  return gm ? go(match_pick_kernel<L, WPL, false, true>) : go(match_pick_kernel<L, WPL, false, false>);
+  if (lpm) return gm ? go(match_pick_kernel<LPR, VEC, true, true>) : go(match_pick_kernel<LPR, VEC, true, false>);
+  return gm ? go(match_pick_kernel<LPR, VEC, false, true>) : go(match_pick_kernel<LPR, VEC, false, false>);
 }
 
 }  // namespace
 
 cudaError_t launch_match_pick(const MatchParams& p, int sm_count, cudaStream_t s) {
   if (p.R == 0) return cudaSuccess;
-  switch (p.ix.W) {
+  switch (p.ix.W) {  // words per row = LPR * VEC
     case 1: return launch_match_t<1, 1>(p, sm_count, s);
-    case 2: return launch_match_t<2, 1>(p, sm_count, s);
-    case 4: return launch_match_t<4, 1>(p, sm_count, s);
-    case 8: return launch_match_t<8, 1>(p, sm_count, s);
-    case 16: return launch_match_t<16, 1>(p, sm_count, s);
-    case 32: return launch_match_t<32, 1>(p, sm_count, s);
-    case 64: return launch_match_t<32, 2>(p, sm_count, s);
+    case 2: return launch_match_t<1, 2>(p, sm_count, s);
+    case 4: return launch_match_t<1, 4>(p, sm_count, s);
+    case 8: return launch_match_t<2, 4>(p, sm_count, s);
+    case 16: return launch_match_t<4, 4>(p, sm_count, s);
+    case 32: return launch_match_t<8, 4>(p, sm_count, s);
+    case 64: return launch_match_t<16, 4>(p, sm_count, s);
     case 128: return launch_match_t<32, 4>(p, sm_count, s);
     default: return cudaErrorInvalidValue;
   }
