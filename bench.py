@@ -118,7 +118,8 @@ def build_config(wl, cfg_id, begin, count, device, max_batch, mode):
 
     profiles, pd = synth.baseline_profiles(cfg_id)
     slots = 4096
-    while slots < 2 * count * wl.lru_capacity:
+    mult = int(os.environ.get("FI_BENCH_SLOT_MULT", "2"))  # index load factor <= 1/mult
+    while slots < mult * count * wl.lru_capacity:
         slots *= 2
     return make_config(num_endpoints=wl.E, block_bytes=wl.block_bytes, max_blocks=wl.max_blocks, lru_capacity=0,
                        max_batch=max_batch, max_prompt_bytes=max_batch * wl.T * 4, index_slots=slots, device=device,

@@ -131,8 +131,6 @@ struct fi_epp {
   uint32_t* d_gmask = nullptr;  // [world][R][mask_words]
   unsigned long long* d_probed = nullptr;
   uint32_t* d_work = nullptr;  // [16] dynamic work-queue counters of in-flight match launches
-  uint32_t* d_ready = nullptr; // per (32-request group, chunk) producer counters of the overlapped hashing
-  bool no_overlap = false;     // FI_EPP_NO_OVERLAP=1: hash then walk on one stream (tuning / debugging)
   // pinned host mirrors
   fi_pick* h_picks = nullptr;
   uint64_t* h_offsets = nullptr;
@@ -256,7 +254,7 @@ int alloc_index(fi_epp* h, uint64_t slots, IndexView* out) {
   v.W = h->W;
   v.logW = 0;
   while ((1u << v.logW) < v.W) ++v.logW;
-  const uint64_t total = slots + 2;
+  const uint64_t total = slots + 3;  // + slots for hash 0, hash ~0, and a permanently-zero row
   FI_CUDA(cudaMalloc(&v.keys, total * sizeof(uint64_t)));
   FI_CUDA(cudaMalloc(&v.rows, total * v.W * sizeof(uint32_t)));
   FI_CUDA(cudaMalloc(&v.cnt, total * sizeof(uint32_t)));
@@ -381,36 +379,10 @@ int upload_endpoints(fi_epp* h) {
 // hash kernels for the request slice [r0, r0+R): prompts → chain (device buffers), on stream s
 int run_hash(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0, uint32_t r0,
              uint32_t R, cudaStream_t s) {
-  uint64_t* pre = h->d_pre + (size_t)r0 * h->MP;
+  uint64_t* pre = h->d_pre;  // tiled by groups of 32 requests: slices must start at r0 == 0
   uint64_t* chain = h->d_chain + (size_t)r0 * h->MP;
   uint32_t* nb = h->d_nblocks + r0;
-  if (h->fast_hash && hash_overlap_supported(h->cfg.block_bytes)) {
-    // producers (chunk-major hashing) and the chain walker run concurrently; the walker waits on
-    // per-chunk counters.  Producers are launched first, so a serialising tool just runs them first.
-    const uint32_t B = h->cfg.block_bytes, M = h->cfg.max_blocks;
-    FI_CUDA(cudaMemsetAsync(h->d_ready, 0, (size_t)hash_overlap_flag_words(R, M) * sizeof(uint32_t), s));
-    const bool overlap = !h->profiling && !h->no_overlap;
-    cudaStream_t sp = overlap ? h->s_hash : s, sw = overlap ? h->s_chain : s;
-    if (overlap) {
-      FI_CUDA(cudaEventRecord(h->ev_fork, s));
-      FI_CUDA(cudaStreamWaitEvent(sp, h->ev_fork, 0));
-      FI_CUDA(cudaStreamWaitEvent(sw, h->ev_fork, 0));
-    }
-    {
-      LaunchScope ls(h, sp, K_HASH);
-      FI_CUDA(launch_hash_chunks(d_prompts, d_offsets + r0, R, B, M, h->MP, pre, nb, h->d_ready, sp));
-    }
-    {
-      LaunchScope ls(h, sw, K_CHAIN);
-      FI_CUDA(launch_chain_walk(pre, d_offsets + r0, d_h0 + r0, R, B, M, h->MP, h->d_ready, chain, sw));
-    }
-    if (overlap) {
-      FI_CUDA(cudaEventRecord(h->ev_h[0], sp));
-      FI_CUDA(cudaEventRecord(h->ev_c[0], sw));
-      FI_CUDA(cudaStreamWaitEvent(s, h->ev_h[0], 0));
-      FI_CUDA(cudaStreamWaitEvent(s, h->ev_c[0], 0));
-    }
-  } else if (h->fast_hash) {
+  if (h->fast_hash) {
     {
       LaunchScope ls(h, s, K_HASH);
       FI_CUDA(launch_hash_blocks(d_prompts, d_offsets + r0, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, pre, nb, s));
@@ -672,7 +644,6 @@ void fi_epp_destroy(fi_epp* h) {
   cudaFree(h->d_gmask);
   cudaFree(h->d_probed);
   cudaFree(h->d_work);
-  cudaFree(h->d_ready);
   cudaFree(h->d_ctr);
   cudaFree(h->d_eps);
   cudaFree(h->d_sc);
@@ -757,7 +728,7 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   if (h->cfg.max_prompt_bytes == 0)
     h->cfg.max_prompt_bytes = (uint64_t)cfg->max_batch * cfg->block_bytes * cfg->max_blocks;
   if (h->cfg.index_slots == 0) {
-    uint64_t want = 2ull * cfg->endpoint_count * (cfg->lru_capacity ? cfg->lru_capacity : 1024);
+    uint64_t want = 2ull * cfg->endpoint_count * (cfg->lru_capacity ? cfg->lru_capacity : 1024);  // load <= 0.5
     if (want < 4096) want = 4096;
     h->cfg.index_slots = pow2_ceil64(want);
     if (h->cfg.index_slots > 0x80000000ull) h->cfg.index_slots = 0x80000000ull;
@@ -789,7 +760,7 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaMalloc(&h->d_prompts, h->cfg.max_prompt_bytes + 64));
   FI_TRY(cudaMalloc(&h->d_offsets, (R + 1) * sizeof(uint64_t)));
   FI_TRY(cudaMalloc(&h->d_h0, R * sizeof(uint64_t)));
-  FI_TRY(cudaMalloc(&h->d_pre, R * h->MP * sizeof(uint64_t)));
+  FI_TRY(cudaMalloc(&h->d_pre, ((R + 31) / 32 * 32) * h->MP * sizeof(uint64_t)));
   FI_TRY(cudaMalloc(&h->d_chain, R * h->MP * sizeof(uint64_t)));
   FI_TRY(cudaMalloc(&h->d_nblocks, R * sizeof(uint32_t)));
   FI_TRY(cudaMalloc(&h->d_picks, R * h->P * sizeof(fi_pick)));
@@ -797,8 +768,6 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaMemset(h->d_probed, 0, sizeof(unsigned long long)));
   FI_TRY(cudaMalloc(&h->d_work, 16 * sizeof(uint32_t)));
   FI_TRY(cudaMemset(h->d_work, 0, 16 * sizeof(uint32_t)));
-  FI_TRY(cudaMalloc(&h->d_ready, (size_t)hash_overlap_flag_words(cfg->max_batch, cfg->max_blocks) * sizeof(uint32_t) + 64));
-  if (const char* e = std::getenv("FI_EPP_NO_OVERLAP")) h->no_overlap = std::atoi(e) != 0;
   FI_TRY(cudaMallocHost(&h->h_picks, R * h->P * sizeof(fi_pick)));
   FI_TRY(cudaMallocHost(&h->h_offsets, (R + 1) * sizeof(uint64_t)));
   FI_TRY(cudaMallocHost(&h->h_h0, R * sizeof(uint64_t)));

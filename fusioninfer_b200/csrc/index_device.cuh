@@ -5,44 +5,48 @@
 namespace fi {
 
 struct BucketRegs {
-  uint4 a, b;  // 4 keys = one 32-byte sector
+  uint4 q[BUCKET_KEYS / 2];  // BUCKET_KEYS keys = one 64-byte bucket (two adjacent 32 B sectors)
 };
 
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
-// issue the loads of the home bucket of h (no dependence on their result)
+// issue the loads of bucket b (no dependence on their result)
 __device__ __forceinline__ BucketRegs bucket_load(const IndexView& ix, uint64_t b) {
   const uint4* p = reinterpret_cast<const uint4*>(ix.keys + b * BUCKET_KEYS);
   BucketRegs r;
-  r.a = __ldg(p);
-  r.b = __ldg(p + 1);
+#pragma unroll
+  for (int i = 0; i < BUCKET_KEYS / 2; ++i) r.q[i] = __ldg(p + i);
   return r;
 }
 
-// 0..3: position of h in the bucket; 4: bucket has an EMPTY key (definite miss); 5: full, keep probing
+// 0..BUCKET_KEYS-1: position of h; BUCKET_KEYS: the bucket has an EMPTY key (definite miss);
+// BUCKET_KEYS+1: full without a match, keep probing
 __device__ __forceinline__ int bucket_scan(const BucketRegs& r, uint64_t h) {
-  const uint64_t k0 = u64_of(r.a.x, r.a.y), k1 = u64_of(r.a.z, r.a.w);
-  const uint64_t k2 = u64_of(r.b.x, r.b.y), k3 = u64_of(r.b.z, r.b.w);
-  if (k0 == h) return 0;
-  if (k1 == h) return 1;
-  if (k2 == h) return 2;
-  if (k3 == h) return 3;
-  if (k0 == KEY_EMPTY || k1 == KEY_EMPTY || k2 == KEY_EMPTY || k3 == KEY_EMPTY) return 4;
-  return 5;
+  int pos = BUCKET_KEYS + 1;
+  bool empty = false;
+#pragma unroll
+  for (int i = BUCKET_KEYS / 2 - 1; i >= 0; --i) {
+    const uint64_t k0 = u64_of(r.q[i].x, r.q[i].y), k1 = u64_of(r.q[i].z, r.q[i].w);
+    empty |= (k0 == KEY_EMPTY) | (k1 == KEY_EMPTY);
+    if (k1 == h) pos = 2 * i + 1;
+    if (k0 == h) pos = 2 * i;
+  }
+  if (pos <= BUCKET_KEYS - 1) return pos;
+  return empty ? BUCKET_KEYS : BUCKET_KEYS + 1;
 }
 
 // finish a lookup whose home bucket was loaded into `first`
 __device__ __forceinline__ uint32_t index_resolve(const IndexView& ix, uint64_t h, const BucketRegs& first) {
   uint64_t b = h & ix.bmask;
   int j = bucket_scan(first, h);
-  if (j < 4) return (uint32_t)(b * BUCKET_KEYS + j);
-  if (j == 4) return SLOT_MISS;
+  if (j < BUCKET_KEYS) return (uint32_t)(b * BUCKET_KEYS + j);
+  if (j == BUCKET_KEYS) return SLOT_MISS;
   for (uint64_t it = 0; it < ix.bmask; ++it) {  // rare: home bucket full
     b = (b + 1) & ix.bmask;
     const BucketRegs r = bucket_load(ix, b);
     j = bucket_scan(r, h);
-    if (j < 4) return (uint32_t)(b * BUCKET_KEYS + j);
-    if (j == 4) return SLOT_MISS;
+    if (j < BUCKET_KEYS) return (uint32_t)(b * BUCKET_KEYS + j);
+    if (j == BUCKET_KEYS) return SLOT_MISS;
   }
   return SLOT_MISS;
 }

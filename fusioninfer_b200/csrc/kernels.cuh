@@ -2,7 +2,8 @@
 //
 // HBM layout (DESIGN.md "Data layout"):
 //   prompts   concatenated prompt bytes, request r = [offsets[r], offsets[r+1])
-//   pre       [R][MP] u64   block pre-states (hash_blocks → chain_finalize)
+//   pre       tiled u64     block pre-states (hash_blocks → chain_finalize): 16-byte unit u of
+//                           request r at ((r/32)*MP/2 + u)*32 + r%32 — coalesced for the chain walker
 //   chain     [R][MP] u64   chained block hashes h_1..h_n
 //   index     keys  [C+2]   u64, buckets of 4 keys = one 32 B sector; 0 = empty,
 //                           ~0 = tombstone; slots C, C+1 hold hashes 0 and ~0
@@ -21,14 +22,14 @@ namespace fi {
 constexpr uint32_t SLOT_MISS = 0xFFFFFFFFu;
 constexpr uint64_t KEY_EMPTY = 0ull;
 constexpr uint64_t KEY_TOMB = ~0ull;
-constexpr int BUCKET_KEYS = 4;
+constexpr int BUCKET_KEYS = 4;  // one 32-byte sector (64-byte buckets of 8 were measured slower: DESIGN.md)
 
 struct IndexView {
   uint64_t* keys;
   uint32_t* rows;
   uint32_t* cnt;
   uint64_t bmask;  // buckets - 1
-  uint64_t C;      // regular slots = buckets * 4
+  uint64_t C;      // regular slots = buckets * BUCKET_KEYS
   uint32_t W;      // words per row (power of two)
   uint32_t logW;
 };
@@ -113,14 +114,6 @@ cudaError_t launch_chain_finalize(const uint64_t* pre, const uint32_t* nblocks, 
 cudaError_t launch_hash_generic(const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
                                 uint32_t R, uint32_t B, uint32_t M, uint32_t MP, uint64_t* chain,
                                 uint32_t* nblocks, cudaStream_t s);
-
-// overlapped hashing: chunk-major producers + flag-waiting chain walker (hash_kernels.cu)
-bool hash_overlap_supported(uint32_t B);
-uint32_t hash_overlap_flag_words(uint32_t R, uint32_t M);
-cudaError_t launch_hash_chunks(const uint8_t* prompts, const uint64_t* offsets, uint32_t R, uint32_t B, uint32_t M,
-                               uint32_t MP, uint64_t* pre, uint32_t* nblocks, uint32_t* ready, cudaStream_t s);
-cudaError_t launch_chain_walk(const uint64_t* pre, const uint64_t* offsets, const uint64_t* h0, uint32_t R, uint32_t B,
-                              uint32_t M, uint32_t MP, const uint32_t* ready, uint64_t* chain, cudaStream_t s);
 
 cudaError_t launch_index_set(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n,
                              uint32_t ep_begin, uint32_t ep_count, cudaStream_t s);

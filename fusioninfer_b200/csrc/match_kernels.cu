@@ -25,6 +25,7 @@
 // endpoint-range shard of a multi-GPU pool) are read G = 32/L rows per load
 // instruction by G lane groups whose counters are merged at the end.
 #include <climits>
+#include <cstdlib>
 
 #include "bitslice.cuh"
 #include "index_device.cuh"
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
   const IndexView ix = p.ix;
   const uint32_t P = p.st.n_profiles;
   const uint32_t* row_base = ix.rows + t * VEC;
+  const uint32_t zero_slot = (uint32_t)(ix.C + 2);  // never written: all-zero row
 
   // dynamic work queue (requests differ a lot in how many rows they touch); the next item is
   // fetched while the current one is processed so the atomic's round trip is off the critical path
@@ -183,8 +185,8 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
       uint64_t hn = 0;
       bool validn = false, plain = false;
       BucketRegs brn;
-      brn.a = make_uint4(0, 0, 0, 0);
-      brn.b = brn.a;
+#pragma unroll
+      for (int qq = 0; qq < BUCKET_KEYS / 2; ++qq) brn.q[qq] = make_uint4(0, 0, 0, 0);
       if (!stop && c + 1 < nchunks) {
         const uint32_t idx = (c + 1) * 32 + lane;
         validn = idx < kg;
@@ -204,10 +206,11 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
 #pragma unroll
         for (int qi = 0; qi < BATCH; ++qi) {
           const int j = (q0 + qi) * G + g;  // row of the chunk this lane helps read
-          const uint32_t s = __shfl_sync(FULL, slot, j & 31);
-          const bool ok = (uint32_t)j < rows_here && s != SLOT_MISS;
+          uint32_t s = __shfl_sync(FULL, slot, j & 31);
+          // rows past the first miss read the permanently-zero row instead of being predicated off
+          if ((uint32_t)j >= rows_here || s == SLOT_MISS) s = zero_slot;
           uint32_t tmp[VEC];
-          load_row_words<VEC>(row_base + ((uint64_t)s << ix.logW), ok, tmp);
+          load_row_words<VEC>(row_base + ((uint64_t)s << ix.logW), true, tmp);
 #pragma unroll
           for (int x = 0; x < VEC; ++x) w[x][qi] = tmp[x];
         }
@@ -216,10 +219,6 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
           // home bucket costs a second dependent sector read; it overlaps the row latency)
           if (validn) slot_next = plain ? index_resolve(ix, hn, brn) : index_find(ix, hn);
           resolved = true;
-          // the next chunk's rows start moving towards L2 a whole chunk ahead of their loads
-#ifdef FI_MATCH_PREFETCH_ROWS
-          if (slot_next != SLOT_MISS) prefetch_l2(ix.rows + ((uint64_t)slot_next << ix.logW));
-#endif
         }
         if (LPM) {
 #pragma unroll
@@ -244,7 +243,14 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
           }
         }
 #pragma unroll
-        for (int x = 0; x < VEC; ++x) bc_add<BATCH>(cnt[x], w[x]);
+        for (int x = 0; x < VEC; ++x) {
+          // membership rows are sparse: most 32-endpoint words of a batch are zero for every lane,
+          // and adding zeros is a no-op — skip the carry-save tree then (warp-uniform branch)
+          uint32_t any = 0;
+#pragma unroll
+          for (int qi = 0; qi < BATCH; ++qi) any |= w[x][qi];
+          if (__any_sync(FULL, any != 0)) bc_add<BATCH>(cnt[x], w[x]);
+        }
       }
       if (!resolved && validn) slot_next = plain ? index_resolve(ix, hn, brn) : index_find(ix, hn);
       matched_rows += rows_here;
@@ -259,7 +265,8 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
     }
 
     // ---- merge the lane groups' counters ---------------------------------------
-    if (G > 1) {
+    const bool nothing = matched_rows == 0;  // warp-uniform: no row was read, every counter is zero
+    if (G > 1 && !nothing) {
 #pragma unroll
       for (int x = 0; x < VEC; ++x) {
 #pragma unroll
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
         b.score = -1.0;
         b.e = FI_NO_ENDPOINT;
         b.m = 0;
-        if (g == 0) {
+        if (g == 0 && !nothing) {
 #pragma unroll
           for (int x = 0; x < VEC; ++x) {
             const uint32_t wi = t * VEC + x;
@@ -302,15 +309,17 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
             }
           }
         }
+        if (!nothing) {
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          const double os = __shfl_xor_sync(FULL, b.score, d);
-          const uint32_t oe = __shfl_xor_sync(FULL, b.e, d);
-          const uint32_t om = __shfl_xor_sync(FULL, b.m, d);
-          if (better(os, oe, b)) {
-            b.score = os;
-            b.e = oe;
-            b.m = om;
+          for (int d = 16; d > 0; d >>= 1) {
+            const double os = __shfl_xor_sync(FULL, b.score, d);
+            const uint32_t oe = __shfl_xor_sync(FULL, b.e, d);
+            const uint32_t om = __shfl_xor_sync(FULL, b.m, d);
+            if (better(os, oe, b)) {
+              b.score = os;
+              b.e = oe;
+              b.m = om;
+            }
           }
         }
         const ZeroBest zb = p.st.zero[pi];
@@ -570,7 +579,12 @@ cudaError_t launch_match_pick(const MatchParams& p, int sm_count, cudaStream_t s
     case 4: return launch_match_t<1, 4>(p, sm_count, s);
     case 8: return launch_match_t<2, 4>(p, sm_count, s);
     case 16: return launch_match_t<4, 4>(p, sm_count, s);
-    case 32: return launch_match_t<8, 4>(p, sm_count, s);
+    case 32: {  // E = 1024: lanes-per-row x words-per-lane is a tuning choice (FI_EPP_MATCH_VEC)
+      static const int vec = [] { const char* e = std::getenv("FI_EPP_MATCH_VEC"); return e ? std::atoi(e) : 4; }();
+      if (vec == 1) return launch_match_t<32, 1>(p, sm_count, s);
+      if (vec == 2) return launch_match_t<16, 2>(p, sm_count, s);
+      return launch_match_t<8, 4>(p, sm_count, s);
+    }
     case 64: return launch_match_t<16, 4>(p, sm_count, s);
     case 128: return launch_match_t<32, 4>(p, sm_count, s);
     default: return cudaErrorInvalidValue;

@@ -114,7 +114,7 @@ typedef struct fi_epp_config {
   uint32_t max_batch;  /* largest R accepted by one pick/hash call */
   uint32_t reserved0;
   uint64_t max_prompt_bytes; /* largest total prompt bytes per call (device staging) */
-  uint64_t index_slots;      /* key slots of the GPU index, power of two; 0 = 2x endpoint_count*lru_capacity */
+  uint64_t index_slots;      /* key slots of the GPU index, power of two; 0 = 2x endpoint_count*lru_capacity (load <= 0.5) */
   uint32_t n_profiles;
   uint32_t pd_enabled;        /* pd-profile-handler present (strategy.go:129-133) */
   uint32_t pd_decode_profile; /* profile index run first */
