@@ -549,8 +549,8 @@ int epo_hash_batch(void* h, const uint8_t* prompts, const uint64_t* offsets, con
 
 // The whole path for R requests; requests are sharded over `nthreads` host
 // threads (the index is read-only during a batch).  out: R*n_profiles picks.
-int epo_pick_batch(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
-                   fi_pick* out, uint64_t* chains_out, uint32_t nthreads) {
+static int pick_batch_impl(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
+                           fi_pick* out, uint64_t* chains_out, uint32_t nthreads, uint32_t repeat) {
   Oracle* o = (Oracle*)h;
   const uint32_t P = o->cfg.n_profiles;
   std::vector<ProfileCtx> ctx(P);
@@ -559,10 +559,11 @@ int epo_pick_batch(void* h, const uint8_t* prompts, const uint64_t* offsets, con
   if (nthreads > R) nthreads = R ? R : 1;
   auto work = [&](uint32_t lo, uint32_t hi) {
     Scratch sc;
-    for (uint32_t r = lo; r < hi; ++r) {
-      pick_one(*o, ctx, prompts + offsets[r], offsets[r + 1] - offsets[r], h0[r], out + (size_t)r * P,
-               chains_out ? chains_out + (size_t)r * o->cfg.max_blocks : nullptr, sc);
-    }
+    for (uint32_t rep = 0; rep < repeat; ++rep)
+      for (uint32_t r = lo; r < hi; ++r) {
+        pick_one(*o, ctx, prompts + offsets[r], offsets[r + 1] - offsets[r], h0[r], out + (size_t)r * P,
+                 chains_out ? chains_out + (size_t)r * o->cfg.max_blocks : nullptr, sc);
+      }
   };
   if (nthreads == 1) {
     work(0, R);
@@ -577,6 +578,18 @@ int epo_pick_batch(void* h, const uint8_t* prompts, const uint64_t* offsets, con
   }
   for (auto& t : th) t.join();
   return FI_OK;
+}
+
+int epo_pick_batch(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
+                   fi_pick* out, uint64_t* chains_out, uint32_t nthreads) {
+  return pick_batch_impl(h, prompts, offsets, h0, R, out, chains_out, nthreads, 1);
+}
+
+// Timing variant: every thread processes its shard `repeat` times (same results), so that thread
+// start-up does not dominate a bounded sample on a many-core host.  Decisions = R * repeat.
+int epo_pick_batch_repeat(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
+                          fi_pick* out, uint32_t nthreads, uint32_t repeat) {
+  return pick_batch_impl(h, prompts, offsets, h0, R, out, nullptr, nthreads, repeat ? repeat : 1);
 }
 
 }  // extern "C"

@@ -54,6 +54,8 @@ def load() -> C.CDLL:
     lib.epo_hash_batch.argtypes = [_P, _P, _P, _P, C.c_uint32, _P, _P]
     lib.epo_pick_batch.restype = C.c_int
     lib.epo_pick_batch.argtypes = [_P, _P, _P, _P, C.c_uint32, _P, _P, C.c_uint32]
+    lib.epo_pick_batch_repeat.restype = C.c_int
+    lib.epo_pick_batch_repeat.argtypes = [_P, _P, _P, _P, C.c_uint32, _P, C.c_uint32, C.c_uint32]
     _lib = lib
     return lib
 
@@ -136,3 +138,11 @@ class Oracle:
         rc = self._lib.epo_pick_batch(self._h, _ptr(prompts), _ptr(offsets), _ptr(h0), R, _ptr(picks), _ptr(chains), nthreads)
         assert rc == 0, rc
         return (picks, chains) if want_chains else picks
+
+    def pick_batch_repeat(self, prompts, offsets, h0, nthreads=1, repeat=1):
+        """Timing helper: each thread walks its shard `repeat` times; returns the picks."""
+        prompts, offsets, h0, R = self._inputs(prompts, offsets, h0)
+        picks = np.zeros((R, self.P), dtype=PICK_DTYPE)
+        rc = self._lib.epo_pick_batch_repeat(self._h, _ptr(prompts), _ptr(offsets), _ptr(h0), R, _ptr(picks), nthreads, repeat)
+        assert rc == 0, rc
+        return picks
