@@ -241,6 +241,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the pick path has no CPU fallback (use --impl reference "
                          "for the CPU arm)")
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         fdist.init_process_group("nccl")
     torch.cuda.set_device(local)
 
@@ -335,7 +338,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     dom = max(("hash_blocks", "match_pick"), key=lambda k: avg_ms[k])
     achieved = alg[dom] / (avg_ms[dom] * 1e-3) / 1e9 if avg_ms[dom] else 0.0
-    traffic = load_traffic()
+    traffic = load_traffic() if (cfg_id == 3 and mode == "replicas" and args.scale == 1.0) else {}  # captured for cfg 3 only
     step_alg = alg["hash_blocks"] + alg["match_pick"]
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
