@@ -1,6 +1,6 @@
 // engine.cu — host side of libfi_epp: the C ABI of include/fi_epp.h.
 //
-// Owns the device buffers, three CUDA streams (compute, index maintenance, copies),
+// Owns the device buffers, two CUDA streams (compute, index maintenance),
 // the pinned op ring that keeps the GPU index live (async H2D on the side stream,
 // ordered before the next pick), the host LRU, the per-batch score tables, and the
 // optional NCCL communicator for endpoint-range sharded pools.  No CPU fallback:
@@ -82,9 +82,6 @@ struct PairHash {
 };
 
 constexpr uint64_t kOpChunk = 1ull << 20;  // ops per pinned staging buffer
-constexpr uint32_t kSubBatch = 0;        // requests per pipeline slice; 0 = off (measured slower: chain_finalize is a
-                                         // flat ~45 us at any size and small slices pay launch/ramp overheads)
-constexpr uint32_t kMaxSub = 16;         // slices per call (one work counter each)
 
 enum KernelKind { K_HASH = 0, K_CHAIN = 1, K_MATCH = 2, K_INDEX = 3, K_OTHER = 4, K_KINDS = 5 };
 
@@ -111,11 +108,8 @@ struct fi_epp {
   uint32_t P = 0;   // profiles
   bool fast_hash = false;
 
-  cudaStream_t s_main = nullptr, s_index = nullptr, s_copy = nullptr;
-  cudaStream_t s_hash = nullptr, s_chain = nullptr, s_match = nullptr;  // pipeline streams, by kernel type
-  cudaEvent_t ev_fork = nullptr, ev_join[1] = {nullptr};
-  cudaEvent_t ev_h[16] = {}, ev_c[16] = {};
-  cudaEvent_t ev_index = nullptr, ev_user = nullptr, ev_done = nullptr, ev_ctr = nullptr, ev_copy = nullptr;
+  cudaStream_t s_main = nullptr, s_index = nullptr;  // compute; index maintenance (side stream)
+  cudaEvent_t ev_index = nullptr, ev_user = nullptr, ev_done = nullptr, ev_ctr = nullptr;
 
   // request buffers (device)
   uint8_t* d_prompts = nullptr;
@@ -447,7 +441,6 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
     // (A sub-batch pipeline over several streams was tried and measured slower — DESIGN.md
     // "What did not work": chain walking costs a flat ~45 us at any batch size and small
     // slices pay launch/ramp overheads.  The overlap now lives inside run_hash.)
-    const uint32_t nsub = 1;
     rc = run_hash(h, d_prompts, d_offsets, d_h0, 0, R, h->s_main);
     if (rc != FI_OK) return rc;
     {
@@ -457,7 +450,7 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
     if (h->tracing) {
       static const char* names[] = {"hash_blocks", "chain_finalize", "match_pick", "index", "other"};
       cudaStreamSynchronize(h->s_main);
-      std::fprintf(stderr, "[fi_epp trace] call %ld: R=%u slices=%u\n", h->trace_call, R, nsub);
+      std::fprintf(stderr, "[fi_epp trace] call %ld: R=%u\n", h->trace_call, R);
       for (auto& e : h->pending_ev) {
         float t0 = 0.f, t1 = 0.f;
         cudaEventSynchronize(e.b);
@@ -627,7 +620,6 @@ void fi_epp_destroy(fi_epp* h) {
   cudaSetDevice(h->cfg.device);
   if (h->s_main) cudaStreamSynchronize(h->s_main);
   if (h->s_index) cudaStreamSynchronize(h->s_index);
-  if (h->s_copy) cudaStreamSynchronize(h->s_copy);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   drain_profile(h);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -662,20 +654,9 @@ void fi_epp_destroy(fi_epp* h) {
   if (h->h_h0) cudaFreeHost(h->h_h0);
   if (h->h_nblocks) cudaFreeHost(h->h_nblocks);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
-  for (cudaEvent_t e : {h->ev_index, h->ev_user, h->ev_done, h->ev_ctr, h->ev_copy})
+  for (cudaEvent_t e : {h->ev_index, h->ev_user, h->ev_done, h->ev_ctr})
     if (e) cudaEventDestroy(e);
-  for (cudaStream_t s : {h->s_hash, h->s_chain, h->s_match})
-    if (s) {
-      cudaStreamSynchronize(s);
-      cudaStreamDestroy(s);
-    }
-  for (uint32_t i = 0; i < kMaxSub; ++i) {
-    if (h->ev_h[i]) cudaEventDestroy(h->ev_h[i]);
-    if (h->ev_c[i]) cudaEventDestroy(h->ev_c[i]);
-  }
-  if (h->ev_join[0]) cudaEventDestroy(h->ev_join[0]);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  for (cudaStream_t s : {h->s_main, h->s_index, h->s_copy})
+  for (cudaStream_t s : {h->s_main, h->s_index})
     if (s) cudaStreamDestroy(s);
   delete h;
 }
@@ -736,25 +717,9 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
 
   FI_TRY(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
   FI_TRY(cudaStreamCreateWithFlags(&h->s_index, cudaStreamNonBlocking));
-  FI_TRY(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-  for (cudaEvent_t* e : {&h->ev_index, &h->ev_user, &h->ev_done, &h->ev_ctr, &h->ev_copy})
+  for (cudaEvent_t* e : {&h->ev_index, &h->ev_user, &h->ev_done, &h->ev_ctr})
     FI_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   FI_TRY(cudaEventRecord(h->ev_index, h->s_index));
-  FI_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  FI_TRY(cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming));
-  {
-    int lo = 0, hi = 0;  // numerically lower = higher priority
-    FI_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    const int mid = (lo + hi) / 2;
-    FI_TRY(cudaStreamCreateWithPriority(&h->s_hash, cudaStreamNonBlocking, lo));
-    FI_TRY(cudaStreamCreateWithPriority(&h->s_match, cudaStreamNonBlocking, mid));
-    FI_TRY(cudaStreamCreateWithPriority(&h->s_chain, cudaStreamNonBlocking, hi));
-  }
-  for (uint32_t i = 0; i < kMaxSub; ++i) {
-    FI_TRY(cudaEventCreateWithFlags(&h->ev_h[i], cudaEventDisableTiming));
-    FI_TRY(cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming));
-  }
-
   const uint64_t R = cfg->max_batch;
   const uint32_t mask_words = (h->MP + 31) / 32;
   FI_TRY(cudaMalloc(&h->d_prompts, h->cfg.max_prompt_bytes + 64));
