@@ -7,6 +7,7 @@ weighted fp64 score → argmax, behind the C ABI of include/fi_epp.h.
 from . import _abi  # noqa: F401
 from .picker import (  # noqa: F401
     ENDPOINT_DTYPE,
+    LORA_DTYPE,
     OP_DTYPE,
     PICK_DTYPE,
     EndpointPicker,
@@ -29,4 +30,5 @@ __all__ = [
     "PICK_DTYPE",
     "OP_DTYPE",
     "ENDPOINT_DTYPE",
+    "LORA_DTYPE",
 ]

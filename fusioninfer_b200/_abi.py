@@ -92,6 +92,20 @@ class fi_endpoint_state(C.Structure):
     ]
 
 
+FI_EPP_MAX_LORA = 8
+
+
+class fi_endpoint_lora(C.Structure):
+    _fields_ = [
+        ("endpoint", C.c_uint32),
+        ("max_active", C.c_uint32),
+        ("n_active", C.c_uint32),
+        ("n_waiting", C.c_uint32),
+        ("active", C.c_uint64 * FI_EPP_MAX_LORA),
+        ("waiting", C.c_uint64 * FI_EPP_MAX_LORA),
+    ]
+
+
 class fi_index_op(C.Structure):
     _fields_ = [("hash", C.c_uint64), ("endpoint", C.c_uint32), ("op", C.c_uint32)]
 
@@ -155,6 +169,15 @@ def np_dtypes():
     return pick, op, ep
 
 
+def lora_dtype():
+    import numpy as np
+
+    dt = np.dtype([("endpoint", "<u4"), ("max_active", "<u4"), ("n_active", "<u4"), ("n_waiting", "<u4"),
+                   ("active", "<u8", (FI_EPP_MAX_LORA,)), ("waiting", "<u8", (FI_EPP_MAX_LORA,))], align=True)
+    assert dt.itemsize == C.sizeof(fi_endpoint_lora) == 144
+    return dt
+
+
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libfi_epp.so")
 
@@ -170,6 +193,7 @@ SYMBOLS = [
     ("fi_epp_last_error", C.c_char_p, [_P]),
     ("fi_epp_model_seed", C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_uint64)]),
     ("fi_epp_endpoints_update", C.c_int, [_P, _P, C.c_uint32]),
+    ("fi_epp_endpoints_lora_update", C.c_int, [_P, _P, C.c_uint32]),
     ("fi_epp_index_apply", C.c_int, [_P, _P, C.c_uint64]),
     ("fi_epp_index_add_chain", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
     ("fi_epp_index_sync", C.c_int, [_P]),
@@ -178,6 +202,8 @@ SYMBOLS = [
     ("fi_epp_hash_batch", C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, _P]),
     ("fi_epp_pick_batch", C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, _P]),
     ("fi_epp_pick_batch_device", C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint64, _P, _P, _P]),
+    ("fi_epp_pick_batch_lora", C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, _P, _P]),
+    ("fi_epp_pick_batch_device_lora", C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, C.c_uint64, _P, _P, _P]),
     ("fi_epp_pinned_alloc", _P, [C.c_size_t]),
     ("fi_epp_pinned_free", None, [_P]),
     ("fi_epp_comm_unique_id", C.c_int, [_P]),

@@ -154,6 +154,11 @@ struct fi_epp {
   double* d_sc = nullptr;
   uint32_t* d_elig = nullptr;
   ZeroBest* d_zero = nullptr;
+  std::vector<LoraDev> lora;   // local endpoints' adapter residency (lora-affinity-scorer)
+  bool lora_dirty = false;
+  LoraDev* d_lora = nullptr;
+  uint64_t* d_adapters = nullptr;  // staging of the host path's per-request adapter ids
+  uint64_t* h_adapters = nullptr;  // pinned
   ScoreTables st{};
 
   // multi-GPU
@@ -370,6 +375,14 @@ int upload_endpoints(fi_epp* h) {
   return FI_OK;
 }
 
+int upload_lora(fi_epp* h) {
+  if (!h->lora_dirty) return FI_OK;
+  FI_CUDA(cudaMemcpyAsync(h->d_lora, h->lora.data(), h->lora.size() * sizeof(LoraDev), cudaMemcpyHostToDevice, h->s_main));
+  h->stats.h2d_bytes += h->lora.size() * sizeof(LoraDev);
+  h->lora_dirty = false;
+  return FI_OK;
+}
+
 // hash kernels for the request slice [r0, r0+R): prompts → chain (device buffers), on stream s
 int run_hash(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0, uint32_t r0,
              uint32_t R, cudaStream_t s) {
@@ -399,8 +412,8 @@ int nccl_allgather(fi_epp* h, const void* send, void* recv, size_t bytes) {
 }
 
 // the whole pick on device buffers; result in d_out ([R][P])
-int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0, uint32_t R,
-             fi_pick* d_out) {
+int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0,
+             const uint64_t* d_adapters, uint32_t R, fi_pick* d_out) {
   int rc = flush_ops(h);
   if (rc != FI_OK) return rc;
   rc = check_counters(h);
@@ -414,11 +427,14 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
   FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_index, 0));  // every submitted op is visible
   rc = upload_endpoints(h);
   if (rc != FI_OK) return rc;
+  rc = upload_lora(h);
+  if (rc != FI_OK) return rc;
   const bool sharded = h->world > 1;
   MatchParams mp{};
   mp.chain = h->d_chain;
   mp.nblocks = h->d_nblocks;
   mp.offsets = d_offsets;
+  mp.adapters = d_adapters;
   mp.R = R;
   mp.MP = h->MP;
   mp.ix = h->ix;
@@ -531,8 +547,8 @@ int validate_config(const fi_epp_config& c, std::string* err) {
     if (c.profiles[p].n_scorers > FI_EPP_MAX_SCORERS) return bad("n_scorers out of range");
     for (uint32_t s = 0; s < c.profiles[p].n_scorers; ++s) {
       const uint32_t k = c.profiles[p].scorers[s].kind;
-      if (k == FI_SCORER_LORA) return bad("lora-affinity-scorer is not implemented yet (SURVEY.md §8f)");
-      if (k != FI_SCORER_PREFIX && k != FI_SCORER_KV_UTIL && k != FI_SCORER_QUEUE) return bad("unknown scorer kind");
+      if (k != FI_SCORER_PREFIX && k != FI_SCORER_KV_UTIL && k != FI_SCORER_QUEUE && k != FI_SCORER_LORA)
+        return bad("unknown scorer kind");
       if (c.profiles[p].scorers[s].weight < 0) return bad("scorer weights must be >= 0");
     }
   }
@@ -641,6 +657,9 @@ void fi_epp_destroy(fi_epp* h) {
   cudaFree(h->d_sc);
   cudaFree(h->d_elig);
   cudaFree(h->d_zero);
+  cudaFree(h->d_lora);
+  cudaFree(h->d_adapters);
+  if (h->h_adapters) cudaFreeHost(h->h_adapters);
   free_index(h->ix);
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->d_sets[b]);
@@ -772,6 +791,16 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   h->st.sc = h->d_sc;
   h->st.elig = h->d_elig;
   h->st.zero = h->d_zero;
+  h->lora.assign(Epad, LoraDev{});
+  FI_TRY(cudaMalloc(&h->d_lora, (size_t)Epad * sizeof(LoraDev)));
+  FI_TRY(cudaMemset(h->d_lora, 0, (size_t)Epad * sizeof(LoraDev)));
+  FI_TRY(cudaMalloc(&h->d_adapters, R * sizeof(uint64_t)));
+  FI_TRY(cudaMallocHost(&h->h_adapters, R * sizeof(uint64_t)));
+  h->st.lora = h->d_lora;
+  h->st.has_lora = 0;
+  for (uint32_t p = 0; p < h->P; ++p)
+    for (uint32_t s = 0; s < cfg->profiles[p].n_scorers; ++s)
+      if (cfg->profiles[p].scorers[s].kind == FI_SCORER_LORA) h->st.has_lora = 1;
   for (uint32_t p = 0; p < h->P; ++p) {
     ProfileDev& d = h->st.prof[p];
     d.n_scorers = cfg->profiles[p].n_scorers;
@@ -803,6 +832,29 @@ int fi_epp_endpoints_update(fi_epp* h, const fi_endpoint_state* s, uint32_t n) {
     e.flags = s[i].flags;
   }
   h->eps_dirty = true;
+  return FI_OK;
+}
+
+int fi_epp_endpoints_lora_update(fi_epp* h, const fi_endpoint_lora* s, uint32_t n) {
+  if (!h || (!s && n)) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (s[i].endpoint >= h->cfg.num_endpoints) return fail(h, FI_ERR_INVALID, "endpoint index out of range");
+    if (s[i].n_active > FI_EPP_MAX_LORA || s[i].n_waiting > FI_EPP_MAX_LORA)
+      return fail(h, FI_ERR_INVALID, "more than FI_EPP_MAX_LORA adapters listed");
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t e = s[i].endpoint - h->cfg.endpoint_begin;
+    if (e >= h->cfg.endpoint_count) continue;  // another rank's shard
+    LoraDev& d = h->lora[e];
+    std::memset(&d, 0, sizeof(d));
+    d.n_active = s[i].n_active;
+    d.n_waiting = s[i].n_waiting;
+    d.max_active = s[i].max_active;
+    for (uint32_t k = 0; k < s[i].n_active; ++k) d.active[k] = s[i].active[k];
+    for (uint32_t k = 0; k < s[i].n_waiting; ++k) d.waiting[k] = s[i].waiting[k];
+  }
+  h->lora_dirty = true;
   return FI_OK;
 }
 
@@ -848,7 +900,9 @@ int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes,
       if (rc != FI_OK) return rc;
     }
   }
-  return flush_ops(h);
+  // the deltas stay staged: they are launched when the staging buffer fills and, at the latest,
+  // by the next pick / sync (one launch group per batch of decisions instead of one per chain)
+  return FI_OK;
 }
 
 int fi_epp_index_sync(fi_epp* h) {
@@ -965,6 +1019,11 @@ int fi_epp_hash_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets
 
 int fi_epp_pick_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
                       fi_pick* out, uint64_t* chains_out) {
+  return fi_epp_pick_batch_lora(h, prompts, offsets, h0, nullptr, R, out, chains_out);
+}
+
+int fi_epp_pick_batch_lora(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
+                           const uint64_t* adapters, uint32_t R, fi_pick* out, uint64_t* chains_out) {
   if (!h || !offsets || (!h0 && R) || (!out && R) || (!prompts && R && offsets[R])) return FI_ERR_INVALID;
   std::lock_guard<std::mutex> lk(h->mu);
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
@@ -974,7 +1033,12 @@ int fi_epp_pick_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets
   if (rc != FI_OK) return rc;
   rc = stage_inputs(h, prompts, offsets, h0, R, total);
   if (rc != FI_OK) return rc;
-  rc = run_pick(h, h->d_prompts, h->d_offsets, h->d_h0, R, h->d_picks);
+  if (adapters) {
+    std::memcpy(h->h_adapters, adapters, (size_t)R * sizeof(uint64_t));
+    FI_CUDA(cudaMemcpyAsync(h->d_adapters, h->h_adapters, (size_t)R * sizeof(uint64_t), cudaMemcpyHostToDevice, h->s_main));
+    h->stats.h2d_bytes += (size_t)R * sizeof(uint64_t);
+  }
+  rc = run_pick(h, h->d_prompts, h->d_offsets, h->d_h0, adapters ? h->d_adapters : nullptr, R, h->d_picks);
   if (rc != FI_OK) return rc;
   const size_t pb = (size_t)R * h->P * sizeof(fi_pick);
   FI_CUDA(cudaMemcpyAsync(h->h_picks, h->d_picks, pb, cudaMemcpyDeviceToHost, h->s_main));
@@ -990,6 +1054,13 @@ int fi_epp_pick_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets
 
 int fi_epp_pick_batch_device(fi_epp* h, const void* d_prompts, const void* d_offsets, const void* d_h0, uint32_t R,
                              uint64_t total_prompt_bytes, void* d_out, void* d_chains_out, void* stream) {
+  return fi_epp_pick_batch_device_lora(h, d_prompts, d_offsets, d_h0, nullptr, R, total_prompt_bytes, d_out, d_chains_out,
+                                       stream);
+}
+
+int fi_epp_pick_batch_device_lora(fi_epp* h, const void* d_prompts, const void* d_offsets, const void* d_h0,
+                                  const void* d_adapters, uint32_t R, uint64_t total_prompt_bytes, void* d_out,
+                                  void* d_chains_out, void* stream) {
   if (!h || !d_offsets || (!d_h0 && R) || (!d_out && R)) return FI_ERR_INVALID;
   std::lock_guard<std::mutex> lk(h->mu);
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
@@ -999,7 +1070,8 @@ int fi_epp_pick_batch_device(fi_epp* h, const void* d_prompts, const void* d_off
   cudaStream_t us = (cudaStream_t)stream;
   FI_CUDA(cudaEventRecord(h->ev_user, us));
   FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_user, 0));
-  int rc = run_pick(h, (const uint8_t*)d_prompts, (const uint64_t*)d_offsets, (const uint64_t*)d_h0, R, (fi_pick*)d_out);
+  int rc = run_pick(h, (const uint8_t*)d_prompts, (const uint64_t*)d_offsets, (const uint64_t*)d_h0,
+                    (const uint64_t*)d_adapters, R, (fi_pick*)d_out);
   if (rc != FI_OK) return rc;
   if (d_chains_out) {
     rc = copy_chains_out(h, (uint64_t*)d_chains_out, R, cudaMemcpyDeviceToDevice, h->s_main);

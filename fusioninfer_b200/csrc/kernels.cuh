@@ -64,6 +64,12 @@ struct EndpointDev {  // raw state of one endpoint of the GLOBAL pool
   uint32_t pad;
 };
 
+struct LoraDev {  // adapter residency of one LOCAL endpoint (lora-affinity-scorer)
+  uint64_t active[FI_EPP_MAX_LORA];
+  uint64_t waiting[FI_EPP_MAX_LORA];
+  uint32_t n_active, n_waiting, max_active, pad;
+};
+
 struct ScoreTables {
   ProfileDev prof[FI_EPP_MAX_PROFILES];
   uint32_t n_profiles;
@@ -71,12 +77,16 @@ struct ScoreTables {
   const double* sc;     // [P][S][Epad] clamp01'd per-endpoint scores of the non-prefix scorers
   const uint32_t* elig; // [P][W] eligibility bit words
   const ZeroBest* zero; // [P]
+  const LoraDev* lora;  // [Epad] or null
+  uint32_t has_lora;    // some profile has a lora-affinity-scorer: scores depend on the request's adapter,
+  uint32_t pad;         // so every eligible endpoint is scored per request (no zero-match shortcut)
 };
 
 struct MatchParams {
   const uint64_t* chain;
   const uint32_t* nblocks;
   const uint64_t* offsets;  // [R+1], prompt byte offsets (PD threshold); may be null if !apply_pd
+  const uint64_t* adapters; // [R] target adapter id per request, or null (= id 0)
   uint32_t R;
   uint32_t MP;  // pitch of chain rows (multiple of 4)
   IndexView ix;

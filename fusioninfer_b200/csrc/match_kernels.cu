@@ -52,8 +52,22 @@ __device__ __forceinline__ bool better(double s, uint32_t e, const Best& b) {
 }
 
 // SURVEY.md Appendix A.4 — identical operation order to oracle/epp_oracle.cpp:total_score
+// upstream lora-affinity-scorer: adapter active on the endpoint 1.0, endpoint
+// has room for one more adapter 0.8, adapter queued there 0.6, else 0
+__device__ __forceinline__ double lora_score(const LoraDev& l, uint64_t adapter) {
+  bool active = false, waiting = false;
+#pragma unroll
+  for (int i = 0; i < (int)FI_EPP_MAX_LORA; ++i) {
+    active |= (uint32_t)i < l.n_active && l.active[i] == adapter;
+    waiting |= (uint32_t)i < l.n_waiting && l.waiting[i] == adapter;
+  }
+  if (active) return 1.0;
+  if (l.n_active + l.n_waiting < l.max_active) return 0.8;
+  return waiting ? 0.6 : 0.0;
+}
+
 __device__ __forceinline__ double total_score(const ProfileDev& pr, const double* __restrict__ sc_p, uint32_t Epad,
-                                              uint32_t e, uint32_t m, uint32_t n) {
+                                              uint32_t e, uint32_t m, uint32_t n, double lora_v = 0.0) {
   double total = 0.0;
 #pragma unroll
   for (int s = 0; s < (int)FI_EPP_MAX_SCORERS; ++s) {
@@ -61,6 +75,8 @@ __device__ __forceinline__ double total_score(const ProfileDev& pr, const double
       double v;
       if (pr.kind[s] == FI_SCORER_PREFIX)
         v = n ? __ddiv_rn((double)m, (double)n) : 0.0;
+      else if (pr.kind[s] == FI_SCORER_LORA)
+        v = lora_v;
       else
         v = sc_p[(uint64_t)s * Epad + e];
       total = __dadd_rn(total, __dmul_rn(v, pr.weight[s]));
@@ -108,7 +124,7 @@ __device__ __forceinline__ void load_row_words(const uint32_t* __restrict__ p, b
 // LPR lanes read one row (VEC words each, LPR*VEC = words per row); a load
 // instruction therefore covers G = 32/LPR rows.  E = 1024 → LPR 8, VEC 4: a 128-byte
 // row is 8 × 16-byte loads and one instruction brings in 4 rows; 32 rows in flight.
-template <int LPR, int VEC, bool LPM, bool GMASK>
+template <int LPR, int VEC, bool LPM, bool GMASK, bool LORA>
 __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_kernel(const MatchParams p) {
   constexpr int G = 32 / LPR;                 // rows per load instruction
   constexpr int BATCH = LPR < 8 ? LPR : 8;    // load instructions in flight
@@ -290,7 +306,31 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
         b.score = -1.0;
         b.e = FI_NO_ENDPOINT;
         b.m = 0;
-        if (g == 0 && !nothing) {
+        if (LORA) {
+          // The lora-affinity score depends on the request's adapter, so there is no per-batch
+          // zero-match best: score every eligible endpoint.  After the merge every lane group holds the
+          // full counters, so group g takes bits [g*32/G, (g+1)*32/G) of its lanes' words.
+          const uint64_t adapter = p.adapters ? p.adapters[r] : 0;
+          constexpr uint32_t BPG = 32 / G;
+          const uint32_t gmask_bits = (BPG >= 32 ? 0xFFFFFFFFu : ((1u << BPG) - 1u)) << (g * BPG);
+#pragma unroll
+          for (int x = 0; x < VEC; ++x) {
+            const uint32_t wi = t * VEC + x;
+            uint32_t cand = p.st.elig[(uint64_t)pi * ix.W + wi] & gmask_bits;
+            while (cand) {
+              const uint32_t bit = __ffs(cand) - 1;
+              cand &= cand - 1;
+              const uint32_t e = wi * 32 + bit;
+              const uint32_t m = bc_get(cnt[x], bit);
+              const double s = total_score(pr, sc_p, p.st.Epad, e, m, n, lora_score(p.st.lora[e], adapter));
+              if (better(s, e, b)) {
+                b.score = s;
+                b.e = e;
+                b.m = m;
+              }
+            }
+          }
+        } else if (g == 0 && !nothing) {
 #pragma unroll
           for (int x = 0; x < VEC; ++x) {
             const uint32_t wi = t * VEC + x;
@@ -309,7 +349,7 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
             }
           }
         }
-        if (!nothing) {
+        if (!nothing || LORA) {
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) {
             const double os = __shfl_xor_sync(FULL, b.score, d);
@@ -323,7 +363,7 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
           }
         }
         const ZeroBest zb = p.st.zero[pi];
-        if (zb.e_local != FI_NO_ENDPOINT && better(zb.score, zb.e_local, b)) {
+        if (!LORA && zb.e_local != FI_NO_ENDPOINT && better(zb.score, zb.e_local, b)) {
           b.score = zb.score;
           b.e = zb.e_local;
           b.m = 0;
@@ -565,8 +605,12 @@ cudaError_t launch_match_t(const MatchParams& p, int sm_count, cudaStream_t s) {
   };
   const bool lpm = p.lpm == FI_MATCH_LPM;
   const bool gm = p.gmask != nullptr;
-  if (lpm) return gm ? go(match_pick_kernel<LPR, VEC, true, true>) : go(match_pick_kernel<LPR, VEC, true, false>);
-  return gm ? go(match_pick_kernel<LPR, VEC, false, true>) : go(match_pick_kernel<LPR, VEC, false, false>);
+  if (p.st.has_lora) {
+    if (lpm) return gm ? go(match_pick_kernel<LPR, VEC, true, true, true>) : go(match_pick_kernel<LPR, VEC, true, false, true>);
+    return gm ? go(match_pick_kernel<LPR, VEC, false, true, true>) : go(match_pick_kernel<LPR, VEC, false, false, true>);
+  }
+  if (lpm) return gm ? go(match_pick_kernel<LPR, VEC, true, true, false>) : go(match_pick_kernel<LPR, VEC, true, false, false>);
+  return gm ? go(match_pick_kernel<LPR, VEC, false, true, false>) : go(match_pick_kernel<LPR, VEC, false, false, false>);
 }
 
 }  // namespace

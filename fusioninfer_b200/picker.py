@@ -17,6 +17,7 @@ import numpy as np
 from . import _abi as abi
 
 PICK_DTYPE, OP_DTYPE, ENDPOINT_DTYPE = abi.np_dtypes()
+LORA_DTYPE = abi.lora_dtype()
 
 
 class FiEppError(RuntimeError):
@@ -146,6 +147,12 @@ class EndpointPicker:
         states = np.ascontiguousarray(states, dtype=ENDPOINT_DTYPE)
         self._check(self._lib.fi_epp_endpoints_update(self._h, _ptr(states), len(states)), "fi_epp_endpoints_update")
 
+    def update_endpoints_lora(self, states: np.ndarray):
+        """Adapter residency per endpoint (LORA_DTYPE rows) for the lora-affinity-scorer."""
+        states = np.ascontiguousarray(states, dtype=LORA_DTYPE)
+        self._check(self._lib.fi_epp_endpoints_lora_update(self._h, _ptr(states), len(states)),
+                    "fi_epp_endpoints_lora_update")
+
     # -- prefix index --------------------------------------------------------
     def index_apply(self, ops: np.ndarray):
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
@@ -193,15 +200,19 @@ class EndpointPicker:
         )
         return chains, nb
 
-    def pick_batch(self, prompts, offsets, h0, want_chains: bool = False):
-        """Schedule R requests held in host memory.  -> picks [R, n_profiles] (PICK_DTYPE)[, chains]"""
+    def pick_batch(self, prompts, offsets, h0, want_chains: bool = False, adapters=None):
+        """Schedule R requests held in host memory.  -> picks [R, n_profiles] (PICK_DTYPE)[, chains]
+        adapters: optional [R] uint64 target adapter ids (lora-affinity-scorer)."""
         prompts, offsets, h0, R = self._inputs(prompts, offsets, h0)
         picks = np.zeros((R, self.n_profiles), dtype=PICK_DTYPE)
         chains = np.zeros((R, self.max_blocks), dtype=np.uint64) if want_chains else None
-        self._check(
-            self._lib.fi_epp_pick_batch(self._h, _ptr(prompts), _ptr(offsets), _ptr(h0), R, _ptr(picks), _ptr(chains)),
-            "fi_epp_pick_batch",
-        )
+        if adapters is None:
+            rc = self._lib.fi_epp_pick_batch(self._h, _ptr(prompts), _ptr(offsets), _ptr(h0), R, _ptr(picks), _ptr(chains))
+        else:
+            ad = np.ascontiguousarray(np.broadcast_to(np.asarray(adapters, dtype=np.uint64), (R,)))
+            rc = self._lib.fi_epp_pick_batch_lora(self._h, _ptr(prompts), _ptr(offsets), _ptr(h0), _ptr(ad), R,
+                                                  _ptr(picks), _ptr(chains))
+        self._check(rc, "fi_epp_pick_batch")
         return (picks, chains) if want_chains else picks
 
     def pick_batch_raw(self, prompts_ptr: int, offsets_ptr: int, h0_ptr: int, R: int, out_ptr: int, chains_ptr: int = 0):

@@ -132,6 +132,20 @@ typedef struct fi_endpoint_state {
   uint32_t flags;      /* FI_ENDPOINT_ALIVE */
 } fi_endpoint_state;
 
+/* LoRA adapters resident / queued on one endpoint (upstream pod metrics ActiveModels,
+ * WaitingModels, MaxActiveModels) — read by the lora-affinity-scorer
+ * (pkg/router/strategy.go:100-113).  Adapter ids are any 64-bit ids the host uses
+ * consistently, e.g. fi_epp_model_seed(adapter name). */
+#define FI_EPP_MAX_LORA 8u
+typedef struct fi_endpoint_lora {
+  uint32_t endpoint;   /* global index */
+  uint32_t max_active; /* MaxActiveModels */
+  uint32_t n_active;   /* <= FI_EPP_MAX_LORA */
+  uint32_t n_waiting;  /* <= FI_EPP_MAX_LORA */
+  uint64_t active[FI_EPP_MAX_LORA];
+  uint64_t waiting[FI_EPP_MAX_LORA];
+} fi_endpoint_lora;
+
 typedef enum fi_index_opcode { FI_OP_SET = 1, FI_OP_CLEAR = 2 } fi_index_opcode;
 
 /* One membership change of the logical index {(endpoint, block hash)}. */
@@ -198,6 +212,10 @@ int fi_epp_model_seed(const void* model, size_t model_len, const void* salt, siz
  * endpoints never listed are not alive. */
 int fi_epp_endpoints_update(fi_epp* h, const fi_endpoint_state* states, uint32_t n);
 
+/* Adapter residency of the listed endpoints (lora-affinity-scorer).  Endpoints never listed
+ * hold no adapter and have max_active 0. */
+int fi_epp_endpoints_lora_update(fi_epp* h, const fi_endpoint_lora* states, uint32_t n);
+
 /* Asynchronous, ordered: every op submitted before a pick call is visible to
  * that pick.  Ops for endpoints outside this handle's shard are ignored. */
 int fi_epp_index_apply(fi_epp* h, const fi_index_op* ops, uint64_t n);
@@ -231,6 +249,15 @@ int fi_epp_pick_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets
 int fi_epp_pick_batch_device(fi_epp* h, const void* d_prompts, const void* d_offsets, const void* d_h0,
                              uint32_t R, uint64_t total_prompt_bytes, void* d_out, void* d_chains_out,
                              void* stream);
+
+/* The same two calls with one target adapter id per request (lora-affinity-scorer: 1.0 if the
+ * adapter is active on the endpoint, 0.8 if the endpoint has room for another adapter, 0.6 if it
+ * is queued there, else 0).  adapters == NULL means "no adapter" (id 0) for every request. */
+int fi_epp_pick_batch_lora(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
+                           const uint64_t* adapters, uint32_t R, fi_pick* out, uint64_t* chains_out);
+int fi_epp_pick_batch_device_lora(fi_epp* h, const void* d_prompts, const void* d_offsets, const void* d_h0,
+                                  const void* d_adapters, uint32_t R, uint64_t total_prompt_bytes, void* d_out,
+                                  void* d_chains_out, void* stream);
 
 void* fi_epp_pinned_alloc(size_t bytes);
 void fi_epp_pinned_free(void* p);

@@ -257,7 +257,22 @@ struct EpState {
   double kv_util = 0.0;
   int32_t queue_depth = 0;
   uint32_t flags = 0;
+  // lora-affinity-scorer inputs (upstream pod metrics ActiveModels / WaitingModels / MaxActiveModels)
+  std::vector<uint64_t> active, waiting;
+  uint32_t max_active = 0;
 };
+
+// upstream lora-affinity-scorer — SURVEY.md §8a row a11 (plugin type of
+// /root/reference/pkg/router/strategy.go:100-113): 1.0 if the target adapter is active on the pod,
+// 0.8 if the pod has room for another adapter, 0.6 if the adapter is queued there, else 0.
+inline double lora_score(const EpState& e, uint64_t adapter) {
+  bool active = false, waiting = false;
+  for (uint64_t a : e.active) active |= a == adapter;
+  for (uint64_t a : e.waiting) waiting |= a == adapter;
+  if (active) return 1.0;
+  if (e.active.size() + e.waiting.size() < e.max_active) return 0.8;
+  return waiting ? 0.6 : 0.0;
+}
 
 struct Oracle {
   fi_epp_config cfg;
@@ -300,7 +315,7 @@ ProfileCtx make_ctx(const Oracle& o, const fi_profile& p) {
 // accumulated in profile order in fp64 without FMA contraction
 // (weights: /root/reference/pkg/router/strategy.go:66,82,97,157,163).
 inline double total_score(const fi_profile& p, const ProfileCtx& c, const EpState& e, uint32_t match,
-                          uint32_t n_blocks) {
+                          uint32_t n_blocks, uint64_t adapter) {
   double total = 0.0;
   for (uint32_t s = 0; s < p.n_scorers; ++s) {
     double sc = 0.0;
@@ -315,6 +330,9 @@ inline double total_score(const fi_profile& p, const ProfileCtx& c, const EpStat
         sc = (c.max_q == c.min_q) ? 1.0
                                   : (double)((int64_t)c.max_q - (int64_t)e.queue_depth) /
                                         (double)((int64_t)c.max_q - (int64_t)c.min_q);
+        break;
+      case FI_SCORER_LORA:
+        sc = lora_score(e, adapter);
         break;
       default:
         sc = 0.0;
@@ -334,7 +352,7 @@ struct Scratch {
 
 // One request: hash → match (A.3) → score (A.4) → pick (A.5) → PD (A.6).
 void pick_one(const Oracle& o, const std::vector<ProfileCtx>& ctx, const uint8_t* prompt, uint64_t len,
-              uint64_t h0, fi_pick* out, uint64_t* chain_out, Scratch& sc) {
+              uint64_t h0, uint64_t adapter, fi_pick* out, uint64_t* chain_out, Scratch& sc) {
   const fi_epp_config& cfg = o.cfg;
   const uint32_t E = cfg.num_endpoints;
   sc.chain.resize(cfg.max_blocks);
@@ -388,7 +406,7 @@ void pick_one(const Oracle& o, const std::vector<ProfileCtx>& ctx, const uint8_t
     for (uint32_t e = 0; e < E; ++e) {  // ascending: first strictly-greater wins → lowest index on ties
       const EpState& es = o.eps[e];
       if (!eligible(es, prof.role_mask)) continue;
-      double t = total_score(prof, ctx[p], es, sc.match[e], n);
+      double t = total_score(prof, ctx[p], es, sc.match[e], n, adapter);
       if (best_e == FI_NO_ENDPOINT || t > best) {
         best = t;
         best_e = e;
@@ -428,7 +446,7 @@ bool validate(const fi_epp_config& c, std::string& err) {
     if (c.profiles[p].n_scorers > FI_EPP_MAX_SCORERS) return err = "n_scorers out of range", false;
     for (uint32_t s = 0; s < c.profiles[p].n_scorers; ++s) {
       uint32_t k = c.profiles[p].scorers[s].kind;
-      if (k != FI_SCORER_PREFIX && k != FI_SCORER_KV_UTIL && k != FI_SCORER_QUEUE)
+      if (k != FI_SCORER_PREFIX && k != FI_SCORER_KV_UTIL && k != FI_SCORER_QUEUE && k != FI_SCORER_LORA)
         return err = "unsupported scorer kind", false;
       if (c.profiles[p].scorers[s].weight < 0) return err = "negative weight", false;
     }
@@ -470,6 +488,19 @@ int epo_endpoints_update(void* h, const fi_endpoint_state* s, uint32_t n) {
     e.kv_util = s[i].kv_util;
     e.queue_depth = s[i].queue_depth;
     e.flags = s[i].flags;
+  }
+  return FI_OK;
+}
+
+int epo_endpoints_lora_update(void* h, const fi_endpoint_lora* s, uint32_t n) {
+  Oracle* o = (Oracle*)h;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (s[i].endpoint >= o->cfg.num_endpoints || s[i].n_active > FI_EPP_MAX_LORA || s[i].n_waiting > FI_EPP_MAX_LORA)
+      return FI_ERR_INVALID;
+    EpState& e = o->eps[s[i].endpoint];
+    e.active.assign(s[i].active, s[i].active + s[i].n_active);
+    e.waiting.assign(s[i].waiting, s[i].waiting + s[i].n_waiting);
+    e.max_active = s[i].max_active;
   }
   return FI_OK;
 }
@@ -549,8 +580,9 @@ int epo_hash_batch(void* h, const uint8_t* prompts, const uint64_t* offsets, con
 
 // The whole path for R requests; requests are sharded over `nthreads` host
 // threads (the index is read-only during a batch).  out: R*n_profiles picks.
-static int pick_batch_impl(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
-                           fi_pick* out, uint64_t* chains_out, uint32_t nthreads, uint32_t repeat) {
+static int pick_batch_impl(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
+                           const uint64_t* adapters, uint32_t R, fi_pick* out, uint64_t* chains_out, uint32_t nthreads,
+                           uint32_t repeat) {
   Oracle* o = (Oracle*)h;
   const uint32_t P = o->cfg.n_profiles;
   std::vector<ProfileCtx> ctx(P);
@@ -561,7 +593,8 @@ static int pick_batch_impl(void* h, const uint8_t* prompts, const uint64_t* offs
     Scratch sc;
     for (uint32_t rep = 0; rep < repeat; ++rep)
       for (uint32_t r = lo; r < hi; ++r) {
-        pick_one(*o, ctx, prompts + offsets[r], offsets[r + 1] - offsets[r], h0[r], out + (size_t)r * P,
+        pick_one(*o, ctx, prompts + offsets[r], offsets[r + 1] - offsets[r], h0[r], adapters ? adapters[r] : 0,
+                 out + (size_t)r * P,
                  chains_out ? chains_out + (size_t)r * o->cfg.max_blocks : nullptr, sc);
       }
   };
@@ -582,14 +615,19 @@ static int pick_batch_impl(void* h, const uint8_t* prompts, const uint64_t* offs
 
 int epo_pick_batch(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
                    fi_pick* out, uint64_t* chains_out, uint32_t nthreads) {
-  return pick_batch_impl(h, prompts, offsets, h0, R, out, chains_out, nthreads, 1);
+  return pick_batch_impl(h, prompts, offsets, h0, nullptr, R, out, chains_out, nthreads, 1);
+}
+
+int epo_pick_batch_lora(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
+                        const uint64_t* adapters, uint32_t R, fi_pick* out, uint64_t* chains_out, uint32_t nthreads) {
+  return pick_batch_impl(h, prompts, offsets, h0, adapters, R, out, chains_out, nthreads, 1);
 }
 
 // Timing variant: every thread processes its shard `repeat` times (same results), so that thread
 // start-up does not dominate a bounded sample on a many-core host.  Decisions = R * repeat.
 int epo_pick_batch_repeat(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
                           fi_pick* out, uint32_t nthreads, uint32_t repeat) {
-  return pick_batch_impl(h, prompts, offsets, h0, R, out, nullptr, nthreads, repeat ? repeat : 1);
+  return pick_batch_impl(h, prompts, offsets, h0, nullptr, R, out, nullptr, nthreads, repeat ? repeat : 1);
 }
 
 }  // extern "C"

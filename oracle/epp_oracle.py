@@ -40,6 +40,10 @@ def load() -> C.CDLL:
     lib.epo_destroy.argtypes = [_P]
     lib.epo_endpoints_update.restype = C.c_int
     lib.epo_endpoints_update.argtypes = [_P, _P, C.c_uint32]
+    lib.epo_endpoints_lora_update.restype = C.c_int
+    lib.epo_endpoints_lora_update.argtypes = [_P, _P, C.c_uint32]
+    lib.epo_pick_batch_lora.restype = C.c_int
+    lib.epo_pick_batch_lora.argtypes = [_P, _P, _P, _P, _P, C.c_uint32, _P, _P, C.c_uint32]
     lib.epo_index_reserve.restype = C.c_int
     lib.epo_index_reserve.argtypes = [_P, C.c_uint64]
     lib.epo_index_apply.restype = C.c_int
@@ -97,6 +101,11 @@ class Oracle:
         rc = self._lib.epo_endpoints_update(self._h, _ptr(states), len(states))
         assert rc == 0, rc
 
+    def update_endpoints_lora(self, states):
+        states = np.ascontiguousarray(states, dtype=abi.lora_dtype())
+        rc = self._lib.epo_endpoints_lora_update(self._h, _ptr(states), len(states))
+        assert rc == 0, rc
+
     def index_reserve(self, keys: int):
         self._lib.epo_index_reserve(self._h, keys)
 
@@ -131,10 +140,16 @@ class Oracle:
         assert rc == 0, rc
         return chains, nb
 
-    def pick_batch(self, prompts, offsets, h0, want_chains=False, nthreads=1):
+    def pick_batch(self, prompts, offsets, h0, want_chains=False, nthreads=1, adapters=None):
         prompts, offsets, h0, R = self._inputs(prompts, offsets, h0)
         picks = np.zeros((R, self.P), dtype=PICK_DTYPE)
         chains = np.zeros((R, self.M), dtype=np.uint64) if want_chains else None
+        if adapters is not None:
+            ad = np.ascontiguousarray(np.broadcast_to(np.asarray(adapters, dtype=np.uint64), (R,)))
+            rc = self._lib.epo_pick_batch_lora(self._h, _ptr(prompts), _ptr(offsets), _ptr(h0), _ptr(ad), R, _ptr(picks),
+                                               _ptr(chains), nthreads)
+            assert rc == 0, rc
+            return (picks, chains) if want_chains else picks
         rc = self._lib.epo_pick_batch(self._h, _ptr(prompts), _ptr(offsets), _ptr(h0), R, _ptr(picks), _ptr(chains), nthreads)
         assert rc == 0, rc
         return (picks, chains) if want_chains else picks

@@ -344,3 +344,42 @@ def test_batch_limits_are_enforced():
         gpu.pick_batch(data, offs, 1)
     assert "max_prompt_bytes" in str(ei.value)
     gpu.close()
+
+
+def _random_lora_states(E, rng, n_adapters=12):
+    from fusioninfer_b200 import LORA_DTYPE
+
+    st = np.zeros(E, dtype=LORA_DTYPE)
+    st["endpoint"] = np.arange(E)
+    for e in range(E):
+        na, nw = int(rng.integers(0, 5)), int(rng.integers(0, 3))
+        ids = rng.permutation(n_adapters)[: na + nw] + 1000
+        st[e]["n_active"], st[e]["n_waiting"] = na, nw
+        st[e]["active"][:na] = ids[:na]
+        st[e]["waiting"][:nw] = ids[na:]
+        st[e]["max_active"] = int(rng.integers(0, 7))
+    return st
+
+
+@pytest.mark.parametrize("E", [8, 100, 1024, 2048])
+@pytest.mark.parametrize("scorers", [[(abi.FI_SCORER_LORA, 100)],
+                                     [(P, 60), (abi.FI_SCORER_LORA, 30), (K, 5), (Q, 5)]])
+def test_pick_parity_lora_affinity(E, scorers):
+    rng = np.random.default_rng(E)
+    wl = H.small_workload(E=E, R=128)
+    cfg = H.config_for(wl, profiles=[{"name": "default", "scorers": scorers}])
+    gpu, cpu = _pair(cfg)
+    _load(wl, gpu, cpu)
+    lora = _random_lora_states(E, rng)
+    gpu.update_endpoints_lora(lora)
+    cpu.update_endpoints_lora(lora)
+    tok, offs = wl.prompts()
+    adapters = (rng.integers(0, 14, size=wl.R) + 1000).astype(np.uint64)  # includes ids nobody holds
+    got = gpu.pick_batch(tok, offs, wl.h0, adapters=adapters)
+    want = cpu.pick_batch(tok, offs, wl.h0, adapters=adapters)
+    assert H.picks_equal(got, want), H.describe_diff(got, want)
+    # without adapters every request uses id 0
+    got0 = gpu.pick_batch(tok, offs, wl.h0)
+    want0 = cpu.pick_batch(tok, offs, wl.h0)
+    assert H.picks_equal(got0, want0), H.describe_diff(got0, want0)
+    gpu.close()

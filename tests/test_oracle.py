@@ -210,3 +210,45 @@ def test_multithreaded_matches_single():
     b = o.pick_batch(tok, offs, wl.h0, nthreads=4)
     assert H.picks_equal(a, b)
     assert (a["match_blocks"] > 0).sum() > len(a) // 2  # the workload really exercises prefix hits
+
+
+def _lora_states(E, rows):
+    """rows: {endpoint: (max_active, [active ids], [waiting ids])}"""
+    from fusioninfer_b200 import LORA_DTYPE
+
+    st = np.zeros(len(rows), dtype=LORA_DTYPE)
+    for i, (e, (mx, act, wai)) in enumerate(sorted(rows.items())):
+        st[i]["endpoint"] = e
+        st[i]["max_active"] = mx
+        st[i]["n_active"] = len(act)
+        st[i]["n_waiting"] = len(wai)
+        st[i]["active"][: len(act)] = act
+        st[i]["waiting"][: len(wai)] = wai
+    return st
+
+
+def test_lora_affinity_scorer_classes():
+    """upstream lora-affinity-scorer (strategy.go:100-113): active 1.0 > room 0.8 > queued 0.6 > none 0."""
+    L = abi.FI_SCORER_LORA
+    prof = [{"name": "default", "scorers": [(L, 100)]}]
+    o, _ = _oracle(E=5, profiles=prof)
+    o.update_endpoints(H.states_array(5))
+    o.update_endpoints_lora(_lora_states(5, {
+        0: (2, [11, 12], [77]),      # full, 77 queued            -> 0.6 for 77, 0 otherwise
+        1: (4, [11], []),            # room                       -> 1.0 for 11, 0.8 otherwise
+        2: (1, [77], []),            # full, 77 active            -> 1.0 for 77
+        3: (1, [12], [13]),          # full, nothing relevant     -> 0
+        # endpoint 4 never listed: max_active 0 -> 0
+    }))
+    data, offs = H.pack_prompts([bytes(64)] * 3)
+    pk = o.pick_batch(data, offs, 1, adapters=np.array([77, 11, 99], dtype=np.uint64))
+    assert (pk[0, 0]["endpoint"], pk[0, 0]["score"]) == (2, 100.0)   # active beats room (0.8) and queued (0.6)
+    assert (pk[1, 0]["endpoint"], pk[1, 0]["score"]) == (0, 100.0)   # lowest index among the endpoints with 11 active
+    assert (pk[2, 0]["endpoint"], pk[2, 0]["score"]) == (1, 80.0)    # only endpoint 1 has room
+    # without room anywhere the queued endpoint wins
+    o.update_endpoints_lora(_lora_states(5, {1: (1, [11], [])}))
+    pk = o.pick_batch(data[:64 + 16], offs[:2], 1, adapters=np.array([77], dtype=np.uint64))
+    assert (pk[0, 0]["endpoint"], pk[0, 0]["score"]) == (2, 100.0)
+    o.update_endpoints_lora(_lora_states(5, {2: (1, [5], [])}))
+    pk = o.pick_batch(data[:64 + 16], offs[:2], 1, adapters=np.array([77], dtype=np.uint64))
+    assert (pk[0, 0]["endpoint"], pk[0, 0]["score"]) == (0, 60.0)
