@@ -22,7 +22,8 @@ Prints ONE JSON line (rank 0):
 Multi-GPU (torchrun, one rank per GPU): --mode replicas (default: the 1 024-endpoint
 pool fits one GPU, so every GPU is an independent replica serving its own batches —
 SURVEY.md §8e) or --mode sharded (configs 4/5: endpoint-range shards + the library's
-NCCL exchange of presence masks and (score, endpoint) pairs).
+exchange of presence masks and (score, endpoint) pairs — in-kernel peer-memory stores over
+NVLink by default, FI_EPP_EXCHANGE=nccl for the two-all-gather path).
 """
 from __future__ import annotations
 
@@ -258,6 +259,7 @@ def main():
     if mode == "sharded" and world > 1:
         uid = EndpointPicker.comm_unique_id() if rank == 0 else None
         picker.comm_init(fdist.broadcast_bytes(uid, 128), rank, world)
+    exchange = picker.comm_exchange()
     picker.update_endpoints(wl.endpoint_states())
     n_ops = 0
     for ops in wl.index_ops(ep_lo=begin, ep_hi=begin + count, chunk_endpoints=128):
@@ -427,7 +429,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(wl, cfg_id, f"{mode}{world}"),
+            "config": dict(workload_config(wl, cfg_id, f"{mode}{world}"), exchange=exchange),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": int(launches),
             "parity": parity,
         }

@@ -208,6 +208,7 @@ SYMBOLS = [
     ("fi_epp_pinned_free", None, [_P]),
     ("fi_epp_comm_unique_id", C.c_int, [_P]),
     ("fi_epp_comm_init", C.c_int, [_P, _P, C.c_uint32, C.c_uint32]),
+    ("fi_epp_comm_exchange", C.c_int, [_P]),
     ("fi_epp_set_profiling", C.c_int, [_P, C.c_int]),
     ("fi_epp_get_stats", C.c_int, [_P, C.POINTER(fi_epp_stats)]),
     ("fi_epp_reset_stats", C.c_int, [_P]),

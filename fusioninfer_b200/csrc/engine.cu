@@ -6,6 +6,7 @@
 // optional NCCL communicator for endpoint-range sharded pools.  No CPU fallback:
 // creation fails without a CUDA device.
 #include <cuda_runtime.h>
+#include <unistd.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -123,6 +124,12 @@ struct fi_epp {
   fi_pick* d_gather = nullptr;  // [world][R][P]
   uint32_t* d_mask = nullptr;   // [R][mask_words]
   uint32_t* d_gmask = nullptr;  // [world][R][mask_words]
+  // peer-memory exchange (sharded mode; kernels.cuh PeerXchg)
+  PeerXchg px{};                 // px.enabled == 0: NCCL all-gathers are used
+  uint8_t* d_xchg = nullptr;     // this rank's exchange buffer
+  uint32_t* d_xerr = nullptr;    // poll-timeout flag of the exchange
+  uint32_t* d_slots = nullptr;   // [R][MP] key slots found by probe_slots_kernel (sharded upstream mode)
+  void* peer_ipc[FI_MAX_RANKS] = {};  // mappings opened with cudaIpcOpenMemHandle (closed in destroy)
   unsigned long long* d_probed = nullptr;
   uint32_t* d_work = nullptr;  // [16] dynamic work-queue counters of in-flight match launches
   // pinned host mirrors
@@ -411,6 +418,115 @@ int nccl_allgather(fi_epp* h, const void* send, void* recv, size_t bytes) {
   return FI_OK;
 }
 
+// Peer-memory exchange set-up (sharded mode): allocate this rank's buffer, exchange its IPC handle over
+// the NCCL communicator, map every peer's buffer.  Falls back to the NCCL all-gather path (px.enabled = 0)
+// when FI_EPP_EXCHANGE=nccl, when there are more than FI_MAX_RANKS ranks, or when any rank cannot map a peer.
+struct XchgBlob {
+  cudaIpcMemHandle_t handle;
+  uint64_t ptr;
+  int64_t pid;
+  int32_t device;
+  int32_t ok;
+  uint8_t pad[40];
+};
+static_assert(sizeof(XchgBlob) == 128, "XchgBlob size");
+
+int setup_peer_exchange(fi_epp* h) {
+  const char* mode = std::getenv("FI_EPP_EXCHANGE");
+  const bool want = !(mode && std::strcmp(mode, "nccl") == 0) && h->world <= (uint32_t)FI_MAX_RANKS;
+  const uint64_t R = h->cfg.max_batch;
+  const uint32_t mask_words = (h->MP + 31) / 32;
+  auto up = [](uint64_t v) { return (v + 255) & ~255ull; };
+  PeerXchg px{};
+  px.world = h->world;
+  px.rank = h->rank;
+  uint64_t off = 0;
+  for (int par = 0; par < 2; ++par) {  // tagged 64-bit words (kernels.cuh PeerXchg)
+    px.off_mask[par] = off;
+    off = up(off + (uint64_t)h->world * R * mask_words * sizeof(uint64_t));
+  }
+  for (int par = 0; par < 2; ++par) {
+    px.off_pick[par] = off;
+    off = up(off + (uint64_t)h->world * R * h->P * 4 * sizeof(uint64_t));
+  }
+  XchgBlob mine{};
+  mine.ok = 0;
+  if (want && cudaMalloc(&h->d_xchg, off) == cudaSuccess && cudaMemset(h->d_xchg, 0, off) == cudaSuccess &&
+      cudaMalloc(&h->d_xerr, sizeof(uint32_t)) == cudaSuccess &&
+      cudaMemset(h->d_xerr, 0, sizeof(uint32_t)) == cudaSuccess &&
+      cudaIpcGetMemHandle(&mine.handle, h->d_xchg) == cudaSuccess) {
+    mine.ok = 1;
+  }
+  cudaGetLastError();
+  mine.ptr = (uint64_t)(uintptr_t)h->d_xchg;
+  mine.pid = (int64_t)getpid();
+  mine.device = h->cfg.device;
+  // round 1: handles; round 2: "I mapped every peer" votes.  Both ride the NCCL communicator.
+  XchgBlob* d_blobs = nullptr;
+  FI_CUDA(cudaMalloc(&d_blobs, (size_t)(h->world + 1) * sizeof(XchgBlob)));
+  std::vector<XchgBlob> all(h->world);
+  auto gather = [&]() -> int {
+    FI_CUDA(cudaMemcpyAsync(d_blobs + h->world, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->s_main));
+    int rc = nccl_allgather(h, d_blobs + h->world, d_blobs, sizeof(XchgBlob));
+    if (rc != FI_OK) return rc;
+    FI_CUDA(cudaMemcpyAsync(all.data(), d_blobs, (size_t)h->world * sizeof(XchgBlob), cudaMemcpyDeviceToHost, h->s_main));
+    FI_CUDA(cudaStreamSynchronize(h->s_main));
+    return FI_OK;
+  };
+  int rc = gather();
+  if (rc != FI_OK) {
+    cudaFree(d_blobs);
+    return rc;
+  }
+  bool ok = true;
+  for (uint32_t k = 0; k < h->world; ++k) ok = ok && all[k].ok;
+  if (ok) {
+    for (uint32_t k = 0; k < h->world && ok; ++k) {
+      if (k == h->rank) {
+        px.base[k] = h->d_xchg;
+      } else if (all[k].pid == mine.pid) {  // same process: plain peer access
+        int can = 0;
+        if (all[k].device != h->cfg.device) {
+          cudaDeviceCanAccessPeer(&can, h->cfg.device, all[k].device);
+          if (can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[k].device, 0);
+            can = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
+            cudaGetLastError();
+          }
+        } else {
+          can = 1;
+        }
+        ok = can != 0;
+        px.base[k] = (uint8_t*)(uintptr_t)all[k].ptr;
+      } else {
+        void* m = nullptr;
+        if (cudaIpcOpenMemHandle(&m, all[k].handle, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+          h->peer_ipc[k] = m;
+          px.base[k] = (uint8_t*)m;
+        } else {
+          cudaGetLastError();
+          ok = false;
+        }
+      }
+    }
+  }
+  mine.ok = ok ? 1 : 0;
+  rc = gather();
+  cudaFree(d_blobs);
+  if (rc != FI_OK) return rc;
+  for (uint32_t k = 0; k < h->world; ++k) ok = ok && all[k].ok;
+  if (ok) {
+    px.enabled = 1;
+    px.step = 0;
+    px.err = h->d_xerr;
+  }
+  h->px = px;
+  if (std::getenv("FI_EPP_VERBOSE"))
+    std::fprintf(stderr, "[fi_epp] rank %u/%u: sharded exchange over %s\n", h->rank, h->world,
+                 px.enabled ? "peer memory (in-kernel tagged stores)" : "NCCL all-gather");
+  return FI_OK;
+}
+
 // the whole pick on device buffers; result in d_out ([R][P])
 int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0,
              const uint64_t* d_adapters, uint32_t R, fi_pick* d_out) {
@@ -487,17 +603,37 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
 
   rc = run_hash(h, d_prompts, d_offsets, d_h0, 0, R, h->s_main);
   if (rc != FI_OK) return rc;
+  const bool p2p = h->px.enabled != 0;
+  if (p2p) {
+    // Peer-memory exchange: the producer kernels store tagged words into every rank's buffer and the
+    // consumer kernels poll per request, so the step has no collective call, no barrier between the
+    // ranks and no host round trip.
+    unsigned int timed_out = 0;  // a timeout of an earlier call is sticky
+    if ((h->stats.pick_calls & 63) == 63) {
+      FI_CUDA(cudaMemcpyAsync(&timed_out, h->d_xerr, sizeof(timed_out), cudaMemcpyDeviceToHost, h->s_main));
+      FI_CUDA(cudaStreamSynchronize(h->s_main));
+      if (timed_out) return fail(h, FI_ERR_COMM, "peer exchange timed out waiting for another rank");
+    }
+    h->px.step += 1;
+    if (h->px.step == 0) h->px.step = 1;  // tag 0 is the zero-initialised buffer
+    mp.px = h->px;
+  }
   if (sharded && h->cfg.match_mode == FI_MATCH_UPSTREAM) {
     // exact upstream semantics need the global first miss: exchange presence masks
     {
       LaunchScope ls(h, h->s_main, K_OTHER);
-      FI_CUDA(launch_probe_mask(mp, h->d_mask, h->sm_count, h->s_main));
+      mp.slots = h->d_slots;
+      FI_CUDA(launch_probe_slots(mp, h->d_mask, h->sm_count, h->s_main));
     }
-    const size_t bytes = (size_t)R * mp.mask_words * sizeof(uint32_t);
-    // gathered layout must be [rank][R][words] with the *call's* R
-    rc = nccl_allgather(h, h->d_mask, h->d_gmask, bytes);
-    if (rc != FI_OK) return rc;
-    mp.gmask = h->d_gmask;
+    if (p2p) {
+      mp.gmask = reinterpret_cast<const uint32_t*>(h->d_xchg + h->px.off_mask[h->px.step & 1u]);
+    } else {
+      const size_t bytes = (size_t)R * mp.mask_words * sizeof(uint32_t);
+      // gathered layout must be [rank][R][words] with the *call's* R
+      rc = nccl_allgather(h, h->d_mask, h->d_gmask, bytes);
+      if (rc != FI_OK) return rc;
+      mp.gmask = h->d_gmask;
+    }
     mp.gmask_ranks = h->world;
   }
   {
@@ -505,10 +641,15 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
     FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
   }
   if (sharded) {
-    rc = nccl_allgather(h, h->d_local, h->d_gather, (size_t)R * h->P * sizeof(fi_pick));
-    if (rc != FI_OK) return rc;
     MergeParams mg{};
-    mg.gathered = h->d_gather;
+    if (p2p) {
+      mg.gathered = reinterpret_cast<const fi_pick*>(h->d_xchg + h->px.off_pick[h->px.step & 1u]);
+      mg.px = h->px;
+    } else {
+      rc = nccl_allgather(h, h->d_local, h->d_gather, (size_t)R * h->P * sizeof(fi_pick));
+      if (rc != FI_OK) return rc;
+      mg.gathered = h->d_gather;
+    }
     mg.ranks = h->world;
     mg.R = R;
     mg.P = h->P;
@@ -650,6 +791,11 @@ void fi_epp_destroy(fi_epp* h) {
   cudaFree(h->d_gather);
   cudaFree(h->d_mask);
   cudaFree(h->d_gmask);
+  for (int k = 0; k < FI_MAX_RANKS; ++k)
+    if (h->peer_ipc[k]) cudaIpcCloseMemHandle(h->peer_ipc[k]);
+  cudaFree(h->d_xchg);
+  cudaFree(h->d_xerr);
+  cudaFree(h->d_slots);
   cudaFree(h->d_probed);
   cudaFree(h->d_work);
   cudaFree(h->d_ctr);
@@ -1125,9 +1271,17 @@ int fi_epp_comm_init(fi_epp* h, const uint8_t id_bytes[FI_EPP_UNIQUE_ID_BYTES], 
   FI_CUDA(cudaMalloc(&h->d_gather, (size_t)world * R * h->P * sizeof(fi_pick)));
   FI_CUDA(cudaMalloc(&h->d_mask, R * mask_words * sizeof(uint32_t)));
   FI_CUDA(cudaMalloc(&h->d_gmask, (size_t)world * R * mask_words * sizeof(uint32_t)));
+  FI_CUDA(cudaMalloc(&h->d_slots, R * h->MP * sizeof(uint32_t)));
   h->rank = rank;
   h->world = world;
-  return FI_OK;
+  return setup_peer_exchange(h);
+}
+
+int fi_epp_comm_exchange(fi_epp* h) {
+  if (!h) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->world <= 1) return FI_EXCHANGE_NONE;
+  return h->px.enabled ? FI_EXCHANGE_PEER : FI_EXCHANGE_NCCL;
 }
 
 int fi_epp_set_profiling(fi_epp* h, int on) {

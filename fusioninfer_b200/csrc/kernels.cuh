@@ -82,6 +82,26 @@ struct ScoreTables {
   uint32_t pad;         // so every eligible endpoint is scored per request (no zero-match shortcut)
 };
 
+// Peer-memory exchange of the endpoint-range sharded mode (one buffer per rank, every rank's buffer
+// mapped into every process over NVLink / CUDA IPC).  Low-latency protocol: every 32-bit datum travels
+// in one aligned 64-bit store together with a 32-bit tag = the step number of the pick call, so a word is
+// valid exactly when its tag matches — no fences, no flags, no barrier between the ranks.  Producers
+// (probe_slots_kernel: presence masks; match_pick_kernel: local picks) store each word into slot
+// [parity][own rank] of EVERY rank's buffer as soon as it exists; consumers (match_pick_kernel,
+// merge_picks_kernel) poll only the words of the request they are about to process, so the transfer of
+// later requests overlaps the work on earlier ones.  Parity double-buffers consecutive steps (a rank can
+// be at most one step ahead of a peer, because its merge needs that peer's picks of the previous step).
+constexpr int FI_MAX_RANKS = 16;
+struct PeerXchg {
+  uint32_t world, rank;
+  uint32_t step;                // tag of this pick call (monotonic, starts at 1; buffers start zeroed)
+  uint32_t enabled;             // 0: the NCCL all-gather path is used instead
+  uint8_t* base[FI_MAX_RANKS];  // base[k] = rank k's exchange buffer as mapped here (base[rank] is local)
+  uint64_t off_mask[2];         // u64 {tag:mask word}  [world][R][mask_words]   (R = the call's batch)
+  uint64_t off_pick[2];         // u64 {tag:word}       [world][R][P][4]  endpoint, match_blocks, score lo, hi
+  uint32_t* err;                // local: set to 1 if a poll timed out
+};
+
 struct MatchParams {
   const uint64_t* chain;
   const uint32_t* nblocks;
@@ -100,10 +120,12 @@ struct MatchParams {
   const uint32_t* gmask;
   uint32_t gmask_ranks;
   uint32_t mask_words;
+  uint32_t* slots;                    // [R][MP] key slot of every block (probe_slots_kernel -> match GMASK)
   fi_pick* out;                       // [R][P]
   unsigned long long* probed_blocks;  // optional Σ N_probe
   uint32_t* work_counter;             // dynamic request queue of the launch
   uint32_t zero_work_counter;         // launcher zeroes it first (0: the caller already did)
+  PeerXchg px;                        // sharded mode, peer-memory exchange (px.enabled)
 };
 
 struct MergeParams {
@@ -114,6 +136,7 @@ struct MergeParams {
   uint32_t apply_pd, pd_decode, pd_prefill;
   double pd_threshold;
   fi_pick* out;  // [R][P]
+  PeerXchg px;   // px.enabled: poll every rank's tagged pick words in-kernel instead of after an all-gather
 };
 
 // ---- launchers (each returns the cudaGetLastError() of its launch) -----------
@@ -138,7 +161,7 @@ cudaError_t launch_prepare_endpoints(const EndpointDev* eps, uint32_t E_global, 
                                      ZeroBest* zero, cudaStream_t s);
 
 cudaError_t launch_match_pick(const MatchParams& p, int sm_count, cudaStream_t s);
-cudaError_t launch_probe_mask(const MatchParams& p, uint32_t* mask_out, int sm_count, cudaStream_t s);
+cudaError_t launch_probe_slots(const MatchParams& p, uint32_t* mask_out, int sm_count, cudaStream_t s);
 cudaError_t launch_merge_picks(const MergeParams& p, cudaStream_t s);
 
 }  // namespace fi

@@ -93,6 +93,33 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // fire-and-forget: pull a line into L2, no destination register, no scoreboard wait
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
+// ---- peer-memory exchange (sharded mode): tagged 64-bit words, see PeerXchg in kernels.cuh ------
+__device__ __forceinline__ void ll_store(uint64_t* p, uint32_t data, uint32_t tag) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(((uint64_t)tag << 32) | data) : "memory");
+}
+__device__ __forceinline__ uint64_t ll_load(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr long long kPollTimeoutCycles = 20000000000ll;  // ~10 s: a peer died or never launched
+// poll one tagged word until it belongs to this step
+__device__ __forceinline__ uint32_t ll_wait(const uint64_t* p, uint32_t tag, uint32_t* err) {
+  uint64_t v = ll_load(p);
+  if ((uint32_t)(v >> 32) != tag) {
+    const long long t0 = clock64();
+    do {
+      __nanosleep(64);
+      v = ll_load(p);
+      if (clock64() - t0 > kPollTimeoutCycles) {
+        *err = 1;
+        break;
+      }
+    } while ((uint32_t)(v >> 32) != tag);
+  }
+  return (uint32_t)v;
+}
+
 // PD rule shared by the single-GPU kernel and the multi-GPU merge kernel
 __device__ __forceinline__ bool pd_prefill_runs(uint32_t dec_endpoint, uint32_t dec_match, uint32_t n, uint64_t len,
                                                 double threshold) {
@@ -149,8 +176,8 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
     if (r >= p.R) break;
     if (lane == 0) r_next = atomicAdd(p.work_counter, 1u);
     const uint32_t n = p.nblocks[r];
-    // ---- 1. stage the chain ---------------------------------------------------
-    {
+    // ---- 1. stage the chain (sharded upstream mode reads the slots probe_slots_kernel found instead)
+    if (!GMASK) {
       const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
       for (uint32_t u = lane; 2 * u < n; u += 32) cp_async16(s_chain + 2 * u, crow + 2 * u);
       cp_async_wait_all();
@@ -160,9 +187,16 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
     uint32_t kg = n;
     if (GMASK) {
       uint32_t orv = 0;
-      if ((uint32_t)lane < p.mask_words)
-        for (uint32_t rk = 0; rk < p.gmask_ranks; ++rk)
-          orv |= p.gmask[((uint64_t)rk * p.R + r) * p.mask_words + lane];
+      if ((uint32_t)lane < p.mask_words) {
+        if (p.px.enabled) {  // tagged words stored by every rank's probe_slots_kernel: wait for this request's only
+          const uint64_t* gm = reinterpret_cast<const uint64_t*>(p.px.base[p.px.rank] + p.px.off_mask[p.px.step & 1u]);
+          for (uint32_t rk = 0; rk < p.gmask_ranks; ++rk)
+            orv |= ll_wait(gm + ((uint64_t)rk * p.R + r) * p.mask_words + lane, p.px.step, p.px.err);
+        } else {
+          for (uint32_t rk = 0; rk < p.gmask_ranks; ++rk)
+            orv |= __ldcg(p.gmask + ((uint64_t)rk * p.R + r) * p.mask_words + lane);
+        }
+      }
       uint32_t inv = ~orv;
       uint32_t pos = ((uint32_t)lane < p.mask_words && inv) ? lane * 32 + (__ffs(inv) - 1) : 0xFFFFFFFFu;
 #pragma unroll
@@ -183,7 +217,7 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
     // ---- 2./3. probe + row reads, 32 blocks per chunk ---------------------------
     const uint32_t nchunks = (kg + 31) / 32;
     uint32_t slot = SLOT_MISS;
-    if ((uint32_t)lane < kg) slot = index_find(ix, s_chain[lane]);
+    if ((uint32_t)lane < kg) slot = GMASK ? __ldcg(p.slots + (uint64_t)r * p.MP + lane) : index_find(ix, s_chain[lane]);
     for (uint32_t c = 0; c < nchunks; ++c) {
       uint32_t rows_here;
       bool stop = false;
@@ -203,17 +237,21 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
       BucketRegs brn;
 #pragma unroll
       for (int qq = 0; qq < BUCKET_KEYS / 2; ++qq) brn.q[qq] = make_uint4(0, 0, 0, 0);
+      uint32_t slot_next = SLOT_MISS;
+      bool resolved = GMASK;
       if (!stop && c + 1 < nchunks) {
         const uint32_t idx = (c + 1) * 32 + lane;
         validn = idx < kg;
         if (validn) {
-          hn = s_chain[idx];
-          plain = !key_is_special(hn);
-          if (plain) brn = bucket_load(ix, hn & ix.bmask);
+          if (GMASK) {
+            slot_next = __ldcg(p.slots + (uint64_t)r * p.MP + idx);
+          } else {
+            hn = s_chain[idx];
+            plain = !key_is_special(hn);
+            if (plain) brn = bucket_load(ix, hn & ix.bmask);
+          }
         }
       }
-      uint32_t slot_next = SLOT_MISS;
-      bool resolved = false;
       // rows of this chunk
 #pragma unroll 1
       for (int q0 = 0; q0 < LPR; q0 += BATCH) {
@@ -372,9 +410,23 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
           dec_e = b.e;
           dec_m = b.m;
         }
-        if (lane == 0) {
+        const bool none = b.e == FI_NO_ENDPOINT;
+        if (p.px.enabled) {
+          // sharded: this rank's pick goes straight into every rank's gather slot as four tagged words
+          // (every lane holds the same b after the butterfly; lane i stores word i%4 to rank i/4)
+          const unsigned long long sb = (unsigned long long)__double_as_longlong(none ? 0.0 : b.score);
+          for (uint32_t i = lane; i < p.px.world * 4; i += 32) {
+            const uint32_t k = i >> 2, wsel = i & 3;
+            const uint32_t val = wsel == 0   ? (none ? FI_NO_ENDPOINT : b.e + p.ep_begin)
+                                 : wsel == 1 ? (none ? 0u : b.m)
+                                 : wsel == 2 ? (uint32_t)sb
+                                             : (uint32_t)(sb >> 32);
+            uint64_t* dst = reinterpret_cast<uint64_t*>(p.px.base[k] + p.px.off_pick[p.px.step & 1u]) +
+                            (((uint64_t)p.px.rank * p.R + r) * P + pi) * 4 + wsel;
+            ll_store(dst, val, p.px.step);
+          }
+        } else if (lane == 0) {
           fi_pick pk;
-          const bool none = b.e == FI_NO_ENDPOINT;
           pk.endpoint = none ? FI_NO_ENDPOINT : b.e + p.ep_begin;
           pk.match_blocks = none ? 0 : (uint16_t)b.m;
           pk.n_blocks = (uint16_t)n;
@@ -402,8 +454,10 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
 }
 
 
-// presence mask of every block of every request on this rank (sharded upstream mode)
-__global__ void __launch_bounds__(kWarps * 32) probe_mask_kernel(const MatchParams p, uint32_t* __restrict__ mask_out) {
+// Sharded upstream mode, first pass: probe every block of every request once.  The slot of each block is
+// kept for the match pass (which then never touches the key array), and the presence mask of the request
+// goes out to every rank — tagged words into peer memory, or a plain array for the NCCL all-gather.
+__global__ void __launch_bounds__(kWarps * 32) probe_slots_kernel(const MatchParams p, uint32_t* __restrict__ mask_out) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   for (uint32_t r = blockIdx.x * kWarps + warp; r < p.R; r += gridDim.x * kWarps) {
@@ -411,10 +465,18 @@ __global__ void __launch_bounds__(kWarps * 32) probe_mask_kernel(const MatchPara
     const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
     for (uint32_t c = 0; c < p.mask_words; ++c) {
       const uint32_t idx = c * 32 + lane;
-      bool present = false;
-      if (idx < n) present = index_find(p.ix, crow[idx]) != SLOT_MISS;
-      const unsigned m = __ballot_sync(FULL, present);
-      if (lane == 0) mask_out[(uint64_t)r * p.mask_words + c] = m;
+      uint32_t slot = SLOT_MISS;
+      if (idx < n) slot = index_find(p.ix, crow[idx]);
+      if (idx < p.MP) p.slots[(uint64_t)r * p.MP + idx] = slot;
+      const unsigned m = __ballot_sync(FULL, slot != SLOT_MISS);
+      if (p.px.enabled) {
+        for (uint32_t k = lane; k < p.px.world; k += 32)
+          ll_store(reinterpret_cast<uint64_t*>(p.px.base[k] + p.px.off_mask[p.px.step & 1u]) +
+                       ((uint64_t)p.px.rank * p.R + r) * p.mask_words + c,
+                   m, p.px.step);
+      } else if (lane == 0) {
+        mask_out[(uint64_t)r * p.mask_words + c] = m;
+      }
     }
   }
 }
@@ -431,7 +493,31 @@ __global__ void __launch_bounds__(256) merge_picks_kernel(const MergeParams p) {
     b.n_blocks = (uint16_t)p.nblocks[r];
     b.score = 0.0;
     for (uint32_t rk = 0; rk < p.ranks; ++rk) {
-      const fi_pick c = p.gathered[((uint64_t)rk * p.R + r) * p.P + pi];
+      fi_pick c;
+      if (p.px.enabled) {  // four tagged words per pick, valid when all carry this step's tag
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(p.gathered) + (((uint64_t)rk * p.R + r) * p.P + pi) * 4;
+        uint64_t v0, v1, v2, v3;
+        const long long t0 = clock64();
+        for (;;) {
+          v0 = ll_load(src);
+          v1 = ll_load(src + 1);
+          v2 = ll_load(src + 2);
+          v3 = ll_load(src + 3);
+          const uint32_t tg = p.px.step;
+          if ((uint32_t)(v0 >> 32) == tg && (uint32_t)(v1 >> 32) == tg && (uint32_t)(v2 >> 32) == tg && (uint32_t)(v3 >> 32) == tg) break;
+          if (clock64() - t0 > kPollTimeoutCycles) {
+            *p.px.err = 1;
+            break;
+          }
+          __nanosleep(64);
+        }
+        c.endpoint = (uint32_t)v0;
+        c.match_blocks = (uint16_t)v1;
+        c.n_blocks = (uint16_t)p.nblocks[r];
+        c.score = __longlong_as_double((long long)((v3 << 32) | (v2 & 0xFFFFFFFFull)));
+      } else {
+        c = p.gathered[((uint64_t)rk * p.R + r) * p.P + pi];
+      }
       if (c.endpoint == FI_NO_ENDPOINT) continue;
       if (b.endpoint == FI_NO_ENDPOINT || c.score > b.score || (c.score == b.score && c.endpoint < b.endpoint)) b = c;
     }
@@ -635,12 +721,12 @@ cudaError_t launch_match_pick(const MatchParams& p, int sm_count, cudaStream_t s
   }
 }
 
-cudaError_t launch_probe_mask(const MatchParams& p, uint32_t* mask_out, int sm_count, cudaStream_t s) {
+cudaError_t launch_probe_slots(const MatchParams& p, uint32_t* mask_out, int sm_count, cudaStream_t s) {
   if (p.R == 0) return cudaSuccess;
   uint32_t grid = (p.R + kWarps - 1) / kWarps;
   const uint32_t cap = (uint32_t)sm_count * 8;
   if (grid > cap) grid = cap;
-  probe_mask_kernel<<<grid, kWarps * 32, 0, s>>>(p, mask_out);
+  probe_slots_kernel<<<grid, kWarps * 32, 0, s>>>(p, mask_out);
   return cudaGetLastError();
 }
 

@@ -245,6 +245,13 @@ class EndpointPicker:
         buf = (C.c_uint8 * abi.FI_EPP_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
         self._check(self._lib.fi_epp_comm_init(self._h, buf, rank, world), "fi_epp_comm_init")
 
+    def comm_exchange(self) -> str:
+        """'none' (one rank), 'peer' (in-kernel stores over NVLink peer memory) or 'nccl' (all-gathers)."""
+        rc = self._lib.fi_epp_comm_exchange(self._h)
+        if rc < 0:
+            raise FiEppError(rc, "fi_epp_comm_exchange")
+        return {0: "none", 1: "peer", 2: "nccl"}[rc]
+
     # -- stats -----------------------------------------------------------------
     def set_profiling(self, on: bool):
         self._check(self._lib.fi_epp_set_profiling(self._h, 1 if on else 0), "fi_epp_set_profiling")

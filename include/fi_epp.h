@@ -266,6 +266,14 @@ void fi_epp_pinned_free(void* p);
  * the host distributes it out of band, every rank calls comm_init. */
 int fi_epp_comm_unique_id(uint8_t out[FI_EPP_UNIQUE_ID_BYTES]);
 int fi_epp_comm_init(fi_epp* h, const uint8_t id[FI_EPP_UNIQUE_ID_BYTES], uint32_t rank, uint32_t world);
+/* How the sharded pick exchanges presence masks and local picks between ranks: FI_EXCHANGE_NONE (one rank),
+ * FI_EXCHANGE_PEER (default: kernels store into every rank's buffer over NVLink peer memory / CUDA IPC and
+ * wait on flags in-kernel — no collective call in the step) or FI_EXCHANGE_NCCL (two ncclAllGather per step:
+ * env FI_EPP_EXCHANGE=nccl, more than 16 ranks, or a rank that cannot map a peer's buffer). */
+#define FI_EXCHANGE_NONE 0
+#define FI_EXCHANGE_PEER 1
+#define FI_EXCHANGE_NCCL 2
+int fi_epp_comm_exchange(fi_epp* h);
 
 int fi_epp_set_profiling(fi_epp* h, int on);
 int fi_epp_get_stats(fi_epp* h, fi_epp_stats* out);

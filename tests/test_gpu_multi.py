@@ -78,3 +78,56 @@ def test_sharded_pd_pick(gpu_count):
     want = cpu.pick_batch(tok, offs, wl.h0)
     assert H.picks_equal(results[0], want), H.describe_diff(results[0], want)
     assert H.picks_equal(results[1], want)
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_sharded_exchange_many_steps(gpu_count, exchange, monkeypatch):
+    """Consecutive picks of different batch sizes through both exchange paths: the peer-memory path
+    double-buffers its slots by step parity, so at least three back-to-back steps must stay exact."""
+    if gpu_count < 2:
+        pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("FI_EPP_EXCHANGE", exchange)
+    world = 2
+    wl = H.small_workload(E=160, R=256, holes=True, lru_capacity=300, pd=True)
+    profiles, pd = synth.baseline_profiles(5)
+    pd = dict(pd, threshold=700.0)
+    batches = []
+    for b, R in enumerate([256, 64, 1, 255, 128, 256]):
+        tok, offs = wl.prompts(batch=b)
+        batches.append((np.ascontiguousarray(tok[:R]), offs[: R + 1].copy(), wl.h0))
+    uid = EndpointPicker.comm_unique_id()
+    results = [[] for _ in range(world)]
+    modes = [None] * world
+    errors = []
+
+    def worker(rank):
+        try:
+            begin, count = shard_range(wl.E, rank, world)
+            cfg = H.config_for(wl, profiles=profiles, pd=pd, device=rank, endpoint_begin=begin, endpoint_count=count)
+            p = EndpointPicker(cfg)
+            p.comm_init(uid, rank, world)
+            modes[rank] = p.comm_exchange()
+            p.update_endpoints(wl.endpoint_states())
+            for ops in wl.index_ops():
+                p.index_apply(ops)
+            for tok, offs, h0 in batches:
+                results[rank].append(p.pick_batch(tok, offs, h0))
+            p.close()
+        except Exception as e:  # pragma: no cover
+            errors.append((rank, repr(e)))
+
+    ths = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=600)
+    assert not errors, errors
+    assert modes == [exchange] * world
+    cpu = eo.Oracle(H.config_for(wl, profiles=profiles, pd=pd))
+    cpu.update_endpoints(wl.endpoint_states())
+    for ops in wl.index_ops():
+        cpu.index_apply(ops)
+    for i, (tok, offs, h0) in enumerate(batches):
+        want = cpu.pick_batch(tok, offs, h0)
+        for r in range(world):
+            assert H.picks_equal(results[r][i], want), f"step {i} rank {r}\n" + H.describe_diff(results[r][i], want)
