@@ -127,7 +127,7 @@ struct fi_epp {
   // peer-memory exchange (sharded mode; kernels.cuh PeerXchg)
   PeerXchg px{};                 // px.enabled == 0: NCCL all-gathers are used
   uint8_t* d_xchg = nullptr;     // this rank's exchange buffer
-  uint32_t* d_xerr = nullptr;    // poll-timeout flag of the exchange
+  volatile uint32_t* h_xerr = nullptr;  // poll-timeout flag of the exchange (mapped pinned host word the kernels set)
   uint32_t* d_slots = nullptr;   // [R][MP] key slots found by probe_slots_kernel (sharded upstream mode)
   void* peer_ipc[FI_MAX_RANKS] = {};  // mappings opened with cudaIpcOpenMemHandle (closed in destroy)
   unsigned long long* d_probed = nullptr;
@@ -452,8 +452,7 @@ int setup_peer_exchange(fi_epp* h) {
   XchgBlob mine{};
   mine.ok = 0;
   if (want && cudaMalloc(&h->d_xchg, off) == cudaSuccess && cudaMemset(h->d_xchg, 0, off) == cudaSuccess &&
-      cudaMalloc(&h->d_xerr, sizeof(uint32_t)) == cudaSuccess &&
-      cudaMemset(h->d_xerr, 0, sizeof(uint32_t)) == cudaSuccess &&
+      cudaHostAlloc((void**)&h->h_xerr, sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess &&
       cudaIpcGetMemHandle(&mine.handle, h->d_xchg) == cudaSuccess) {
     mine.ok = 1;
   }
@@ -518,13 +517,34 @@ int setup_peer_exchange(fi_epp* h) {
   if (ok) {
     px.enabled = 1;
     px.step = 0;
-    px.err = h->d_xerr;
+    *h->h_xerr = 0;
+    px.err = const_cast<uint32_t*>(h->h_xerr);  // unified addressing: the host pointer is the device pointer
   }
   h->px = px;
   if (std::getenv("FI_EPP_VERBOSE"))
     std::fprintf(stderr, "[fi_epp] rank %u/%u: sharded exchange over %s\n", h->rank, h->world,
                  px.enabled ? "peer memory (in-kernel tagged stores)" : "NCCL all-gather");
   return FI_OK;
+}
+
+// FI_EPP_TRACE=<call index>: print that call's kernel timeline (start/end relative to the call's start)
+void dump_trace(fi_epp* h, uint32_t R) {
+  if (!h->tracing) return;
+  static const char* names[] = {"hash_blocks", "chain_finalize", "match_pick", "index", "other"};
+  cudaStreamSynchronize(h->s_main);
+  std::fprintf(stderr, "[fi_epp trace] rank %u call %ld: R=%u\n", h->rank, h->trace_call, R);
+  for (auto& e : h->pending_ev) {
+    float t0 = 0.f, t1 = 0.f;
+    cudaEventSynchronize(e.b);
+    cudaEventElapsedTime(&t0, h->ev_trace0, e.a);
+    cudaEventElapsedTime(&t1, h->ev_trace0, e.b);
+    std::fprintf(stderr, "[fi_epp trace]   r%u %-15s start %8.1f us  end %8.1f us  (%6.1f us)\n", h->rank, names[e.kind],
+                 t0 * 1e3, t1 * 1e3, (t1 - t0) * 1e3);
+    h->ev_pool.push_back(e.a);
+    h->ev_pool.push_back(e.b);
+  }
+  h->pending_ev.clear();
+  h->tracing = false;
 }
 
 // the whole pick on device buffers; result in d_out ([R][P])
@@ -579,23 +599,7 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
       LaunchScope ls(h, h->s_main, K_MATCH);
       FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
     }
-    if (h->tracing) {
-      static const char* names[] = {"hash_blocks", "chain_finalize", "match_pick", "index", "other"};
-      cudaStreamSynchronize(h->s_main);
-      std::fprintf(stderr, "[fi_epp trace] call %ld: R=%u\n", h->trace_call, R);
-      for (auto& e : h->pending_ev) {
-        float t0 = 0.f, t1 = 0.f;
-        cudaEventSynchronize(e.b);
-        cudaEventElapsedTime(&t0, h->ev_trace0, e.a);
-        cudaEventElapsedTime(&t1, h->ev_trace0, e.b);
-        std::fprintf(stderr, "[fi_epp trace]   %-15s start %8.1f us  end %8.1f us  (%6.1f us)\n", names[e.kind], t0 * 1e3,
-                     t1 * 1e3, (t1 - t0) * 1e3);
-        h->ev_pool.push_back(e.a);
-        h->ev_pool.push_back(e.b);
-      }
-      h->pending_ev.clear();
-      h->tracing = false;
-    }
+    dump_trace(h, R);
     h->stats.pick_calls++;
     h->stats.requests += R;
     return FI_OK;
@@ -608,12 +612,8 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
     // Peer-memory exchange: the producer kernels store tagged words into every rank's buffer and the
     // consumer kernels poll per request, so the step has no collective call, no barrier between the
     // ranks and no host round trip.
-    unsigned int timed_out = 0;  // a timeout of an earlier call is sticky
-    if ((h->stats.pick_calls & 63) == 63) {
-      FI_CUDA(cudaMemcpyAsync(&timed_out, h->d_xerr, sizeof(timed_out), cudaMemcpyDeviceToHost, h->s_main));
-      FI_CUDA(cudaStreamSynchronize(h->s_main));
-      if (timed_out) return fail(h, FI_ERR_COMM, "peer exchange timed out waiting for another rank");
-    }
+    // a timeout seen by any earlier call is sticky (the kernels set the mapped host word)
+    if (*h->h_xerr) return fail(h, FI_ERR_COMM, "peer exchange timed out waiting for another rank");
     h->px.step += 1;
     if (h->px.step == 0) h->px.step = 1;  // tag 0 is the zero-initialised buffer
     mp.px = h->px;
@@ -660,8 +660,11 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
     mg.pd_prefill = h->cfg.pd_prefill_profile;
     mg.pd_threshold = h->cfg.pd_threshold;
     mg.out = d_out;
-    LaunchScope ls(h, h->s_main, K_OTHER);
-    FI_CUDA(launch_merge_picks(mg, h->s_main));
+    {
+      LaunchScope ls(h, h->s_main, K_OTHER);
+      FI_CUDA(launch_merge_picks(mg, h->s_main));
+    }
+    dump_trace(h, R);
   }
   h->stats.pick_calls++;
   h->stats.requests += R;
@@ -794,7 +797,7 @@ void fi_epp_destroy(fi_epp* h) {
   for (int k = 0; k < FI_MAX_RANKS; ++k)
     if (h->peer_ipc[k]) cudaIpcCloseMemHandle(h->peer_ipc[k]);
   cudaFree(h->d_xchg);
-  cudaFree(h->d_xerr);
+  if (h->h_xerr) cudaFreeHost((void*)h->h_xerr);
   cudaFree(h->d_slots);
   cudaFree(h->d_probed);
   cudaFree(h->d_work);
@@ -1194,6 +1197,7 @@ int fi_epp_pick_batch_lora(fi_epp* h, const uint8_t* prompts, const uint64_t* of
     if (rc != FI_OK) return rc;
   }
   FI_CUDA(cudaStreamSynchronize(h->s_main));
+  if (h->h_xerr && *h->h_xerr) return fail(h, FI_ERR_COMM, "peer exchange timed out waiting for another rank");
   std::memcpy(out, h->h_picks, pb);
   return FI_OK;
 }
