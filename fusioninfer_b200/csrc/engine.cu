@@ -110,6 +110,12 @@ struct fi_epp {
   bool fast_hash = false;
 
   cudaStream_t s_main = nullptr, s_index = nullptr;  // compute; index maintenance (side stream)
+  // host-buffer picks feed the prompts in slices: the copy engine runs ahead on s_copy while s_main hashes,
+  // walks and matches the slices that have landed (the step is PCIe-bound: only the last slice's work is exposed)
+  cudaStream_t s_copy = nullptr;
+  static constexpr int kMaxFeedSlices = 16;
+  cudaEvent_t ev_copy[kMaxFeedSlices] = {};
+  uint32_t feed_slices = 8;  // FI_EPP_FEED_SLICES (1: one copy, then the whole batch)
   cudaEvent_t ev_index = nullptr, ev_user = nullptr, ev_done = nullptr, ev_ctr = nullptr;
 
   // request buffers (device)
@@ -393,7 +399,7 @@ int upload_lora(fi_epp* h) {
 // hash kernels for the request slice [r0, r0+R): prompts → chain (device buffers), on stream s
 int run_hash(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0, uint32_t r0,
              uint32_t R, cudaStream_t s) {
-  uint64_t* pre = h->d_pre;  // tiled by groups of 32 requests: slices must start at r0 == 0
+  uint64_t* pre = h->d_pre + (size_t)r0 * h->MP;  // tiled by groups of 32 requests: r0 % 32 == 0
   uint64_t* chain = h->d_chain + (size_t)r0 * h->MP;
   uint32_t* nb = h->d_nblocks + r0;
   if (h->fast_hash) {
@@ -547,9 +553,15 @@ void dump_trace(fi_epp* h, uint32_t R) {
   h->tracing = false;
 }
 
+// host prompts still to be copied (fi_epp_pick_batch): run_pick copies them, in slices when it can
+struct HostFeed {
+  const uint8_t* prompts;   // host
+  const uint64_t* offsets;  // host, [R+1]
+};
+
 // the whole pick on device buffers; result in d_out ([R][P])
 int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0,
-             const uint64_t* d_adapters, uint32_t R, fi_pick* d_out) {
+             const uint64_t* d_adapters, uint32_t R, fi_pick* d_out, const HostFeed* feed = nullptr) {
   int rc = flush_ops(h);
   if (rc != FI_OK) return rc;
   rc = check_counters(h);
@@ -589,10 +601,49 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
   mp.work_counter = h->d_work;
   mp.zero_work_counter = 1;
 
+  const uint32_t S = h->feed_slices;
+  if (feed && !sharded && h->fast_hash && S > 1 && R >= 64 * S && feed->offsets[R] >= (8ull << 20)) {
+    // Sliced feed.  (On DEVICE-resident inputs slicing the step is slower — DESIGN.md "What did not
+    // work" — but here the copy engine is the bottleneck and the kernels of slice k hide under copy k+1.)
+    uint8_t* dp = const_cast<uint8_t*>(d_prompts);
+    const uint32_t per = (((R + S - 1) / S) + 31) & ~31u;
+    uint32_t used = 0;
+    for (uint32_t k = 0; k * per < R; ++k, ++used) {
+      const uint32_t r0 = k * per, r1 = std::min(R, r0 + per);
+      const uint64_t b0 = feed->offsets[r0], b1 = feed->offsets[r1];
+      if (b1 > b0) FI_CUDA(cudaMemcpyAsync(dp + b0, feed->prompts + b0, b1 - b0, cudaMemcpyHostToDevice, h->s_copy));
+      FI_CUDA(cudaEventRecord(h->ev_copy[k], h->s_copy));
+    }
+    h->stats.h2d_bytes += feed->offsets[R];
+    for (uint32_t k = 0; k < used; ++k) {
+      const uint32_t r0 = k * per, Rk = std::min(per, R - r0);
+      FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_copy[k], 0));
+      rc = run_hash(h, d_prompts, d_offsets, d_h0, r0, Rk, h->s_main);
+      if (rc != FI_OK) return rc;
+      MatchParams ms = mp;
+      ms.chain = mp.chain + (size_t)r0 * h->MP;
+      ms.nblocks = mp.nblocks + r0;
+      ms.offsets = mp.offsets ? mp.offsets + r0 : nullptr;
+      ms.adapters = mp.adapters ? mp.adapters + r0 : nullptr;
+      ms.R = Rk;
+      ms.out = mp.out + (size_t)r0 * h->P;
+      ms.work_counter = h->d_work + k;
+      LaunchScope ls(h, h->s_main, K_MATCH);
+      FI_CUDA(launch_match_pick(ms, h->sm_count, h->s_main));
+    }
+    dump_trace(h, R);
+    h->stats.pick_calls++;
+    h->stats.requests += R;
+    return FI_OK;
+  }
+  if (feed && feed->offsets[R]) {  // one copy, then the whole batch
+    FI_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(d_prompts), feed->prompts, feed->offsets[R], cudaMemcpyHostToDevice, h->s_main));
+    h->stats.h2d_bytes += feed->offsets[R];
+  }
   if (!sharded) {
-    // (A sub-batch pipeline over several streams was tried and measured slower — DESIGN.md
-    // "What did not work": chain walking costs a flat ~45 us at any batch size and small
-    // slices pay launch/ramp overheads.  The overlap now lives inside run_hash.)
+    // (A sub-batch pipeline over several streams was tried and measured slower on device-resident
+    // inputs — DESIGN.md "What did not work": the chain walk costs a flat serial latency at any batch
+    // size and small slices pay launch/ramp overheads.)
     rc = run_hash(h, d_prompts, d_offsets, d_h0, 0, R, h->s_main);
     if (rc != FI_OK) return rc;
     {
@@ -824,7 +875,9 @@ void fi_epp_destroy(fi_epp* h) {
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   for (cudaEvent_t e : {h->ev_index, h->ev_user, h->ev_done, h->ev_ctr})
     if (e) cudaEventDestroy(e);
-  for (cudaStream_t s : {h->s_main, h->s_index})
+  for (int k = 0; k < fi_epp::kMaxFeedSlices; ++k)
+    if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);
+  for (cudaStream_t s : {h->s_main, h->s_index, h->s_copy})
     if (s) cudaStreamDestroy(s);
   delete h;
 }
@@ -885,6 +938,12 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
 
   FI_TRY(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
   FI_TRY(cudaStreamCreateWithFlags(&h->s_index, cudaStreamNonBlocking));
+  FI_TRY(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+  for (int k = 0; k < fi_epp::kMaxFeedSlices; ++k) FI_TRY(cudaEventCreateWithFlags(&h->ev_copy[k], cudaEventDisableTiming));
+  if (const char* e = std::getenv("FI_EPP_FEED_SLICES")) {
+    const long v = std::strtol(e, nullptr, 10);
+    h->feed_slices = (uint32_t)std::min<long>(std::max<long>(v, 1), fi_epp::kMaxFeedSlices);
+  }
   for (cudaEvent_t* e : {&h->ev_index, &h->ev_user, &h->ev_done, &h->ev_ctr})
     FI_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   FI_TRY(cudaEventRecord(h->ev_index, h->s_index));
@@ -1123,13 +1182,16 @@ static int check_batch(fi_epp* h, const uint64_t* offsets, uint32_t R, uint64_t*
 }
 
 static int stage_inputs(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
-                        uint64_t total) {
+                        uint64_t total, bool copy_prompts = true) {
   std::memcpy(h->h_offsets, offsets, (size_t)(R + 1) * sizeof(uint64_t));
   std::memcpy(h->h_h0, h0, (size_t)R * sizeof(uint64_t));
   FI_CUDA(cudaMemcpyAsync(h->d_offsets, h->h_offsets, (size_t)(R + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->s_main));
   FI_CUDA(cudaMemcpyAsync(h->d_h0, h->h_h0, (size_t)R * sizeof(uint64_t), cudaMemcpyHostToDevice, h->s_main));
-  if (total) FI_CUDA(cudaMemcpyAsync(h->d_prompts, prompts, total, cudaMemcpyHostToDevice, h->s_main));
-  h->stats.h2d_bytes += total + (size_t)(2 * R + 1) * sizeof(uint64_t);
+  if (total && copy_prompts) {
+    FI_CUDA(cudaMemcpyAsync(h->d_prompts, prompts, total, cudaMemcpyHostToDevice, h->s_main));
+    h->stats.h2d_bytes += total;
+  }
+  h->stats.h2d_bytes += (size_t)(2 * R + 1) * sizeof(uint64_t);
   return FI_OK;
 }
 
@@ -1180,14 +1242,15 @@ int fi_epp_pick_batch_lora(fi_epp* h, const uint8_t* prompts, const uint64_t* of
   uint64_t total = 0;
   int rc = check_batch(h, offsets, R, &total);
   if (rc != FI_OK) return rc;
-  rc = stage_inputs(h, prompts, offsets, h0, R, total);
+  rc = stage_inputs(h, prompts, offsets, h0, R, total, /*copy_prompts=*/false);  // run_pick feeds the prompts
   if (rc != FI_OK) return rc;
   if (adapters) {
     std::memcpy(h->h_adapters, adapters, (size_t)R * sizeof(uint64_t));
     FI_CUDA(cudaMemcpyAsync(h->d_adapters, h->h_adapters, (size_t)R * sizeof(uint64_t), cudaMemcpyHostToDevice, h->s_main));
     h->stats.h2d_bytes += (size_t)R * sizeof(uint64_t);
   }
-  rc = run_pick(h, h->d_prompts, h->d_offsets, h->d_h0, adapters ? h->d_adapters : nullptr, R, h->d_picks);
+  const HostFeed feed{prompts, offsets};
+  rc = run_pick(h, h->d_prompts, h->d_offsets, h->d_h0, adapters ? h->d_adapters : nullptr, R, h->d_picks, &feed);
   if (rc != FI_OK) return rc;
   const size_t pb = (size_t)R * h->P * sizeof(fi_pick);
   FI_CUDA(cudaMemcpyAsync(h->h_picks, h->d_picks, pb, cudaMemcpyDeviceToHost, h->s_main));

@@ -383,3 +383,31 @@ def test_pick_parity_lora_affinity(E, scorers):
     want0 = cpu.pick_batch(tok, offs, wl.h0)
     assert H.picks_equal(got0, want0), H.describe_diff(got0, want0)
     gpu.close()
+
+
+@pytest.mark.parametrize("slices", ["1", "3", "8", "16"])
+def test_host_path_sliced_feed_is_exact(slices, monkeypatch):
+    """fi_epp_pick_batch copies the prompts in slices and runs hash/walk/match per slice while the next
+    slice is in flight (>= 8 MB of prompts): ragged prompt lengths, a batch size that is not a multiple of
+    the slice size, PD profiles, chains_out — all equal to the oracle and to the single-copy path."""
+    monkeypatch.setenv("FI_EPP_FEED_SLICES", slices)
+    wl = synth.Workload(R=1000, E=96, T=4096, seed=synth.SEEDS[1], lru_capacity=2000, pd=True)
+    profiles, pd = synth.baseline_profiles(5)
+    pd = dict(pd, threshold=9000.0)
+    cfg = H.config_for(wl, profiles=profiles, pd=pd, max_prompt_bytes=wl.R * wl.T * 4)
+    gpu, cpu = _pair(cfg)
+    _load(wl, gpu, cpu)
+    tok, offs = wl.prompts()
+    # ragged: cut a pseudo-random tail off every prompt (keeps 4-byte token alignment, some become empty)
+    rng = np.random.default_rng(7)
+    keep = rng.integers(0, wl.T + 1, size=wl.R)
+    keep[::9] = wl.T
+    keep[5] = 0
+    blobs = [tok[r, : keep[r]].tobytes() for r in range(wl.R)]
+    data, offs = H.pack_prompts(blobs)
+    assert len(data) >= (8 << 20)
+    got, gch = gpu.pick_batch(data, offs, wl.h0, want_chains=True)
+    want, wch = cpu.pick_batch(data, offs, wl.h0, want_chains=True)
+    assert H.picks_equal(got, want), H.describe_diff(got, want)
+    assert np.array_equal(gch, wch)
+    gpu.close()
