@@ -51,6 +51,20 @@ __device__ __forceinline__ uint32_t index_resolve(const IndexView& ix, uint64_t 
   return SLOT_MISS;
 }
 
+// out-of-line continuation of a lookup whose home bucket was full without a match (keeps callers that
+// hold several buckets in registers small)
+static __device__ __noinline__ uint32_t index_resolve_overflow(const IndexView ix, uint64_t h) {
+  uint64_t b = h & ix.bmask;
+  for (uint64_t it = 0; it < ix.bmask; ++it) {
+    b = (b + 1) & ix.bmask;
+    const BucketRegs r = bucket_load(ix, b);
+    const int j = bucket_scan(r, h);
+    if (j < BUCKET_KEYS) return (uint32_t)(b * BUCKET_KEYS + j);
+    if (j == BUCKET_KEYS) return SLOT_MISS;
+  }
+  return SLOT_MISS;
+}
+
 __device__ __forceinline__ bool key_is_special(uint64_t h) { return h == KEY_EMPTY || h == KEY_TOMB; }
 
 // slot holding key h, whatever its row (regular keys: present ⇒ row non-empty)
@@ -67,5 +81,8 @@ __device__ __forceinline__ uint32_t index_find(const IndexView& ix, uint64_t h) 
   }
   return index_resolve(ix, h, bucket_load(ix, h & ix.bmask));
 }
+
+// out-of-line index_find for the rare paths of callers that keep several lookups in flight
+static __device__ __noinline__ uint32_t index_find_slow(const IndexView ix, uint64_t h) { return index_find(ix, h); }
 
 }  // namespace fi

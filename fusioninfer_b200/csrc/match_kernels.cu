@@ -457,25 +457,53 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
 // Sharded upstream mode, first pass: probe every block of every request once.  The slot of each block is
 // kept for the match pass (which then never touches the key array), and the presence mask of the request
 // goes out to every rank — tagged words into peer memory, or a plain array for the NCCL all-gather.
-__global__ void __launch_bounds__(kWarps * 32) probe_slots_kernel(const MatchParams p, uint32_t* __restrict__ mask_out) {
+__global__ void __launch_bounds__(kWarps * 32, 4) probe_slots_kernel(const MatchParams p, uint32_t* __restrict__ mask_out) {
+  constexpr int D = 4;  // chunks of 32 blocks whose home-bucket loads are in flight together (per lane)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   for (uint32_t r = blockIdx.x * kWarps + warp; r < p.R; r += gridDim.x * kWarps) {
     const uint32_t n = p.nblocks[r];
     const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
-    for (uint32_t c = 0; c < p.mask_words; ++c) {
-      const uint32_t idx = c * 32 + lane;
-      uint32_t slot = SLOT_MISS;
-      if (idx < n) slot = index_find(p.ix, crow[idx]);
-      if (idx < p.MP) p.slots[(uint64_t)r * p.MP + idx] = slot;
-      const unsigned m = __ballot_sync(FULL, slot != SLOT_MISS);
-      if (p.px.enabled) {
-        for (uint32_t k = lane; k < p.px.world; k += 32)
-          ll_store(reinterpret_cast<uint64_t*>(p.px.base[k] + p.px.off_mask[p.px.step & 1u]) +
-                       ((uint64_t)p.px.rank * p.R + r) * p.mask_words + c,
-                   m, p.px.step);
-      } else if (lane == 0) {
-        mask_out[(uint64_t)r * p.mask_words + c] = m;
+    for (uint32_t c0 = 0; c0 < p.mask_words; c0 += D) {
+      uint64_t hk[D];
+      BucketRegs br[D];
+      bool valid[D], plain[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const uint32_t idx = (c0 + d) * 32 + lane;
+        valid[d] = idx < n;
+        hk[d] = valid[d] ? crow[idx] : 0;
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        plain[d] = valid[d] && !key_is_special(hk[d]);
+#pragma unroll
+        for (int qq = 0; qq < BUCKET_KEYS / 2; ++qq) br[d].q[qq] = make_uint4(0, 0, 0, 0);
+        if (plain[d]) br[d] = bucket_load(p.ix, hk[d] & p.ix.bmask);
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const uint32_t c = c0 + d;
+        if (c >= p.mask_words) break;  // warp-uniform
+        const uint32_t idx = c * 32 + lane;
+        uint32_t slot = SLOT_MISS;
+        if (plain[d]) {
+          const int j = bucket_scan(br[d], hk[d]);
+          if (j < BUCKET_KEYS) slot = (uint32_t)((hk[d] & p.ix.bmask) * BUCKET_KEYS + j);
+          else if (j > BUCKET_KEYS) slot = index_resolve_overflow(p.ix, hk[d]);
+        } else if (valid[d]) {
+          slot = index_find_slow(p.ix, hk[d]);
+        }
+        if (idx < p.MP) p.slots[(uint64_t)r * p.MP + idx] = slot;
+        const unsigned m = __ballot_sync(FULL, slot != SLOT_MISS);
+        if (p.px.enabled) {
+          for (uint32_t k = lane; k < p.px.world; k += 32)
+            ll_store(reinterpret_cast<uint64_t*>(p.px.base[k] + p.px.off_mask[p.px.step & 1u]) +
+                         ((uint64_t)p.px.rank * p.R + r) * p.mask_words + c,
+                     m, p.px.step);
+        } else if (lane == 0) {
+          mask_out[(uint64_t)r * p.mask_words + c] = m;
+        }
       }
     }
   }
