@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
   uint64_t* s_chain = s_mem + (size_t)warp * p.MP;
   const IndexView ix = p.ix;
   const uint32_t P = p.st.n_profiles;
-  const uint32_t* row_base = ix.rows + t * VEC;
+  const char* row_base = reinterpret_cast<const char*>(ix.rows + t * VEC);
+  const uint32_t row_bytes = 4u << ix.logW;
   const uint32_t zero_slot = (uint32_t)(ix.C + 2);  // never written: all-zero row
 
   // dynamic work queue (requests differ a lot in how many rows they touch); the next item is
@@ -252,7 +253,9 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
           }
         }
       }
-      // rows of this chunk
+      // rows of this chunk; rows past the first miss read the permanently-zero row instead of being
+      // predicated off (decided once per chunk, so a row load is shuffle + multiply-add + load)
+      const uint32_t slot_eff = ((uint32_t)lane < rows_here && slot != SLOT_MISS) ? slot : zero_slot;
 #pragma unroll 1
       for (int q0 = 0; q0 < LPR; q0 += BATCH) {
         if ((uint32_t)(q0 * G) >= rows_here) break;
@@ -260,11 +263,9 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
 #pragma unroll
         for (int qi = 0; qi < BATCH; ++qi) {
           const int j = (q0 + qi) * G + g;  // row of the chunk this lane helps read
-          uint32_t s = __shfl_sync(FULL, slot, j & 31);
-          // rows past the first miss read the permanently-zero row instead of being predicated off
-          if ((uint32_t)j >= rows_here || s == SLOT_MISS) s = zero_slot;
+          const uint32_t s = __shfl_sync(FULL, slot_eff, j);
           uint32_t tmp[VEC];
-          load_row_words<VEC>(row_base + ((uint64_t)s << ix.logW), true, tmp);
+          load_row_words<VEC>(reinterpret_cast<const uint32_t*>(row_base + (uint64_t)s * row_bytes), true, tmp);
 #pragma unroll
           for (int x = 0; x < VEC; ++x) w[x][qi] = tmp[x];
         }

@@ -1,11 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q --timeout 900 2>&1 | tail -n 4
-for S in 8 1 4 16 8; do
-FI_EPP_FEED_SLICES=$S timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/feed_$S.json 2> gpurun_out/feed_$S.err
-python - gpurun_out/feed_$S.json $S <<'PY'
+show() { python - "$1" "$2" <<'PY'
 import json,sys
 d=json.load(open(sys.argv[1]))
-print("feed_slices", sys.argv[2], "value %.1fM" % (d["value"]/1e6), "e2e %.3fM/s  %.3f ms/step" % (d["e2e"]["value"]/1e6, d["e2e"]["ms_per_step"]), "parity", d.get("parity"))
+print("%s value=%.1fM ms=%.4f kernel_ms=%s" % (sys.argv[2], d["value"]/1e6, d["ms_per_step"], {k:round(v,4) for k,v in d["roofline"]["kernel_ms"].items()}))
 PY
-done
+}
+run() { env "$@" timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu --no-e2e > gpurun_out/ab.json 2> gpurun_out/ab.err; show gpurun_out/ab.json "$*"; }
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 600 2>&1 | tail -n 2
+run A=1
+run A=2
