@@ -189,6 +189,21 @@ def run_reference(args, wl, cfg_id):
     print(json.dumps(line), flush=True)
 
 
+class stdout_to_stderr:
+    """Point file descriptor 1 at stderr for the duration (native libraries print to fd 1 directly)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def workload_config(wl, cfg_id, parallelism):
     return {
         "workload": f"cfg{cfg_id}: {wl.R} req x {wl.E} endpoints x {wl.T}-token prompts (uint32), "
@@ -245,7 +260,14 @@ def main():
         # stdout carries exactly one JSON line: keep NCCL's version banner off it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
-        fdist.init_process_group("nccl")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its banner when the first communicator is created (lazily, at the first collective):
+        # do that now with fd 1 pointing at stderr, whatever the debug settings of the box are
+        with stdout_to_stderr():
+            fdist.init_process_group("nccl")
+            torch.cuda.set_device(local)
+            fdist.barrier()
+            torch.cuda.synchronize()
     torch.cuda.set_device(local)
 
     # ---- set-up (untimed) ----------------------------------------------------------
@@ -258,7 +280,8 @@ def main():
     picker = EndpointPicker(cfg)
     if mode == "sharded" and world > 1:
         uid = EndpointPicker.comm_unique_id() if rank == 0 else None
-        picker.comm_init(fdist.broadcast_bytes(uid, 128), rank, world)
+        with stdout_to_stderr():  # the library's own communicator
+            picker.comm_init(fdist.broadcast_bytes(uid, 128), rank, world)
     exchange = picker.comm_exchange()
     picker.update_endpoints(wl.endpoint_states())
     n_ops = 0
