@@ -268,9 +268,13 @@ int alloc_index(fi_epp* h, uint64_t slots, IndexView* out) {
   while ((1u << v.logW) < v.W) ++v.logW;
   const uint64_t total = slots + 3;  // + slots for hash 0, hash ~0, and a permanently-zero row
   FI_CUDA(cudaMalloc(&v.keys, total * sizeof(uint64_t)));
+  FI_CUDA(cudaMalloc(&v.node_of, total * sizeof(uint32_t)));
+  FI_CUDA(cudaMalloc(&v.klog, total * sizeof(uint64_t)));
   FI_CUDA(cudaMalloc(&v.rows, total * v.W * sizeof(uint32_t)));
   FI_CUDA(cudaMalloc(&v.cnt, total * sizeof(uint32_t)));
   FI_CUDA(cudaMemsetAsync(v.keys, 0, total * sizeof(uint64_t), h->s_index));
+  FI_CUDA(cudaMemsetAsync(v.node_of, 0xFF, total * sizeof(uint32_t), h->s_index));  // NODE_INVALID
+  FI_CUDA(cudaMemsetAsync(v.klog, 0, total * sizeof(uint64_t), h->s_index));
   FI_CUDA(cudaMemsetAsync(v.rows, 0, total * v.W * sizeof(uint32_t), h->s_index));
   FI_CUDA(cudaMemsetAsync(v.cnt, 0, total * sizeof(uint32_t), h->s_index));
   *out = v;
@@ -279,9 +283,13 @@ int alloc_index(fi_epp* h, uint64_t slots, IndexView* out) {
 
 void free_index(IndexView& v) {
   cudaFree(v.keys);
+  cudaFree(v.node_of);
+  cudaFree(v.klog);
   cudaFree(v.rows);
   cudaFree(v.cnt);
   v.keys = nullptr;
+  v.node_of = nullptr;
+  v.klog = nullptr;
   v.rows = nullptr;
   v.cnt = nullptr;
 }

@@ -1,12 +1,24 @@
 // index_device.cuh — device-side lookup of the hash index (see index_kernels.cu).
+//
+// Two levels: the open-addressed TABLE (keys[slot], node_of[slot]; buckets of 4 keys = one 32-byte
+// sector, linear probing over buckets) maps a block hash to a NODE; nodes are numbered in insertion
+// order and own the data: klog[node] = the key, rows[node] = the membership bitset, cnt[node] = its
+// popcount.  Lookups return node ids.  Because a prompt's block hashes are inserted in chain order
+// (upstream PreRequest: indexer.Add(hashes, pod)), the nodes of a cached prefix are consecutive: the
+// match kernel verifies "node of block i+1 == node of block i + 1" with one coalesced read of klog
+// instead of hashing into the table for every block (index_kernels.cu, match_kernels.cu).
 #pragma once
 #include "kernels.cuh"
 
 namespace fi {
 
+constexpr uint32_t NODE_INVALID = 0xFFFFFFFFu;  // node_of[] of a slot whose node is not published yet
+
 struct BucketRegs {
-  uint4 q[BUCKET_KEYS / 2];  // BUCKET_KEYS keys = one 64-byte bucket (two adjacent 32 B sectors)
+  uint4 q[BUCKET_KEYS / 2];  // the bucket's BUCKET_KEYS keys
+  uint4 nodes;               // and their nodes (node_of[b*4 .. b*4+3]) — loaded in parallel, not after the scan
 };
+static_assert(BUCKET_KEYS == 4, "BucketRegs::nodes holds exactly four node ids");
 
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
@@ -16,6 +28,7 @@ __device__ __forceinline__ BucketRegs bucket_load(const IndexView& ix, uint64_t 
   BucketRegs r;
 #pragma unroll
   for (int i = 0; i < BUCKET_KEYS / 2; ++i) r.q[i] = __ldg(p + i);
+  r.nodes = __ldg(reinterpret_cast<const uint4*>(ix.node_of + b * BUCKET_KEYS));
   return r;
 }
 
@@ -35,45 +48,41 @@ __device__ __forceinline__ int bucket_scan(const BucketRegs& r, uint64_t h) {
   return empty ? BUCKET_KEYS : BUCKET_KEYS + 1;
 }
 
-// finish a lookup whose home bucket was loaded into `first`
-__device__ __forceinline__ uint32_t index_resolve(const IndexView& ix, uint64_t h, const BucketRegs& first) {
-  uint64_t b = h & ix.bmask;
-  int j = bucket_scan(first, h);
-  if (j < BUCKET_KEYS) return (uint32_t)(b * BUCKET_KEYS + j);
-  if (j == BUCKET_KEYS) return SLOT_MISS;
-  for (uint64_t it = 0; it < ix.bmask; ++it) {  // rare: home bucket full
-    b = (b + 1) & ix.bmask;
-    const BucketRegs r = bucket_load(ix, b);
-    j = bucket_scan(r, h);
-    if (j < BUCKET_KEYS) return (uint32_t)(b * BUCKET_KEYS + j);
-    if (j == BUCKET_KEYS) return SLOT_MISS;
-  }
-  return SLOT_MISS;
+__device__ __forceinline__ uint32_t bucket_node(const BucketRegs& r, int j) {
+  return j == 0 ? r.nodes.x : j == 1 ? r.nodes.y : j == 2 ? r.nodes.z : r.nodes.w;
 }
 
-// out-of-line continuation of a lookup whose home bucket was full without a match (keeps callers that
-// hold several buckets in registers small)
+// out-of-line continuation of a lookup whose home bucket was full without a match
 static __device__ __noinline__ uint32_t index_resolve_overflow(const IndexView ix, uint64_t h) {
   uint64_t b = h & ix.bmask;
   for (uint64_t it = 0; it < ix.bmask; ++it) {
     b = (b + 1) & ix.bmask;
     const BucketRegs r = bucket_load(ix, b);
     const int j = bucket_scan(r, h);
-    if (j < BUCKET_KEYS) return (uint32_t)(b * BUCKET_KEYS + j);
+    if (j < BUCKET_KEYS) return bucket_node(r, j);
     if (j == BUCKET_KEYS) return SLOT_MISS;
   }
   return SLOT_MISS;
 }
 
+// finish a lookup whose home bucket was loaded into `first`: node of h, or SLOT_MISS
+__device__ __forceinline__ uint32_t index_resolve(const IndexView& ix, uint64_t h, const BucketRegs& first) {
+  const int j = bucket_scan(first, h);
+  if (j < BUCKET_KEYS) return bucket_node(first, j);
+  if (j == BUCKET_KEYS) return SLOT_MISS;
+  return index_resolve_overflow(ix, h);  // rare: home bucket full
+}
+
 __device__ __forceinline__ bool key_is_special(uint64_t h) { return h == KEY_EMPTY || h == KEY_TOMB; }
 
-// slot holding key h, whatever its row (regular keys: present ⇒ row non-empty)
+// node holding key h, whatever its row (regular keys: present ⇔ row non-empty).  The hashes 0 and ~0
+// (the table's EMPTY / TOMB markers) own the fixed nodes C and C+1.
 __device__ __forceinline__ uint32_t index_find_key(const IndexView& ix, uint64_t h) {
   if (key_is_special(h)) return (uint32_t)(ix.C + (h == KEY_TOMB ? 1 : 0));
   return index_resolve(ix, h, bucket_load(ix, h & ix.bmask));
 }
 
-// slot of h if at least one local endpoint holds it, else SLOT_MISS
+// node of h if at least one local endpoint holds it, else SLOT_MISS
 __device__ __forceinline__ uint32_t index_find(const IndexView& ix, uint64_t h) {
   if (key_is_special(h)) {
     const uint64_t s = ix.C + (h == KEY_TOMB ? 1 : 0);
@@ -84,5 +93,11 @@ __device__ __forceinline__ uint32_t index_find(const IndexView& ix, uint64_t h) 
 
 // out-of-line index_find for the rare paths of callers that keep several lookups in flight
 static __device__ __noinline__ uint32_t index_find_slow(const IndexView ix, uint64_t h) { return index_find(ix, h); }
+
+// Speculation: is `cand` the node of the regular key h?  (klog of a free or retired node is 0, and a
+// regular key is never 0.)
+__device__ __forceinline__ bool node_holds(const IndexView& ix, uint32_t cand, uint64_t h) {
+  return cand < ix.C && __ldg(ix.klog + cand) == h;
+}
 
 }  // namespace fi

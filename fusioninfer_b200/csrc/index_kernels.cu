@@ -5,10 +5,13 @@
 // physically a table keyed by block hash whose value is a bitset row over the local
 // endpoints: one 128 B row read answers "which of 1024 endpoints hold this block".
 // Keys live in buckets of 4 (one 32 B sector); linear probing over buckets.
-// Inserts claim an EMPTY key with atomicCAS, membership bits flip with
+// Inserts claim an EMPTY key with atomicCAS and give it the next NODE: nodes are
+// numbered in insertion order and own the key's row (index_device.cuh), so a chain
+// inserted in order occupies consecutive rows.  Membership bits flip with
 // atomicOr/atomicAnd, cnt tracks the row popcount so that "key present ⇔ row
-// non-empty" holds: a key whose row empties becomes a tombstone (never reused
-// until a rebuild), which keeps lookups exact without reading the row.
+// non-empty" holds: a key whose row empties becomes a tombstone and its node is
+// retired (neither is reused until a rebuild compacts the live nodes in order),
+// which keeps lookups exact without reading the row.
 #include "index_device.cuh"
 #include "kernels.cuh"
 
@@ -16,10 +19,10 @@ namespace fi {
 
 namespace {
 
-// find the slot of h or claim an EMPTY one.  SLOT_MISS on a full table.
-__device__ uint32_t index_find_or_claim(const IndexView& ix, IndexCounters* ctr, uint64_t h) {
-  if (h == KEY_EMPTY) return (uint32_t)ix.C;
-  if (h == KEY_TOMB) return (uint32_t)(ix.C + 1);
+// find the table slot of h or claim an EMPTY one (*claimed = true: the caller allocates its node).
+// SLOT_MISS on a full table.
+__device__ uint32_t table_find_or_claim(const IndexView& ix, IndexCounters* ctr, uint64_t h, bool* claimed) {
+  *claimed = false;
   uint64_t b = h & ix.bmask;
   for (uint64_t it = 0; it <= ix.bmask; ++it) {
     unsigned long long* kb = reinterpret_cast<unsigned long long*>(ix.keys + b * BUCKET_KEYS);
@@ -30,7 +33,7 @@ __device__ uint32_t index_find_or_claim(const IndexView& ix, IndexCounters* ctr,
       if (k == KEY_EMPTY) {
         unsigned long long old = atomicCAS(kb + j, (unsigned long long)KEY_EMPTY, (unsigned long long)h);
         if (old == KEY_EMPTY) {
-          atomicAdd(&ctr->used, 1ull);
+          *claimed = true;
           return (uint32_t)(b * BUCKET_KEYS + j);
         }
         if (old == h) return (uint32_t)(b * BUCKET_KEYS + j);
@@ -43,19 +46,100 @@ __device__ uint32_t index_find_or_claim(const IndexView& ix, IndexCounters* ctr,
   return SLOT_MISS;
 }
 
+// Node allocation of one CTA pass: the threads that claimed a new key get CONSECUTIVE nodes in thread
+// (= op) order — one atomicAdd per CTA — so the keys of a chain that arrives as consecutive ops sit
+// next to each other in klog / rows.  Returns the node of a claiming thread (NODE_INVALID on overflow).
+__device__ uint32_t alloc_nodes_cta(const IndexView& ix, IndexCounters* ctr, bool claimed) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ unsigned long long s_base;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, claimed);
+  const uint32_t rank_in_warp = __popc(m & ((1u << lane) - 1u));
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t c = s_warp[w];
+      s_warp[w] = tot;
+      tot += c;
+    }
+    s_base = tot ? atomicAdd(&ctr->used, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  uint32_t node = NODE_INVALID;
+  if (claimed) {
+    const unsigned long long n = s_base + s_warp[warp] + rank_in_warp;
+    if (n < ix.C) node = (uint32_t)n;
+    else atomicExch(&ctr->overflow, 1ull);
+  }
+  __syncthreads();  // s_warp / s_base are reused by the next pass
+  return node;
+}
+
+// node of a slot some other thread claimed: wait until that thread has published it
+__device__ __forceinline__ uint32_t wait_node(const IndexView& ix, uint32_t slot) {
+  const volatile uint32_t* p = ix.node_of + slot;
+  uint32_t n;
+  while ((n = *p) == NODE_INVALID) __nanosleep(20);
+  return n;
+}
+
 __global__ void __launch_bounds__(256) index_set_kernel(IndexView ix, IndexCounters* ctr,
                                                         const fi_index_op* __restrict__ ops, uint64_t n,
                                                         uint32_t ep_begin, uint32_t ep_count) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const fi_index_op op = ops[i];
-    const uint32_t e = op.endpoint - ep_begin;
-    if (op.op != FI_OP_SET || e >= ep_count) continue;
-    const uint32_t slot = index_find_or_claim(ix, ctr, op.hash);
-    if (slot == SLOT_MISS) continue;
-    const uint32_t bit = 1u << (e & 31);
-    const uint32_t old = atomicOr(ix.rows + ((uint64_t)slot << ix.logW) + (e >> 5), bit);
-    if (!(old & bit)) atomicAdd(ix.cnt + slot, 1u);
+  // every thread of a CTA runs the same number of passes (block-wide barriers inside)
+  for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = base + threadIdx.x;
+    fi_index_op op{};
+    bool active = false;
+    uint32_t e = 0;
+    if (i < n) {
+      op = ops[i];
+      e = op.endpoint - ep_begin;
+      active = op.op == FI_OP_SET && e < ep_count;
+    }
+    // 1. table slot (claim an empty one for a new key)
+    bool claimed = false;
+    uint32_t slot = SLOT_MISS, node = NODE_INVALID;
+    if (active) {
+      if (key_is_special(op.hash)) node = (uint32_t)(ix.C + (op.hash == KEY_TOMB ? 1 : 0));
+      else slot = table_find_or_claim(ix, ctr, op.hash, &claimed);
+    }
+    // 2. new keys get consecutive nodes in op order and publish them
+    const uint32_t mine = alloc_nodes_cta(ix, ctr, claimed);
+    if (claimed) {
+      if (mine != NODE_INVALID) {
+        node = mine;
+        ix.klog[node] = op.hash;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(ix.node_of + slot) = node;
+      } else {  // out of nodes (reported through ctr->overflow): park the key on the zero row
+        *reinterpret_cast<volatile uint32_t*>(ix.node_of + slot) = (uint32_t)(ix.C + 2);
+      }
+    }
+    // 3. keys that were already there (possibly claimed by another CTA a moment ago): their node.  No
+    // thread waits before it has published its own nodes, so the waits cannot form a cycle.
+    if (active && !claimed && slot != SLOT_MISS) node = wait_node(ix, slot);
+    if (active && node != NODE_INVALID && node != (uint32_t)(ix.C + 2)) {
+      const uint32_t bit = 1u << (e & 31);
+      const uint32_t old = atomicOr(ix.rows + ((uint64_t)node << ix.logW) + (e >> 5), bit);
+      if (!(old & bit)) atomicAdd(ix.cnt + node, 1u);
+    }
   }
+}
+
+// table slot of a regular key (not its node): the clear path retires the slot
+__device__ uint32_t table_find_slot(const IndexView& ix, uint64_t h) {
+  uint64_t b = h & ix.bmask;
+  for (uint64_t it = 0; it <= ix.bmask; ++it) {
+    const BucketRegs r = bucket_load(ix, b);
+    const int j = bucket_scan(r, h);
+    if (j < BUCKET_KEYS) return (uint32_t)(b * BUCKET_KEYS + j);
+    if (j == BUCKET_KEYS) return SLOT_MISS;
+    b = (b + 1) & ix.bmask;
+  }
+  return SLOT_MISS;
 }
 
 __global__ void __launch_bounds__(256) index_clear_kernel(IndexView ix, IndexCounters* ctr,
@@ -65,39 +149,54 @@ __global__ void __launch_bounds__(256) index_clear_kernel(IndexView ix, IndexCou
     const fi_index_op op = ops[i];
     const uint32_t e = op.endpoint - ep_begin;
     if (op.op != FI_OP_CLEAR || e >= ep_count) continue;
-    const uint32_t slot = index_find_key(ix, op.hash);
-    if (slot == SLOT_MISS) continue;
+    uint32_t slot = SLOT_MISS, node;
+    if (key_is_special(op.hash)) {
+      node = (uint32_t)(ix.C + (op.hash == KEY_TOMB ? 1 : 0));
+    } else {
+      slot = table_find_slot(ix, op.hash);
+      if (slot == SLOT_MISS) continue;
+      node = ix.node_of[slot];
+    }
     const uint32_t bit = 1u << (e & 31);
-    const uint32_t old = atomicAnd(ix.rows + ((uint64_t)slot << ix.logW) + (e >> 5), ~bit);
+    const uint32_t old = atomicAnd(ix.rows + ((uint64_t)node << ix.logW) + (e >> 5), ~bit);
     if (old & bit) {
-      const uint32_t c = atomicSub(ix.cnt + slot, 1u);
-      if (c == 1u && slot < ix.C) {  // row emptied: retire the key
+      const uint32_t c = atomicSub(ix.cnt + node, 1u);
+      if (c == 1u && slot != SLOT_MISS) {  // row emptied: retire the key and its node
         ix.keys[slot] = KEY_TOMB;
+        ix.klog[node] = 0;
         atomicAdd(&ctr->tombstones, 1ull);
       }
     }
   }
 }
 
-// re-insert every live key of `from` into the (zeroed) table `to`, moving its row
+// Re-insert every live node of `from` into the (fresh) index `to`, in node order, so that runs of
+// consecutive nodes stay consecutive (each CTA pass compacts 256 consecutive old nodes into one range).
 __global__ void __launch_bounds__(256) index_rebuild_kernel(IndexView from, IndexView to, IndexCounters* ctr) {
-  const uint64_t total = from.C + 2;
-  for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < total;
-       s += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t h;
-    if (s >= from.C) {
-      if (from.cnt[s] == 0) continue;
-      h = (s == from.C) ? KEY_EMPTY : KEY_TOMB;
-    } else {
-      h = from.keys[s];
-      if (h == KEY_EMPTY || h == KEY_TOMB) continue;
+  for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < from.C; base += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t s = base + threadIdx.x;
+    uint64_t h = 0;
+    if (s < from.C) h = from.klog[s];
+    bool claimed = false;
+    uint32_t slot = SLOT_MISS;
+    if (h != 0) slot = table_find_or_claim(to, ctr, h, &claimed);  // keys are unique: always a fresh claim
+    const uint32_t d = alloc_nodes_cta(to, ctr, claimed);
+    if (claimed && d != NODE_INVALID) {
+      to.klog[d] = h;
+      to.node_of[slot] = d;
+      to.cnt[d] = from.cnt[s];
+      const uint32_t* src = from.rows + (s << from.logW);
+      uint32_t* dst = to.rows + ((uint64_t)d << to.logW);
+      for (uint32_t w = 0; w < from.W; ++w) dst[w] = src[w];
     }
-    const uint32_t d = index_find_or_claim(to, ctr, h);
-    if (d == SLOT_MISS) continue;
-    to.cnt[d] = from.cnt[s];
-    const uint32_t* src = from.rows + (s << from.logW);
-    uint32_t* dst = to.rows + ((uint64_t)d << to.logW);
-    for (uint32_t w = 0; w < from.W; ++w) dst[w] = src[w];
+  }
+  // the two special nodes keep their place
+  if (blockIdx.x == 0 && threadIdx.x < 2) {
+    const uint64_t s = from.C + threadIdx.x;
+    if (from.cnt[s]) {
+      to.cnt[s] = from.cnt[s];
+      for (uint32_t w = 0; w < from.W; ++w) to.rows[(s << to.logW) + w] = from.rows[(s << from.logW) + w];
+    }
   }
 }
 
@@ -109,8 +208,8 @@ __global__ void __launch_bounds__(256) index_contains_kernel(IndexView ix, const
     const uint32_t e = q[i].endpoint - ep_begin;
     uint8_t r = 0;
     if (e < ep_count) {
-      const uint32_t slot = index_find(ix, q[i].hash);
-      if (slot != SLOT_MISS) r = (ix.rows[((uint64_t)slot << ix.logW) + (e >> 5)] >> (e & 31)) & 1u;
+      const uint32_t node = index_find(ix, q[i].hash);
+      if (node != SLOT_MISS) r = (ix.rows[((uint64_t)node << ix.logW) + (e >> 5)] >> (e & 31)) & 1u;
     }
     out[i] = r;
   }
@@ -140,7 +239,7 @@ cudaError_t launch_index_clear(IndexView ix, IndexCounters* ctr, const fi_index_
 }
 
 cudaError_t launch_index_rebuild(IndexView from, IndexView to, IndexCounters* ctr, cudaStream_t s) {
-  index_rebuild_kernel<<<grid_for(from.C + 2), 256, 0, s>>>(from, to, ctr);
+  index_rebuild_kernel<<<grid_for(from.C), 256, 0, s>>>(from, to, ctr);
   return cudaGetLastError();
 }
 

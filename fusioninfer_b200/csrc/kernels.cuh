@@ -5,11 +5,13 @@
 //   pre       tiled u64     block pre-states (hash_blocks → chain_finalize): 16-byte unit u of
 //                           request r at ((r/32)*MP/2 + u)*32 + r%32 — coalesced for the chain walker
 //   chain     [R][MP] u64   chained block hashes h_1..h_n
-//   index     keys  [C+2]   u64, buckets of 4 keys = one 32 B sector; 0 = empty,
-//                           ~0 = tombstone; slots C, C+1 hold hashes 0 and ~0
-//             rows  [C+2][W] u32, row s = membership bitset of key s over the
-//                           local endpoints (bit e%32 of word e/32)
-//             cnt   [C+2]   u32 popcount of the row (key present ⇔ cnt > 0)
+//   index     keys    [C]     u64 table, buckets of 4 keys = one 32 B sector; 0 = empty, ~0 = tombstone
+//             node_of [C]     u32 node of the key in that slot
+//             klog    [C+3]   u64 key of node n (0: free / retired); nodes are numbered in insertion order,
+//                             nodes C, C+1 belong to the hashes 0 and ~0, node C+2 is a never-written row
+//             rows    [C+3][W] u32, row n = membership bitset of node n over the local endpoints
+//                             (bit e%32 of word e/32)
+//             cnt     [C+3]   u32 popcount of the row (key present ⇔ cnt > 0)
 //   picks     [R][P]        fi_pick
 #pragma once
 #include <cuda_runtime.h>
@@ -26,6 +28,8 @@ constexpr int BUCKET_KEYS = 4;  // one 32-byte sector (64-byte buckets of 8 were
 
 struct IndexView {
   uint64_t* keys;
+  uint32_t* node_of;
+  uint64_t* klog;
   uint32_t* rows;
   uint32_t* cnt;
   uint64_t bmask;  // buckets - 1
@@ -36,7 +40,7 @@ struct IndexView {
 
 // device-side counters of the index (one cache line)
 struct IndexCounters {
-  unsigned long long used;        // slots claimed (keys + tombstones)
+  unsigned long long used;        // slots claimed = nodes allocated (keys + tombstones)
   unsigned long long tombstones;  // keys retired because their row emptied
   unsigned long long overflow;    // != 0: an insert found no free slot
   unsigned long long pad;

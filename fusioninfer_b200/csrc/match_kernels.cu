@@ -148,6 +148,45 @@ __device__ __forceinline__ void load_row_words(const uint32_t* __restrict__ p, b
   }
 }
 
+// Nodes of the (up to) 32 blocks of a chunk, one block per lane.  A cached prefix was inserted in chain
+// order, so its nodes are consecutive (index_device.cuh): lanes already confirmed by the caller's
+// speculation come in with done = true; for the rest, the FIRST unresolved lane looks its key up in the
+// hash table, and the lanes after it check "my node = that node + my distance" with one coalesced klog
+// read.  A miss ends the walk (the lanes behind it are irrelevant: both match modes stop at the first
+// block the index does not hold).  After two table lookups that did not settle the chunk (a prefix whose
+// nodes are scattered) every remaining lane probes the table in parallel, as a plain hash index would.
+__device__ __forceinline__ uint32_t resolve_chunk_nodes(const IndexView& ix, uint64_t h, bool valid, uint32_t node, bool done,
+                                                        int lane) {
+  const bool plain = valid && !key_is_special(h);
+  done = done || !valid;
+  for (int tries = 0;; ++tries) {
+    const unsigned m = __ballot_sync(FULL, !done);
+    if (!m) break;
+    if (tries < 2) {
+      const int first = __ffs(m) - 1;
+      uint32_t nf = SLOT_MISS;
+      if (lane == first) nf = index_find(ix, h);
+      nf = __shfl_sync(FULL, nf, first);
+      if (lane == first) {
+        node = nf;
+        done = true;
+      }
+      if (nf == SLOT_MISS) break;  // first miss of the request
+      if (!done && plain && lane > first) {
+        const uint32_t cand = nf + (uint32_t)(lane - first);
+        if (nf < ix.C && node_holds(ix, cand, h)) {
+          node = cand;
+          done = true;
+        }
+      }
+    } else if (!done) {
+      node = index_find(ix, h);
+      done = true;
+    }
+  }
+  return node;
+}
+
 // LPR lanes read one row (VEC words each, LPR*VEC = words per row); a load
 // instruction therefore covers G = 32/LPR rows.  E = 1024 → LPR 8, VEC 4: a 128-byte
 // row is 8 × 16-byte loads and one instruction brings in 4 rows; 32 rows in flight.
@@ -217,8 +256,13 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
 
     // ---- 2./3. probe + row reads, 32 blocks per chunk ---------------------------
     const uint32_t nchunks = (kg + 31) / 32;
-    uint32_t slot = SLOT_MISS;
-    if ((uint32_t)lane < kg) slot = GMASK ? __ldcg(p.slots + (uint64_t)r * p.MP + lane) : index_find(ix, s_chain[lane]);
+    uint32_t slot = SLOT_MISS;  // node of this lane's block of the current chunk
+    if (GMASK) {
+      if ((uint32_t)lane < kg) slot = __ldcg(p.slots + (uint64_t)r * p.MP + lane);
+    } else {
+      const bool v0 = (uint32_t)lane < kg;
+      slot = resolve_chunk_nodes(ix, v0 ? s_chain[lane] : 0ull, v0, SLOT_MISS, false, lane);
+    }
     for (uint32_t c = 0; c < nchunks; ++c) {
       uint32_t rows_here;
       bool stop = false;
@@ -232,24 +276,25 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
           real_miss = (c * 32 + rows_here) < n;
         }
       }
-      // issue the next chunk's probe before touching this chunk's rows
-      uint64_t hn = 0;
-      bool validn = false, plain = false;
-      BucketRegs brn;
-#pragma unroll
-      for (int qq = 0; qq < BUCKET_KEYS / 2; ++qq) brn.q[qq] = make_uint4(0, 0, 0, 0);
+      // Issue the next chunk's lookup before touching this chunk's rows: the speculative read of
+      // klog[node of this chunk's last block + 1 + lane] (all 32 lanes hit here, or we would stop).
+      uint64_t hn = 0, kspec = 0;
+      bool validn = false, spec = false;
+      uint32_t cand = SLOT_MISS;
       uint32_t slot_next = SLOT_MISS;
       bool resolved = GMASK;
       if (!stop && c + 1 < nchunks) {
         const uint32_t idx = (c + 1) * 32 + lane;
         validn = idx < kg;
-        if (validn) {
-          if (GMASK) {
-            slot_next = __ldcg(p.slots + (uint64_t)r * p.MP + idx);
-          } else {
+        if (GMASK) {
+          if (validn) slot_next = __ldcg(p.slots + (uint64_t)r * p.MP + idx);
+        } else {
+          const uint32_t last = __shfl_sync(FULL, slot, 31);
+          if (validn) {
             hn = s_chain[idx];
-            plain = !key_is_special(hn);
-            if (plain) brn = bucket_load(ix, hn & ix.bmask);
+            cand = last + 1u + (uint32_t)lane;
+            spec = last < ix.C && cand < ix.C && !key_is_special(hn);
+            if (spec) kspec = __ldg(ix.klog + cand);
           }
         }
       }
@@ -270,9 +315,9 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
           for (int x = 0; x < VEC; ++x) w[x][qi] = tmp[x];
         }
         if (!resolved) {
-          // resolve the next chunk's probe while this chunk's rows are in flight (a full
-          // home bucket costs a second dependent sector read; it overlaps the row latency)
-          if (validn) slot_next = plain ? index_resolve(ix, hn, brn) : index_find(ix, hn);
+          // settle the next chunk's nodes while this chunk's rows are in flight
+          const bool hit = spec && kspec == hn;
+          slot_next = resolve_chunk_nodes(ix, hn, validn, hit ? cand : SLOT_MISS, hit, lane);
           resolved = true;
         }
         if (LPM) {
@@ -307,7 +352,10 @@ __global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_k
           if (__any_sync(FULL, any != 0)) bc_add<BATCH>(cnt[x], w[x]);
         }
       }
-      if (!resolved && validn) slot_next = plain ? index_resolve(ix, hn, brn) : index_find(ix, hn);
+      if (!resolved) {
+        const bool hit = spec && kspec == hn;
+        slot_next = resolve_chunk_nodes(ix, hn, validn, hit ? cand : SLOT_MISS, hit, lane);
+      }
       matched_rows += rows_here;
       if (stop) break;
       if (LPM) {  // every local endpoint already dropped out: nothing more can match
@@ -480,6 +528,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) probe_slots_kernel(const Match
         plain[d] = valid[d] && !key_is_special(hk[d]);
 #pragma unroll
         for (int qq = 0; qq < BUCKET_KEYS / 2; ++qq) br[d].q[qq] = make_uint4(0, 0, 0, 0);
+        br[d].nodes = make_uint4(0, 0, 0, 0);
         if (plain[d]) br[d] = bucket_load(p.ix, hk[d] & p.ix.bmask);
       }
 #pragma unroll
@@ -490,7 +539,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) probe_slots_kernel(const Match
         uint32_t slot = SLOT_MISS;
         if (plain[d]) {
           const int j = bucket_scan(br[d], hk[d]);
-          if (j < BUCKET_KEYS) slot = (uint32_t)((hk[d] & p.ix.bmask) * BUCKET_KEYS + j);
+          if (j < BUCKET_KEYS) slot = bucket_node(br[d], j);
           else if (j > BUCKET_KEYS) slot = index_resolve_overflow(p.ix, hk[d]);
         } else if (valid[d]) {
           slot = index_find_slow(p.ix, hk[d]);
