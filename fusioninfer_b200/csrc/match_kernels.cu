@@ -191,7 +191,8 @@ __device__ __forceinline__ uint32_t resolve_chunk_nodes(const IndexView& ix, uin
 // instruction therefore covers G = 32/LPR rows.  E = 1024 → LPR 8, VEC 4: a 128-byte
 // row is 8 × 16-byte loads and one instruction brings in 4 rows; 32 rows in flight.
 template <int LPR, int VEC, bool LPM, bool GMASK, bool LORA>
-__global__ void __launch_bounds__(kWarps * 32, FI_MATCH_MIN_BLOCKS) match_pick_kernel(const MatchParams p) {
+__global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS : FI_MATCH_MIN_BLOCKS + 1))
+    match_pick_kernel(const MatchParams p) {
   constexpr int G = 32 / LPR;                 // rows per load instruction
   constexpr int BATCH = LPR < 8 ? LPR : 8;    // load instructions in flight
   extern __shared__ __align__(16) uint64_t s_mem[];
@@ -781,19 +782,21 @@ cudaError_t launch_match_t(const MatchParams& p, int sm_count, cudaStream_t s) {
 
 cudaError_t launch_match_pick(const MatchParams& p, int sm_count, cudaStream_t s) {
   if (p.R == 0) return cudaSuccess;
-  switch (p.ix.W) {  // words per row = LPR * VEC
+  // Words per row = LPR * VEC.  Two words per lane (half the counter registers of VEC = 4 -> three CTAs
+  // = 24 warps per SM instead of 16) is the measured optimum since lookups stopped saturating the memory
+  // system: the kernel is bound by per-warp instruction latency and wants warps, not wide loads
+  // (E = 1024: 76 us vs 88 us).  FI_EPP_MATCH_VEC=4 / 1 select the other shapes where they exist.
+  static const int vec = [] { const char* e = std::getenv("FI_EPP_MATCH_VEC"); return e ? std::atoi(e) : 2; }();
+  switch (p.ix.W) {
     case 1: return launch_match_t<1, 1>(p, sm_count, s);
     case 2: return launch_match_t<1, 2>(p, sm_count, s);
-    case 4: return launch_match_t<1, 4>(p, sm_count, s);
-    case 8: return launch_match_t<2, 4>(p, sm_count, s);
-    case 16: return launch_match_t<4, 4>(p, sm_count, s);
-    case 32: {  // E = 1024: lanes-per-row x words-per-lane is a tuning choice (FI_EPP_MATCH_VEC)
-      static const int vec = [] { const char* e = std::getenv("FI_EPP_MATCH_VEC"); return e ? std::atoi(e) : 4; }();
+    case 4: return vec == 4 ? launch_match_t<1, 4>(p, sm_count, s) : launch_match_t<2, 2>(p, sm_count, s);
+    case 8: return vec == 4 ? launch_match_t<2, 4>(p, sm_count, s) : launch_match_t<4, 2>(p, sm_count, s);
+    case 16: return vec == 4 ? launch_match_t<4, 4>(p, sm_count, s) : launch_match_t<8, 2>(p, sm_count, s);
+    case 32:
       if (vec == 1) return launch_match_t<32, 1>(p, sm_count, s);
-      if (vec == 2) return launch_match_t<16, 2>(p, sm_count, s);
-      return launch_match_t<8, 4>(p, sm_count, s);
-    }
-    case 64: return launch_match_t<16, 4>(p, sm_count, s);
+      return vec == 4 ? launch_match_t<8, 4>(p, sm_count, s) : launch_match_t<16, 2>(p, sm_count, s);
+    case 64: return vec == 4 ? launch_match_t<16, 4>(p, sm_count, s) : launch_match_t<32, 2>(p, sm_count, s);
     case 128: return launch_match_t<32, 4>(p, sm_count, s);
     default: return cudaErrorInvalidValue;
   }
