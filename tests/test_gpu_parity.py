@@ -411,3 +411,36 @@ def test_host_path_sliced_feed_is_exact(slices, monkeypatch):
     assert H.picks_equal(got, want), H.describe_diff(got, want)
     assert np.array_equal(gch, wch)
     gpu.close()
+
+
+@pytest.mark.parametrize("order", ["shuffled", "reversed", "interleaved"])
+@pytest.mark.parametrize("mode", [abi.FI_MATCH_UPSTREAM, abi.FI_MATCH_LPM])
+def test_pick_parity_whatever_the_insertion_order(order, mode):
+    """The index numbers its nodes in insertion order and the match kernel first tries "next block = next
+    node"; a prefix whose keys arrived out of chain order (shuffled op stream, reversed chains, two
+    endpoints' ops interleaved) must fall back to table lookups and still give the oracle's answer."""
+    wl = H.small_workload(E=96, R=256, holes=True, lru_capacity=600)
+    cfg = H.config_for(wl, profiles=[{"name": "default", "scorers": [(P, 100), (K, 9), (Q, 5)]}], match_mode=mode)
+    gpu, cpu = _pair(cfg)
+    st = wl.endpoint_states()
+    gpu.update_endpoints(st)
+    cpu.update_endpoints(st)
+    ops = np.concatenate(list(wl.index_ops()))
+    rng = np.random.default_rng(11)
+    if order == "shuffled":
+        ops = ops[rng.permutation(len(ops))]
+    elif order == "reversed":
+        ops = ops[::-1].copy()
+    else:  # odd and even positions of the stream swapped pairwise: runs of length one
+        idx = np.arange(len(ops))
+        idx[: len(ops) // 2 * 2] = idx[: len(ops) // 2 * 2].reshape(-1, 2)[:, ::-1].reshape(-1)
+        ops = ops[idx]
+    for lo in range(0, len(ops), 5000):  # several launches: node ranges of different launches interleave
+        gpu.index_apply(ops[lo:lo + 5000])
+    cpu.index_apply(ops)
+    tok, offs = wl.prompts()
+    got = gpu.pick_batch(tok, offs, wl.h0)
+    want = cpu.pick_batch(tok, offs, wl.h0)
+    assert H.picks_equal(got, want), H.describe_diff(got, want)
+    assert int((got["match_blocks"] > 0).sum()) > 50
+    gpu.close()
