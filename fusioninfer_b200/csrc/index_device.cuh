@@ -91,8 +91,35 @@ __device__ __forceinline__ uint32_t index_find(const IndexView& ix, uint64_t h) 
   return index_resolve(ix, h, bucket_load(ix, h & ix.bmask));
 }
 
+// Bulk variant for passes that probe many blocks most of which are absent (the sharded mode looks every
+// block up on every rank): keys only, the node is fetched with a second, dependent read on a hit — a miss
+// costs one DRAM transaction instead of two.
+__device__ __forceinline__ BucketRegs bucket_load_keys(const IndexView& ix, uint64_t b) {
+  const uint4* p = reinterpret_cast<const uint4*>(ix.keys + b * BUCKET_KEYS);
+  BucketRegs r;
+#pragma unroll
+  for (int i = 0; i < BUCKET_KEYS / 2; ++i) r.q[i] = __ldg(p + i);
+  r.nodes = make_uint4(0, 0, 0, 0);
+  return r;
+}
+__device__ __forceinline__ uint32_t index_find_lazy(const IndexView& ix, uint64_t h) {
+  if (key_is_special(h)) {
+    const uint64_t s = ix.C + (h == KEY_TOMB ? 1 : 0);
+    return ix.cnt[s] ? (uint32_t)s : SLOT_MISS;
+  }
+  uint64_t b = h & ix.bmask;
+  for (uint64_t it = 0; it <= ix.bmask; ++it) {
+    const BucketRegs r = bucket_load_keys(ix, b);
+    const int j = bucket_scan(r, h);
+    if (j < BUCKET_KEYS) return __ldg(ix.node_of + b * BUCKET_KEYS + j);
+    if (j == BUCKET_KEYS) return SLOT_MISS;
+    b = (b + 1) & ix.bmask;
+  }
+  return SLOT_MISS;
+}
+
 // out-of-line index_find for the rare paths of callers that keep several lookups in flight
-static __device__ __noinline__ uint32_t index_find_slow(const IndexView ix, uint64_t h) { return index_find(ix, h); }
+static __device__ __noinline__ uint32_t index_find_slow(const IndexView ix, uint64_t h) { return index_find_lazy(ix, h); }
 
 // Speculation: is `cand` the node of the regular key h?  (klog of a free or retired node is 0, and a
 // regular key is never 0.)

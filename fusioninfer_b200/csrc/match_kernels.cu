@@ -180,7 +180,7 @@ __device__ __forceinline__ uint32_t resolve_chunk_nodes(const IndexView& ix, uin
         }
       }
     } else if (!done) {
-      node = index_find(ix, h);
+      node = index_find_lazy(ix, h);
       done = true;
     }
   }
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) probe_slots_kernel(const Match
 #pragma unroll
         for (int qq = 0; qq < BUCKET_KEYS / 2; ++qq) br[d].q[qq] = make_uint4(0, 0, 0, 0);
         br[d].nodes = make_uint4(0, 0, 0, 0);
-        if (plain[d]) br[d] = bucket_load(p.ix, hk[d] & p.ix.bmask);
+        if (plain[d]) br[d] = bucket_load_keys(p.ix, hk[d] & p.ix.bmask);
       }
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -540,8 +540,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) probe_slots_kernel(const Match
         uint32_t slot = SLOT_MISS;
         if (plain[d]) {
           const int j = bucket_scan(br[d], hk[d]);
-          if (j < BUCKET_KEYS) slot = bucket_node(br[d], j);
-          else if (j > BUCKET_KEYS) slot = index_resolve_overflow(p.ix, hk[d]);
+          if (j < BUCKET_KEYS) slot = __ldg(p.ix.node_of + (hk[d] & p.ix.bmask) * BUCKET_KEYS + j);
+          else if (j > BUCKET_KEYS) slot = index_find_slow(p.ix, hk[d]);
         } else if (valid[d]) {
           slot = index_find_slow(p.ix, hk[d]);
         }
