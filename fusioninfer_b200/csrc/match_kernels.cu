@@ -537,13 +537,28 @@ __global__ void __launch_bounds__(kWarps * 32, 4) probe_slots_kernel(const Match
         const uint32_t c = c0 + d;
         if (c >= p.mask_words) break;  // warp-uniform
         const uint32_t idx = c * 32 + lane;
+        // `slot` ends up as the block's NODE.  A table hit in the home bucket only yields the table slot; the
+        // hits of a chunk are mostly one run of consecutive nodes, so the first of them reads node_of[] and
+        // the others confirm "that node + my distance" against klog (coalesced) before falling back to it.
         uint32_t slot = SLOT_MISS;
+        uint64_t tslot = ~0ull;  // table slot of a home-bucket hit whose node is not known yet
         if (plain[d]) {
           const int j = bucket_scan(br[d], hk[d]);
-          if (j < BUCKET_KEYS) slot = __ldg(p.ix.node_of + (hk[d] & p.ix.bmask) * BUCKET_KEYS + j);
+          if (j < BUCKET_KEYS) tslot = (hk[d] & p.ix.bmask) * BUCKET_KEYS + j;
           else if (j > BUCKET_KEYS) slot = index_find_slow(p.ix, hk[d]);
         } else if (valid[d]) {
           slot = index_find_slow(p.ix, hk[d]);
+        }
+        const unsigned hm = __ballot_sync(FULL, tslot != ~0ull);
+        if (hm) {
+          const int f = __ffs(hm) - 1;
+          uint32_t nf = 0;
+          if (lane == f) nf = __ldg(p.ix.node_of + tslot);
+          nf = __shfl_sync(FULL, nf, f);
+          if (tslot != ~0ull) {
+            const uint32_t cand = nf + (uint32_t)(lane - f);
+            slot = (lane == f || node_holds(p.ix, cand, hk[d])) ? cand : __ldg(p.ix.node_of + tslot);
+          }
         }
         if (idx < p.MP) p.slots[(uint64_t)r * p.MP + idx] = slot;
         const unsigned m = __ballot_sync(FULL, slot != SLOT_MISS);
