@@ -800,18 +800,16 @@ cudaError_t launch_match_pick(const MatchParams& p, int sm_count, cudaStream_t s
   // Words per row = LPR * VEC.  Two words per lane (half the counter registers of VEC = 4 -> three CTAs
   // = 24 warps per SM instead of 16) is the measured optimum since lookups stopped saturating the memory
   // system: the kernel is bound by per-warp instruction latency and wants warps, not wide loads
-  // (E = 1024: 76 us vs 88 us).  FI_EPP_MATCH_VEC=4 / 1 select the other shapes where they exist.
+  // (E = 1024: 76 us vs 88 us; FI_EPP_MATCH_VEC=4 selects the four-word shape there for comparison).
   static const int vec = [] { const char* e = std::getenv("FI_EPP_MATCH_VEC"); return e ? std::atoi(e) : 2; }();
   switch (p.ix.W) {
     case 1: return launch_match_t<1, 1>(p, sm_count, s);
     case 2: return launch_match_t<1, 2>(p, sm_count, s);
-    case 4: return vec == 4 ? launch_match_t<1, 4>(p, sm_count, s) : launch_match_t<2, 2>(p, sm_count, s);
-    case 8: return vec == 4 ? launch_match_t<2, 4>(p, sm_count, s) : launch_match_t<4, 2>(p, sm_count, s);
-    case 16: return vec == 4 ? launch_match_t<4, 4>(p, sm_count, s) : launch_match_t<8, 2>(p, sm_count, s);
-    case 32:
-      if (vec == 1) return launch_match_t<32, 1>(p, sm_count, s);
-      return vec == 4 ? launch_match_t<8, 4>(p, sm_count, s) : launch_match_t<16, 2>(p, sm_count, s);
-    case 64: return vec == 4 ? launch_match_t<16, 4>(p, sm_count, s) : launch_match_t<32, 2>(p, sm_count, s);
+    case 4: return launch_match_t<2, 2>(p, sm_count, s);
+    case 8: return launch_match_t<4, 2>(p, sm_count, s);
+    case 16: return launch_match_t<8, 2>(p, sm_count, s);
+    case 32: return vec == 4 ? launch_match_t<8, 4>(p, sm_count, s) : launch_match_t<16, 2>(p, sm_count, s);
+    case 64: return launch_match_t<32, 2>(p, sm_count, s);
     case 128: return launch_match_t<32, 4>(p, sm_count, s);
     default: return cudaErrorInvalidValue;
   }
