@@ -444,3 +444,55 @@ def test_pick_parity_whatever_the_insertion_order(order, mode):
     assert H.picks_equal(got, want), H.describe_diff(got, want)
     assert int((got["match_blocks"] > 0).sum()) > 50
     gpu.close()
+
+
+def test_pick_parity_after_churn_and_rebuild():
+    """Chains are retired (every endpoint drops them: their nodes die), re-added for other endpoints in a
+    different order, and the small table is forced through rebuilds (which compact the live nodes in node
+    order); picks must follow the oracle through every phase."""
+    wl = H.small_workload(E=48, R=192, lru_capacity=400)
+    profiles = [{"name": "default", "scorers": [(P, 100), (K, 7), (Q, 3)]}]
+    ops0 = np.concatenate(list(wl.index_ops()))
+    uniq = len(np.unique(ops0["hash"]))
+    slots = 256
+    while slots * 0.55 < uniq:  # live keys stay under 60 % but tombstones push `used` over 70 %
+        slots *= 2
+    cfg = H.config_for(wl, profiles=profiles, index_slots=slots)
+    gpu, cpu = _pair(cfg)
+    st = wl.endpoint_states()
+    gpu.update_endpoints(st)
+    cpu.update_endpoints(st)
+    tok, offs = wl.prompts()
+
+    def check(tag):
+        got = gpu.pick_batch(tok, offs, wl.h0)
+        want = cpu.pick_batch(tok, offs, wl.h0)
+        assert H.picks_equal(got, want), tag + "\n" + H.describe_diff(got, want)
+        return got
+
+    for arr in np.array_split(ops0, 7):
+        gpu.index_apply(arr)
+        cpu.index_apply(arr)
+    first = check("initial")
+    assert int((first["match_blocks"] > 0).sum()) > 40
+    rng = np.random.default_rng(5)
+    for phase in range(6):
+        # drop everything a random third of the endpoints hold, then give the same hashes to other endpoints
+        victims = rng.choice(wl.E, size=wl.E // 3, replace=False)
+        sel = ops0[np.isin(ops0["endpoint"], victims)]
+        clr = sel.copy()
+        clr["op"] = abi.FI_OP_CLEAR
+        gpu.index_apply(clr)
+        cpu.index_apply(clr)
+        check(f"phase {phase} after clears")
+        re = sel[rng.permutation(len(sel))[: len(sel) // 2]].copy()
+        re["endpoint"] = (re["endpoint"] + 1 + phase) % wl.E
+        gpu.index_apply(re)
+        cpu.index_apply(re)
+        check(f"phase {phase} after re-adds")
+        back = sel.copy()  # the victims get their chains back, in chain order
+        gpu.index_apply(back)
+        cpu.index_apply(back)
+    check("final")
+    assert gpu.index_stats().rebuilds >= 1
+    gpu.close()
