@@ -116,6 +116,16 @@ struct fi_epp {
   static constexpr int kMaxFeedSlices = 16;
   cudaEvent_t ev_copy[kMaxFeedSlices] = {};
   uint32_t feed_slices = 8;  // FI_EPP_FEED_SLICES (1: one copy, then the whole batch)
+  // Pipelined device path (fi_epp_pick_submit / fi_epp_pick_wait): stage A (block hashing + chain walk) of
+  // batch k+1 runs on s_a while stage B (match + pick) of batch k runs on s_main; the chain / block-count
+  // buffers are double-buffered (slot = batch parity), the pre-states are not (stage A is serial on s_a).
+  cudaStream_t s_a = nullptr;
+  uint64_t* d_chain2 = nullptr;
+  uint32_t* d_nblocks2 = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_a[2] = {}, ev_b[2] = {};
+  cudaEvent_t ev_pick = nullptr;   // completion of the most recent pick of any kind on s_main
+  cudaEvent_t ev_plain = nullptr;  // completion of the most recent stream-ordered (not pipelined) pick
+  uint64_t pipe_seq = 0;          // batches submitted
   cudaEvent_t ev_index = nullptr, ev_user = nullptr, ev_done = nullptr, ev_ctr = nullptr;
 
   // request buffers (device)
@@ -339,6 +349,8 @@ int flush_ops(fi_epp* h) {
   int rc = check_counters(h);  // may rebuild (swaps tables) — only ever between groups
   if (rc != FI_OK) return rc;
   const int b = h->cur_buf;
+  // ops submitted after a pick returned must not overtake it on the GPU: the pick sees the index as of its call
+  FI_CUDA(cudaStreamWaitEvent(h->s_index, h->ev_pick, 0));
   if (h->n_sets) {
     FI_CUDA(cudaMemcpyAsync(h->d_sets[b], h->h_sets[b], h->n_sets * sizeof(fi_index_op), cudaMemcpyHostToDevice, h->s_index));
     h->stats.h2d_bytes += h->n_sets * sizeof(fi_index_op);
@@ -568,8 +580,8 @@ struct HostFeed {
 };
 
 // the whole pick on device buffers; result in d_out ([R][P])
-int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0,
-             const uint64_t* d_adapters, uint32_t R, fi_pick* d_out, const HostFeed* feed = nullptr) {
+int run_pick_impl(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0,
+                  const uint64_t* d_adapters, uint32_t R, fi_pick* d_out, const HostFeed* feed) {
   int rc = flush_ops(h);
   if (rc != FI_OK) return rc;
   rc = check_counters(h);
@@ -585,6 +597,9 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
   if (rc != FI_OK) return rc;
   rc = upload_lora(h);
   if (rc != FI_OK) return rc;
+  if (h->pipe_seq) {  // a plain pick after pipelined submits: their stage A shares d_pre with ours
+    FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_a[(h->pipe_seq - 1) & 1], 0));
+  }
   const bool sharded = h->world > 1;
   MatchParams mp{};
   mp.chain = h->d_chain;
@@ -725,6 +740,101 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
     }
     dump_trace(h, R);
   }
+  h->stats.pick_calls++;
+  h->stats.requests += R;
+  return FI_OK;
+}
+
+int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0,
+             const uint64_t* d_adapters, uint32_t R, fi_pick* d_out, const HostFeed* feed = nullptr) {
+  int rc = run_pick_impl(h, d_prompts, d_offsets, d_h0, d_adapters, R, d_out, feed);
+  if (rc != FI_OK) return rc;
+  FI_CUDA(cudaEventRecord(h->ev_pick, h->s_main));  // index updates submitted later wait for this pick
+  FI_CUDA(cudaEventRecord(h->ev_plain, h->s_main));
+  return FI_OK;
+}
+
+// Pipelined device path: enqueue one batch.  Stage A on s_a, stage B on s_main (see fi_epp::s_a).
+int submit_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0, uint32_t R,
+                fi_pick* d_out, cudaStream_t us) {
+  int rc = flush_ops(h);
+  if (rc != FI_OK) return rc;
+  rc = check_counters(h);
+  if (rc != FI_OK) return rc;
+  if (!h->d_chain2) {
+    FI_CUDA(cudaMalloc(&h->d_chain2, (size_t)h->cfg.max_batch * h->MP * sizeof(uint64_t)));
+    FI_CUDA(cudaMalloc(&h->d_nblocks2, (size_t)h->cfg.max_batch * sizeof(uint32_t)));
+  }
+  // FI_EPP_TRACE=<call>: timeline of three consecutive pipelined batches (printed by fi_epp_pick_wait)
+  if (!h->profiling && h->trace_call >= 0 && (long)h->stats.pick_calls >= h->trace_call &&
+      (long)h->stats.pick_calls < h->trace_call + 3) {
+    if ((long)h->stats.pick_calls == h->trace_call) {
+      if (!h->ev_trace0) cudaEventCreate(&h->ev_trace0);
+      FI_CUDA(cudaStreamSynchronize(h->s_main));
+      FI_CUDA(cudaStreamSynchronize(h->s_a));
+      FI_CUDA(cudaEventRecord(h->ev_trace0, h->s_main));
+      FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_trace0, 0));
+    }
+    h->tracing = true;
+  } else if (h->tracing && (long)h->stats.pick_calls >= h->trace_call + 3) {
+    h->tracing = false;  // events stay queued until the dump
+  }
+  const uint32_t slot = (uint32_t)(h->pipe_seq & 1);
+  uint64_t* chain = slot ? h->d_chain2 : h->d_chain;
+  uint32_t* nb = slot ? h->d_nblocks2 : h->d_nblocks;
+  // ---- stage A: inputs are ready in the caller's stream order; the slot's buffers are free once the
+  // match of two batches ago is done; d_pre is free once the previous plain pick (if any) is done
+  FI_CUDA(cudaEventRecord(h->ev_in, us));
+  FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_in, 0));
+  if (h->pipe_seq >= 2) FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_b[slot], 0));
+  FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_plain, 0));
+  {
+    LaunchScope ls(h, h->s_a, K_HASH);
+    FI_CUDA(launch_hash_blocks(d_prompts, d_offsets, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, h->d_pre, nb, h->s_a));
+  }
+  // The chain walk is serial latency — a warp per scheduler that wants an issue slot every few cycles — and
+  // runs 3x slower next to a busy kernel (measured: 30 -> 100 us under match_pick), so it waits for the
+  // previous batch's match to drain; what overlaps is this batch's block hashing with that match.
+  if (h->pipe_seq >= 1) FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_b[slot ^ 1u], 0));
+  {
+    LaunchScope ls(h, h->s_a, K_CHAIN);
+    FI_CUDA(launch_chain_finalize(h->d_pre, nb, d_h0, R, h->MP, chain, h->s_a));
+  }
+  FI_CUDA(cudaEventRecord(h->ev_a[slot], h->s_a));
+  // ---- stage B
+  FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_index, 0));  // every submitted op is visible
+  rc = upload_endpoints(h);
+  if (rc != FI_OK) return rc;
+  rc = upload_lora(h);
+  if (rc != FI_OK) return rc;
+  FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_a[slot], 0));
+  MatchParams mp{};
+  mp.chain = chain;
+  mp.nblocks = nb;
+  mp.offsets = d_offsets;
+  mp.adapters = nullptr;
+  mp.R = R;
+  mp.MP = h->MP;
+  mp.ix = h->ix;
+  mp.st = h->st;
+  mp.ep_begin = h->cfg.endpoint_begin;
+  mp.lpm = h->cfg.match_mode;
+  mp.apply_pd = h->cfg.pd_enabled ? 1 : 0;
+  mp.pd_decode = h->cfg.pd_decode_profile;
+  mp.pd_prefill = h->cfg.pd_prefill_profile;
+  mp.pd_threshold = h->cfg.pd_threshold;
+  mp.mask_words = (h->MP + 31) / 32;
+  mp.out = d_out;
+  mp.probed_blocks = h->profiling ? h->d_probed : nullptr;
+  mp.work_counter = h->d_work + 8 + slot;
+  mp.zero_work_counter = 1;
+  {
+    LaunchScope ls(h, h->s_main, K_MATCH);
+    FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
+  }
+  FI_CUDA(cudaEventRecord(h->ev_b[slot], h->s_main));
+  FI_CUDA(cudaEventRecord(h->ev_pick, h->s_main));
+  h->pipe_seq++;
   h->stats.pick_calls++;
   h->stats.requests += R;
   return FI_OK;
@@ -885,7 +995,11 @@ void fi_epp_destroy(fi_epp* h) {
     if (e) cudaEventDestroy(e);
   for (int k = 0; k < fi_epp::kMaxFeedSlices; ++k)
     if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);
-  for (cudaStream_t s : {h->s_main, h->s_index, h->s_copy})
+  for (cudaEvent_t e : {h->ev_in, h->ev_a[0], h->ev_a[1], h->ev_b[0], h->ev_b[1], h->ev_pick, h->ev_plain})
+    if (e) cudaEventDestroy(e);
+  cudaFree(h->d_chain2);
+  cudaFree(h->d_nblocks2);
+  for (cudaStream_t s : {h->s_main, h->s_index, h->s_copy, h->s_a})
     if (s) cudaStreamDestroy(s);
   delete h;
 }
@@ -947,6 +1061,9 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
   FI_TRY(cudaStreamCreateWithFlags(&h->s_index, cudaStreamNonBlocking));
   FI_TRY(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+  FI_TRY(cudaStreamCreateWithFlags(&h->s_a, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&h->ev_in, &h->ev_a[0], &h->ev_a[1], &h->ev_b[0], &h->ev_b[1], &h->ev_pick, &h->ev_plain})
+    FI_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (int k = 0; k < fi_epp::kMaxFeedSlices; ++k) FI_TRY(cudaEventCreateWithFlags(&h->ev_copy[k], cudaEventDisableTiming));
   if (const char* e = std::getenv("FI_EPP_FEED_SLICES")) {
     const long v = std::strtol(e, nullptr, 10);
@@ -1300,6 +1417,31 @@ int fi_epp_pick_batch_device_lora(fi_epp* h, const void* d_prompts, const void* 
   }
   FI_CUDA(cudaEventRecord(h->ev_done, h->s_main));
   FI_CUDA(cudaStreamWaitEvent(us, h->ev_done, 0));
+  return FI_OK;
+}
+
+int fi_epp_pick_submit(fi_epp* h, const void* d_prompts, const void* d_offsets, const void* d_h0, uint32_t R,
+                       uint64_t total_prompt_bytes, void* d_out, void* stream) {
+  if (!h || !d_offsets || (!d_h0 && R) || (!d_out && R)) return FI_ERR_INVALID;
+  if (h->world > 1 || !h->fast_hash)  // sharded pools and odd block sizes: the stream-ordered path
+    return fi_epp_pick_batch_device(h, d_prompts, d_offsets, d_h0, R, total_prompt_bytes, d_out, nullptr, stream);
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  if (R == 0) return FI_OK;
+  if (R > h->cfg.max_batch) return fail(h, FI_ERR_CAPACITY, "batch larger than max_batch");
+  return submit_pick(h, (const uint8_t*)d_prompts, (const uint64_t*)d_offsets, (const uint64_t*)d_h0, R, (fi_pick*)d_out,
+                     (cudaStream_t)stream);
+}
+
+int fi_epp_pick_wait(fi_epp* h, void* stream) {
+  if (!h) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  FI_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_pick, 0));  // s_main runs the batches in order
+  if (!h->profiling && !h->pending_ev.empty() && h->ev_trace0) {
+    h->tracing = true;
+    dump_trace(h, 0);
+  }
   return FI_OK;
 }
 

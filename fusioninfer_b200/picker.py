@@ -232,6 +232,17 @@ class EndpointPicker:
             "fi_epp_pick_batch_device",
         )
 
+    def pick_submit(self, d_prompts: int, d_offsets: int, d_h0: int, R: int, total_bytes: int, d_out: int, stream: int = 0):
+        """Pipelined device path: enqueue a batch; its result is valid for `stream` only after pick_wait."""
+        self._check(
+            self._lib.fi_epp_pick_submit(self._h, d_prompts, d_offsets, d_h0, R, total_bytes, d_out, stream or None),
+            "fi_epp_pick_submit",
+        )
+
+    def pick_wait(self, stream: int = 0):
+        """Make `stream` wait (device-side) for every batch submitted so far."""
+        self._check(self._lib.fi_epp_pick_wait(self._h, stream or None), "fi_epp_pick_wait")
+
     # -- multi-GPU -------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

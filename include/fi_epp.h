@@ -259,6 +259,17 @@ int fi_epp_pick_batch_device_lora(fi_epp* h, const void* d_prompts, const void* 
                                   const void* d_adapters, uint32_t R, uint64_t total_prompt_bytes, void* d_out,
                                   void* d_chains_out, void* stream);
 
+/* Pipelined device path.  fi_epp_pick_submit enqueues one batch exactly like fi_epp_pick_batch_device (inputs
+ * ready in `stream` order at the call) but does NOT order `stream` behind the result: batch k+1's block
+ * hashing and chain walk run while batch k is still being matched (two batches in flight, internal
+ * streams).  The inputs and `d_out` of a submitted batch must stay untouched until a fi_epp_pick_wait
+ * issued after it: that call makes `stream` wait (on the device; the host does not block) for every batch
+ * submitted so far.  Batches complete in submission order and see the index as of their submit call.
+ * Sharded handles and block sizes that are not a multiple of 32 take the stream-ordered path inside. */
+int fi_epp_pick_submit(fi_epp* h, const void* d_prompts, const void* d_offsets, const void* d_h0, uint32_t R,
+                       uint64_t total_prompt_bytes, void* d_out, void* stream);
+int fi_epp_pick_wait(fi_epp* h, void* stream);
+
 void* fi_epp_pinned_alloc(size_t bytes);
 void fi_epp_pinned_free(void* p);
 

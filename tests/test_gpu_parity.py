@@ -496,3 +496,63 @@ def test_pick_parity_after_churn_and_rebuild():
     check("final")
     assert gpu.index_stats().rebuilds >= 1
     gpu.close()
+
+
+def test_pipelined_submit_equals_oracle_with_index_updates_in_between():
+    """fi_epp_pick_submit keeps two batches in flight (batch k+1 is hashed while batch k is matched).  Seven
+    different batches of different sizes are submitted back to back, index updates and a pod-state refresh
+    are interleaved (each batch must see the index and the pod states as of ITS submit call), stream-ordered
+    picks are mixed in; after one fi_epp_pick_wait every output equals the oracle's."""
+    import torch
+
+    wl = H.small_workload(E=128, R=384, T=1024, max_blocks=64, lru_capacity=500, pd=True)
+    profiles, pd = synth.baseline_profiles(5)
+    pd = dict(pd, threshold=900.0)
+    cfg = H.config_for(wl, profiles=profiles, pd=pd)
+    gpu, cpu = _pair(cfg)
+    st = wl.endpoint_states()
+    gpu.update_endpoints(st)
+    cpu.update_endpoints(st)
+    all_ops = np.concatenate(list(wl.index_ops()))
+    parts = np.array_split(all_ops, 8)
+    gpu.index_apply(parts[0])
+    cpu.index_apply(parts[0])
+    s = torch.cuda.current_stream().cuda_stream
+    sizes = [384, 100, 1, 383, 64, 384, 200]
+    keep, wants, outs = [], [], []
+    rng = np.random.default_rng(3)
+    for k, R in enumerate(sizes):
+        tok, offs = wl.prompts(batch=k)
+        tok = np.ascontiguousarray(tok[:R])
+        offs = offs[: R + 1].copy()
+        d_tok = torch.from_numpy(tok.view(np.int32)).cuda()
+        d_off = torch.from_numpy(offs.view(np.int64)).cuda()
+        d_h0 = torch.full((R,), np.uint64(wl.h0).astype(np.int64), dtype=torch.int64, device="cuda")
+        d_out = torch.zeros(R * 2 * 16, dtype=torch.uint8, device="cuda")
+        keep.append((d_tok, d_off, d_h0))
+        wants.append(cpu.pick_batch(tok, offs, wl.h0))
+        if k == 4:  # a stream-ordered pick in the middle of the pipeline
+            gpu.pick_batch_device(d_tok.data_ptr(), d_off.data_ptr(), d_h0.data_ptr(), R, tok.nbytes, d_out.data_ptr(), 0, s)
+        else:
+            gpu.pick_submit(d_tok.data_ptr(), d_off.data_ptr(), d_h0.data_ptr(), R, tok.nbytes, d_out.data_ptr(), s)
+        outs.append(d_out)
+        # the NEXT batch sees more of the index, some clears, and (once) refreshed pod states
+        nxt = parts[k + 1]
+        gpu.index_apply(nxt)
+        cpu.index_apply(nxt)
+        clr = parts[k][rng.permutation(len(parts[k]))[:200]].copy()
+        clr["op"] = abi.FI_OP_CLEAR
+        gpu.index_apply(clr)
+        cpu.index_apply(clr)
+        if k == 2:
+            st2 = st.copy()
+            st2["queue_depth"] = st2["queue_depth"][::-1].copy()
+            st2["kv_util"] = 1.0 - st2["kv_util"]
+            gpu.update_endpoints(st2)
+            cpu.update_endpoints(st2)
+    gpu.pick_wait(s)
+    torch.cuda.synchronize()
+    for k, R in enumerate(sizes):
+        got = outs[k].cpu().numpy().view(H.PICK_DTYPE).reshape(R, 2)
+        assert H.picks_equal(got, wants[k]), f"batch {k}\n" + H.describe_diff(got, wants[k])
+    gpu.close()
