@@ -124,7 +124,7 @@ struct MatchParams {
   const uint32_t* gmask;
   uint32_t gmask_ranks;
   uint32_t mask_words;
-  uint32_t* slots;                    // [R][MP] key slot of every block (probe_slots_kernel -> match GMASK)
+  uint32_t* slots;                    // [R][MP] index node of every block (probe_slots_kernel -> match GMASK)
   fi_pick* out;                       // [R][P]
   unsigned long long* probed_blocks;  // optional Σ N_probe
   uint32_t* work_counter;             // dynamic request queue of the launch

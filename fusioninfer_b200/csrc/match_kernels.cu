@@ -1,15 +1,17 @@
 // match_kernels.cu — batched longest-prefix-match + weighted score + warp-shuffle
-// argmax over all endpoints, sm_100a.  HBM/L2-latency bound random row reads; no
-// tensor cores (there is no dense contraction on this path).
+// argmax over all endpoints, sm_100a.  Bound by per-warp latency (dependent index / row reads and the
+// counting arithmetic); no tensor cores (there is no dense contraction on this path).
 //
-// One warp per request (persistent, strided over requests):
+// One warp per request (persistent grid, dynamic queue):
 //   1. stage the request's block-hash chain in shared memory (cp.async);
-//   2. 32 blocks at a time: every lane probes one block hash in the key table
-//      (one 32 B sector), the warp finds the first miss with a ballot
-//      (upstream Plugin.matchLongestPrefix stops at the first block no pod holds —
-//      SURVEY.md Appendix A.3), the next 32 probes are issued, then the rows of
-//      the present blocks are read 16 at a time, fully coalesced (a row is the
-//      bitset over the local endpoints; a lane owns one 32-endpoint word);
+//   2. 32 blocks at a time, one block per lane: find the block's index NODE.  The index numbers its
+//      nodes in insertion order (index_device.cuh), so after one table lookup for the first block the
+//      lanes check "my node = the previous block's node + 1" with a coalesced read of klog; the table is
+//      probed again only where that fails — normally at the first block the index does not hold, which
+//      ends the walk (upstream Plugin.matchLongestPrefix stops at the first block no pod holds —
+//      SURVEY.md Appendix A.3).  The next chunk's check is issued before this chunk's rows are read;
+//      the rows (consecutive 128-byte bitsets over the local endpoints) are read 2 per load instruction,
+//      16 in flight per lane group;
 //   3. per-endpoint match counts accumulate in bit-planes (bitslice.cuh);
 //   4. only endpoints with a non-zero count are scored individually, in fp64 with
 //      explicit round-to-nearest mul/add in profile order (SURVEY.md Appendix A.4,
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
     if (r >= p.R) break;
     if (lane == 0) r_next = atomicAdd(p.work_counter, 1u);
     const uint32_t n = p.nblocks[r];
-    // ---- 1. stage the chain (sharded upstream mode reads the slots probe_slots_kernel found instead)
+    // ---- 1. stage the chain (sharded upstream mode reads the nodes probe_slots_kernel found instead)
     if (!GMASK) {
       const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
       for (uint32_t u = lane; 2 * u < n; u += 32) cp_async16(s_chain + 2 * u, crow + 2 * u);
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
 
 
 // Sharded upstream mode, first pass: probe every block of every request once.  The slot of each block is
-// kept for the match pass (which then never touches the key array), and the presence mask of the request
+// kept for the match pass (which then never touches the table), and the presence mask of the request
 // goes out to every rank — tagged words into peer memory, or a plain array for the NCCL all-gather.
 __global__ void __launch_bounds__(kWarps * 32, 4) probe_slots_kernel(const MatchParams p, uint32_t* __restrict__ mask_out) {
   constexpr int D = 4;  // chunks of 32 blocks whose home-bucket loads are in flight together (per lane)
