@@ -208,12 +208,14 @@ def run_reference(args, wl, cfg_id):
     sub = synth.Workload(**{**wl.__dict__, "R": S})
     tok, offs = sub.prompts(batch=100)
     # Every thread walks its shard `rep` times per step so that thread start-up (~50 us x cores)
-    # does not dominate a bounded sample: calibrate rep for ~1 s of wall time per step.
+    # does not dominate a bounded sample: calibrate rep for up to ~1 s of wall time per step.
     S_eff = S
     t0 = time.perf_counter()
     o.pick_batch_repeat(tok, offs, wl.h0, nthreads=ncores, repeat=2)
     per_pass = (time.perf_counter() - t0) / 2
-    rep = int(max(1, min(64, 1.0 / max(per_pass, 1e-6))))
+    # per-step wall time: ~1 s, less when many steps are asked for (the whole run stays around a minute)
+    target = min(1.0, 60.0 / max(args.steps + args.warmup, 1))
+    rep = int(max(1, min(64, target / max(per_pass, 1e-6))))
     for _ in range(args.warmup):
         o.pick_batch_repeat(tok, offs, wl.h0, nthreads=ncores, repeat=rep)
     t0 = time.perf_counter()
