@@ -282,6 +282,11 @@ int alloc_index(fi_epp* h, uint64_t slots, IndexView* out) {
   FI_CUDA(cudaMalloc(&v.klog, total * sizeof(uint64_t)));
   FI_CUDA(cudaMalloc(&v.rows, total * v.W * sizeof(uint32_t)));
   FI_CUDA(cudaMalloc(&v.cnt, total * sizeof(uint32_t)));
+  v.log2F = 3;  // 8 filter bits per slot
+  while ((1ull << v.log2F) < 8 * slots) ++v.log2F;
+  const size_t filt_bytes = ((size_t)1 << v.log2F) / 8;
+  FI_CUDA(cudaMalloc(&v.filt, filt_bytes < 4 ? 4 : filt_bytes));
+  FI_CUDA(cudaMemsetAsync(v.filt, 0, filt_bytes < 4 ? 4 : filt_bytes, h->s_index));
   FI_CUDA(cudaMemsetAsync(v.keys, 0, total * sizeof(uint64_t), h->s_index));
   FI_CUDA(cudaMemsetAsync(v.node_of, 0xFF, total * sizeof(uint32_t), h->s_index));  // NODE_INVALID
   FI_CUDA(cudaMemsetAsync(v.klog, 0, total * sizeof(uint64_t), h->s_index));
@@ -297,6 +302,8 @@ void free_index(IndexView& v) {
   cudaFree(v.klog);
   cudaFree(v.rows);
   cudaFree(v.cnt);
+  cudaFree(v.filt);
+  v.filt = nullptr;
   v.keys = nullptr;
   v.node_of = nullptr;
   v.klog = nullptr;

@@ -91,6 +91,19 @@ __device__ __forceinline__ uint32_t index_find(const IndexView& ix, uint64_t h) 
   return index_resolve(ix, h, bucket_load(ix, h & ix.bmask));
 }
 
+// Presence filter (kernels.cuh IndexView::filt): a clear bit proves that the regular key h was never
+// claimed since the last rebuild.  The filter is small enough to stay L2-resident (C bytes), so a pass that
+// mostly probes absent blocks pays an L2 hit instead of a DRAM transaction for them.
+__device__ __forceinline__ uint64_t filter_bit(const IndexView& ix, uint64_t h) { return h >> (64 - ix.log2F); }
+__device__ __forceinline__ void filter_set(const IndexView& ix, uint64_t h) {
+  const uint64_t b = filter_bit(ix, h);
+  atomicOr(ix.filt + (b >> 5), 1u << (b & 31));
+}
+__device__ __forceinline__ const uint32_t* filter_word(const IndexView& ix, uint64_t h) { return ix.filt + (filter_bit(ix, h) >> 5); }
+__device__ __forceinline__ bool filter_test(const IndexView& ix, uint64_t h, uint32_t word) {
+  return (word >> (filter_bit(ix, h) & 31)) & 1u;
+}
+
 // Bulk variant for passes that probe many blocks most of which are absent (the sharded mode looks every
 // block up on every rank): keys only, the node is fetched with a second, dependent read on a hit — a miss
 // costs one DRAM transaction instead of two.

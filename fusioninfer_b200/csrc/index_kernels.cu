@@ -34,6 +34,7 @@ __device__ uint32_t table_find_or_claim(const IndexView& ix, IndexCounters* ctr,
         unsigned long long old = atomicCAS(kb + j, (unsigned long long)KEY_EMPTY, (unsigned long long)h);
         if (old == KEY_EMPTY) {
           *claimed = true;
+          filter_set(ix, h);
           return (uint32_t)(b * BUCKET_KEYS + j);
         }
         if (old == h) return (uint32_t)(b * BUCKET_KEYS + j);

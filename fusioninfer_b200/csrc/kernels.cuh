@@ -12,6 +12,8 @@
 //             rows    [C+3][W] u32, row n = membership bitset of node n over the local endpoints
 //                             (bit e%32 of word e/32)
 //             cnt     [C+3]   u32 popcount of the row (key present ⇔ cnt > 0)
+//             filt    [C/4]   u32 presence filter, 8 bits per slot: bit (hash >> (64 - log2F)) is set when a key
+//                             is claimed; a clear bit proves absence (bulk probing of mostly-absent blocks)
 //   picks     [R][P]        fi_pick
 #pragma once
 #include <cuda_runtime.h>
@@ -32,6 +34,8 @@ struct IndexView {
   uint64_t* klog;
   uint32_t* rows;
   uint32_t* cnt;
+  uint32_t* filt;  // presence filter: one bit per 1/8 slot, set when a key is claimed (never cleared until a rebuild)
+  uint32_t log2F;  // filter bits = 1 << log2F = 8 * C
   uint64_t bmask;  // buckets - 1
   uint64_t C;      // regular slots = buckets * BUCKET_KEYS
   uint32_t W;      // words per row (power of two)
