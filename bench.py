@@ -62,8 +62,10 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region: an in-process NVML poll every ~0.5 ms (the timed
-    region of the default run is a few milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as fallback."""
+    """SM clock + throttle reasons DURING the timed region: an in-process NVML poll every 2 ms (the timed
+    region of the default run is ~30 ms, too short for `nvidia-smi -lms`), nvidia-smi as fallback.  Only the
+    rank that prints the line samples (its own GPU): several processes polling NVML at a high rate contend
+    on the driver and delay each other's kernel launches (seen at 4 ranks: 0.3 -> 0.8 ms per sharded step)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -114,13 +116,15 @@ class ClockSampler:
                 self.samples.append((mhz, rs))
             except Exception:
                 pass
-            time.sleep(0.0005)
+            time.sleep(0.002)
 
     def _pump(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "not sampled on this rank"}
         if self.nvml is not None:
             self.stop_flag = True
             self.t.join(timeout=2)
@@ -394,7 +398,8 @@ def main():
     torch.cuda.synchronize()
     picker.reset_stats()
     clocks = ClockSampler(local)
-    clocks.start()
+    if rank == 0 and os.environ.get("FI_BENCH_NO_CLOCKS") != "1":
+        clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     run_steps(args.steps)
