@@ -62,10 +62,11 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region: an in-process NVML poll every 2 ms (the timed
-    region of the default run is ~30 ms, too short for `nvidia-smi -lms`), nvidia-smi as fallback.  Only the
-    rank that prints the line samples (its own GPU): several processes polling NVML at a high rate contend
-    on the driver and delay each other's kernel launches (seen at 4 ranks: 0.3 -> 0.8 ms per sharded step)."""
+    """SM clock + throttle reasons around and DURING the timed region: in-process NVML, one sample right
+    before the region, one every 10 ms inside it (the default run's region is ~30 ms — too short for
+    `nvidia-smi -lms`), one right after; nvidia-smi as fallback.  Only the rank that prints the line samples
+    (its own GPU), and sparsely: NVML calls contend with kernel launches on the driver — every rank polling at
+    2 kHz took a 4-rank sharded step from 0.29 to 0.78 ms, rank 0 alone at 500 Hz still to 0.43 ms."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -90,6 +91,7 @@ class ClockSampler:
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
+            self._sample()  # right before the timed region (the warm-up has just run: clocks are at load level)
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
             return
@@ -104,19 +106,24 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def _poll(self):
+    def _sample(self):
         n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append((mhz, rs))
+
+    def _poll(self):
         while not self.stop_flag:
+            time.sleep(0.010)
+            if self.stop_flag:
+                break
             try:
-                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-                try:
-                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                except Exception:
-                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                self.samples.append((mhz, rs))
+                self._sample()
             except Exception:
                 pass
-            time.sleep(0.002)
 
     def _pump(self):
         for ln in self.proc.stdout:
@@ -128,6 +135,10 @@ class ClockSampler:
         if self.nvml is not None:
             self.stop_flag = True
             self.t.join(timeout=2)
+            try:
+                self._sample()  # right after the last timed kernel
+            except Exception:
+                pass
             n = self.nvml
             bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
