@@ -27,7 +27,7 @@ $(LIB): $(CU_OBJS) $(OBJDIR)/epp_config.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -ldl
 
 # host-only build of the shared host/device arithmetic, for CPU unit tests
-$(HOSTCHECK): $(CSRC)/hostcheck.cpp $(CSRC)/xxh64.cuh $(CSRC)/bitslice.cuh $(CSRC)/lru.h
+$(HOSTCHECK): $(CSRC)/hostcheck.cpp $(CSRC)/xxh64.cuh $(CSRC)/bitslice.cuh $(CSRC)/lru.h $(CSRC)/tiebreak.cuh
 	@mkdir -p $(dir $(HOSTCHECK))
 	$(CXX) -O2 -std=c++17 -ffp-contract=off -fPIC -Wall -Wextra -shared -x c++ $(CSRC)/hostcheck.cpp -o $@
 

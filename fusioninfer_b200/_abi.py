@@ -11,7 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-FI_EPP_ABI_VERSION = 1
+FI_EPP_ABI_VERSION = 2
 FI_EPP_MAX_PROFILES = 4
 FI_EPP_MAX_SCORERS = 4
 FI_EPP_MAX_BLOCKS = 1023
@@ -196,6 +196,7 @@ SYMBOLS = [
     ("fi_epp_endpoints_lora_update", C.c_int, [_P, _P, C.c_uint32]),
     ("fi_epp_index_apply", C.c_int, [_P, _P, C.c_uint64]),
     ("fi_epp_index_add_chain", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
+    ("fi_epp_index_add_chains", C.c_int, [_P, _P, _P, C.c_uint32, _P, C.c_uint32]),
     ("fi_epp_index_sync", C.c_int, [_P]),
     ("fi_epp_index_contains", C.c_int, [_P, _P, C.c_uint64, _P]),
     ("fi_epp_index_stats", C.c_int, [_P, C.POINTER(fi_index_stats)]),

@@ -10,15 +10,21 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
+
+#include <sched.h>
 
 #include "../../include/fi_epp.h"
 #include "kernels.cuh"
@@ -97,6 +103,86 @@ uint64_t pow2_ceil64(uint64_t v) {
   return p;
 }
 
+// host cores this process may run on (affinity mask; the cgroup quota is the caller's business)
+unsigned usable_cores() {
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+    const int n = CPU_COUNT(&set);
+    if (n > 0) return (unsigned)n;
+  }
+  const unsigned hc = std::thread::hardware_concurrency();
+  return hc ? hc : 1u;
+}
+
+// Persistent worker threads for the host LRU (fi_epp_index_add_chains): run(n, fn) calls fn(task, worker)
+// for task = 0..n-1, tasks handed out dynamically; the caller is worker 0.
+class WorkerPool {
+ public:
+  explicit WorkerPool(unsigned workers) : n_(workers < 1 ? 1 : workers) {
+    for (unsigned w = 1; w < n_; ++w) th_.emplace_back([this, w] { loop(w); });
+  }
+  ~WorkerPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  unsigned size() const { return n_; }
+  void run(uint32_t ntasks, const std::function<void(uint32_t, unsigned)>& fn) {
+    if (ntasks == 0) return;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      ntasks_ = ntasks;
+      next_.store(0, std::memory_order_relaxed);
+      busy_ = n_ - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    work(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return busy_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work(unsigned w) {
+    for (;;) {
+      const uint32_t t = next_.fetch_add(1, std::memory_order_relaxed);
+      if (t >= ntasks_) break;
+      (*fn_)(t, w);
+    }
+  }
+  void loop(unsigned w) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      work(w);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--busy_ == 0) done_.notify_one();
+    }
+  }
+  unsigned n_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(uint32_t, unsigned)>* fn_ = nullptr;
+  uint32_t ntasks_ = 0;
+  std::atomic<uint32_t> next_{0};
+  unsigned busy_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 }  // namespace
 
 struct fi_epp {
@@ -138,14 +224,23 @@ struct fi_epp {
   fi_pick* d_picks = nullptr;   // [R][P] final
   fi_pick* d_local = nullptr;   // [R][P] this rank's picks (sharded)
   fi_pick* d_gather = nullptr;  // [world][R][P]
-  uint32_t* d_mask = nullptr;   // [R][mask_words]
-  uint32_t* d_gmask = nullptr;  // [world][R][mask_words]
   // peer-memory exchange (sharded mode; kernels.cuh PeerXchg)
   PeerXchg px{};                 // px.enabled == 0: NCCL all-gathers are used
   uint8_t* d_xchg = nullptr;     // this rank's exchange buffer
   volatile uint32_t* h_xerr = nullptr;  // poll-timeout flag of the exchange (mapped pinned host word the kernels set)
-  uint32_t* d_slots = nullptr;   // [R][MP] key slots found by probe_slots_kernel (sharded upstream mode)
   void* peer_ipc[FI_MAX_RANKS] = {};  // mappings opened with cudaIpcOpenMemHandle (closed in destroy)
+  // sharded mode: every rank hashes R/world requests and the chains are all-gathered (FI_EPP_SHARD_HASH=split,
+  // the default) instead of every rank hashing every prompt (=replicated)
+  bool split_hash = true;
+  uint32_t chain_rows = 0;  // rows allocated in d_chain / d_pre / d_nblocks (max_batch padded for the gather)
+  // sharded mode: directory gossip (index_kernels.cu): this rank's transition log of the current round and the
+  // buffers the ranks' logs are gathered into
+  unsigned long long* d_glog_n = nullptr;  // [2] appear / vanish counts
+  uint64_t* d_glog_a = nullptr;            // [kOpChunk]
+  uint64_t* d_glog_v = nullptr;            // [kOpChunk]
+  unsigned long long* d_ghdr = nullptr;    // [world][2] gathered counts
+  unsigned long long* h_ghdr = nullptr;    // pinned copy
+  uint64_t* d_ggather = nullptr;           // [world][kOpChunk]
   unsigned long long* d_probed = nullptr;
   uint32_t* d_work = nullptr;  // [16] dynamic work-queue counters of in-flight match launches
   // pinned host mirrors
@@ -156,6 +251,8 @@ struct fi_epp {
 
   // index
   IndexView ix{};
+  IndexView ix_spare{};  // rebuild target, allocated at the first rebuild and reused alternately
+  bool spare_ready = false;
   IndexCounters* d_ctr = nullptr;
   IndexCounters* h_ctr = nullptr;  // pinned
   bool ctr_pending = false;
@@ -169,6 +266,7 @@ struct fi_epp {
   uint64_t n_sets = 0, n_clears = 0;
   std::unordered_set<PairKey, PairHash> cleared;
   std::vector<LruSet> lrus;
+  std::unique_ptr<WorkerPool> pool;  // host LRU workers (fi_epp_index_add_chains), created on first use
 
   // endpoints / score tables
   std::vector<EndpointDev> eps;  // global pool
@@ -177,6 +275,7 @@ struct fi_epp {
   double* d_sc = nullptr;
   uint32_t* d_elig = nullptr;
   ZeroBest* d_zero = nullptr;
+  uint32_t* d_ztie = nullptr;
   std::vector<LoraDev> lora;   // local endpoints' adapter residency (lora-affinity-scorer)
   bool lora_dirty = false;
   LoraDev* d_lora = nullptr;
@@ -269,6 +368,38 @@ void drain_profile(fi_epp* h) {
   h->pending_ev.clear();
 }
 
+void free_index(IndexView& v) {
+  cudaFree(v.keys);
+  cudaFree(v.node_of);
+  cudaFree(v.klog);
+  cudaFree(v.rows);
+  cudaFree(v.cnt);
+  cudaFree(v.rmask);
+  v.keys = nullptr;
+  v.node_of = nullptr;
+  v.klog = nullptr;
+  v.rows = nullptr;
+  v.cnt = nullptr;
+  v.rmask = nullptr;
+}
+
+size_t index_bytes(uint64_t slots, uint32_t W) {
+  const uint64_t total = slots + 3;
+  return total * (sizeof(uint64_t) * 2 + sizeof(uint32_t) * 3 + (size_t)W * sizeof(uint32_t));
+}
+
+// queue the clears that make `v` an empty index (on the index stream)
+int clear_index(fi_epp* h, IndexView& v) {
+  const uint64_t total = v.C + 3;
+  FI_CUDA(cudaMemsetAsync(v.keys, 0, total * sizeof(uint64_t), h->s_index));
+  FI_CUDA(cudaMemsetAsync(v.node_of, 0xFF, total * sizeof(uint32_t), h->s_index));  // NODE_INVALID
+  FI_CUDA(cudaMemsetAsync(v.klog, 0, total * sizeof(uint64_t), h->s_index));
+  FI_CUDA(cudaMemsetAsync(v.rows, 0, total * v.W * sizeof(uint32_t), h->s_index));
+  FI_CUDA(cudaMemsetAsync(v.cnt, 0, total * sizeof(uint32_t), h->s_index));
+  FI_CUDA(cudaMemsetAsync(v.rmask, 0, total * sizeof(uint32_t), h->s_index));
+  return FI_OK;
+}
+
 int alloc_index(fi_epp* h, uint64_t slots, IndexView* out) {
   IndexView v{};
   v.C = slots;
@@ -277,57 +408,53 @@ int alloc_index(fi_epp* h, uint64_t slots, IndexView* out) {
   v.logW = 0;
   while ((1u << v.logW) < v.W) ++v.logW;
   const uint64_t total = slots + 3;  // + slots for hash 0, hash ~0, and a permanently-zero row
-  FI_CUDA(cudaMalloc(&v.keys, total * sizeof(uint64_t)));
-  FI_CUDA(cudaMalloc(&v.node_of, total * sizeof(uint32_t)));
-  FI_CUDA(cudaMalloc(&v.klog, total * sizeof(uint64_t)));
-  FI_CUDA(cudaMalloc(&v.rows, total * v.W * sizeof(uint32_t)));
-  FI_CUDA(cudaMalloc(&v.cnt, total * sizeof(uint32_t)));
-  v.log2F = 3;  // 8 filter bits per slot
-  while ((1ull << v.log2F) < 8 * slots) ++v.log2F;
-  const size_t filt_bytes = ((size_t)1 << v.log2F) / 8;
-  FI_CUDA(cudaMalloc(&v.filt, filt_bytes < 4 ? 4 : filt_bytes));
-  FI_CUDA(cudaMemsetAsync(v.filt, 0, filt_bytes < 4 ? 4 : filt_bytes, h->s_index));
-  FI_CUDA(cudaMemsetAsync(v.keys, 0, total * sizeof(uint64_t), h->s_index));
-  FI_CUDA(cudaMemsetAsync(v.node_of, 0xFF, total * sizeof(uint32_t), h->s_index));  // NODE_INVALID
-  FI_CUDA(cudaMemsetAsync(v.klog, 0, total * sizeof(uint64_t), h->s_index));
-  FI_CUDA(cudaMemsetAsync(v.rows, 0, total * v.W * sizeof(uint32_t), h->s_index));
-  FI_CUDA(cudaMemsetAsync(v.cnt, 0, total * sizeof(uint32_t), h->s_index));
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && index_bytes(slots, v.W) + (256ull << 20) > free_b) {
+    h->err = "index of " + std::to_string(index_bytes(slots, v.W) >> 20) + " MiB does not fit in the " +
+             std::to_string(free_b >> 20) + " MiB of free device memory";
+    return FI_ERR_NOMEM;
+  }
+  cudaError_t e = cudaMalloc(&v.keys, total * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&v.node_of, total * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&v.klog, total * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&v.rows, total * v.W * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&v.cnt, total * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&v.rmask, total * sizeof(uint32_t));
+  if (e != cudaSuccess) {  // nothing of a partial view survives
+    cudaGetLastError();
+    free_index(v);
+    h->err = std::string("index allocation: ") + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? FI_ERR_NOMEM : FI_ERR_CUDA;
+  }
+  int rc = clear_index(h, v);
+  if (rc != FI_OK) {
+    free_index(v);
+    return rc;
+  }
   *out = v;
   return FI_OK;
 }
 
-void free_index(IndexView& v) {
-  cudaFree(v.keys);
-  cudaFree(v.node_of);
-  cudaFree(v.klog);
-  cudaFree(v.rows);
-  cudaFree(v.cnt);
-  cudaFree(v.filt);
-  v.filt = nullptr;
-  v.keys = nullptr;
-  v.node_of = nullptr;
-  v.klog = nullptr;
-  v.rows = nullptr;
-  v.cnt = nullptr;
-}
-
+// Compact the live nodes into the spare table and swap.  Everything is queued on the index stream — no host
+// synchronisation: picks submitted later wait for ev_index (recorded by the flush that called us) and are
+// launched with the new view; picks already in flight keep reading the old tables, which are not touched again
+// before the NEXT rebuild, and that one is ordered behind them (flush_ops makes s_index wait for ev_pick).
+// The spare is allocated once, at the first rebuild (the only point where memory doubles), and then reused.
 int rebuild_index(fi_epp* h) {
-  IndexView nv{};
-  int rc = alloc_index(h, h->ix.C, &nv);
-  if (rc != FI_OK) {
-    free_index(nv);
-    return rc;
+  if (!h->spare_ready) {
+    int rc = alloc_index(h, h->ix.C, &h->ix_spare);  // clears it too
+    if (rc != FI_OK) return rc;
+    h->spare_ready = true;
+  } else {
+    int rc = clear_index(h, h->ix_spare);
+    if (rc != FI_OK) return rc;
   }
   FI_CUDA(cudaMemsetAsync(h->d_ctr, 0, sizeof(IndexCounters), h->s_index));
   {
     LaunchScope ls(h, h->s_index, K_INDEX);
-    FI_CUDA(launch_index_rebuild(h->ix, nv, h->d_ctr, h->s_index));
+    FI_CUDA(launch_index_rebuild(h->ix, h->ix_spare, h->d_ctr, h->s_index));
   }
-  FI_CUDA(cudaStreamSynchronize(h->s_index));
-  // the compute stream may still be reading the old table
-  FI_CUDA(cudaStreamSynchronize(h->s_main));
-  free_index(h->ix);
-  h->ix = nv;
+  std::swap(h->ix, h->ix_spare);
   h->rebuilds++;
   return FI_OK;
 }
@@ -342,10 +469,26 @@ int check_counters(fi_epp* h) {
   const uint64_t used = h->h_ctr->used, tomb = h->h_ctr->tombstones;
   if (used * 10 > h->ix.C * 7) {
     if ((used - tomb) * 10 > h->ix.C * 6) return fail(h, FI_ERR_CAPACITY, "index above 60% live keys: raise index_slots");
+    // the rebuild reads the old tables on s_index: every pick that still uses them must be ordered before the
+    // NEXT rebuild clears them — flush_ops (our only caller that launches work) waits for ev_pick first
+    FI_CUDA(cudaStreamWaitEvent(h->s_index, h->ev_pick, 0));
     int rc = rebuild_index(h);
     if (rc != FI_OK) return rc;
+    FI_CUDA(cudaEventRecord(h->ev_index, h->s_index));
   }
   return FI_OK;
+}
+
+GossipLog gossip_log(fi_epp* h) {
+  GossipLog g{};
+  if (h->world > 1) {
+    g.n_appear = h->d_glog_n;
+    g.n_vanish = h->d_glog_n + 1;
+    g.appear = h->d_glog_a;
+    g.vanish = h->d_glog_v;
+    g.cap = kOpChunk;
+  }
+  return g;
 }
 
 // launch the staged SET then CLEAR ops of the current group on the index stream.
@@ -358,17 +501,20 @@ int flush_ops(fi_epp* h) {
   const int b = h->cur_buf;
   // ops submitted after a pick returned must not overtake it on the GPU: the pick sees the index as of its call
   FI_CUDA(cudaStreamWaitEvent(h->s_index, h->ev_pick, 0));
+  const GossipLog gl = gossip_log(h);
   if (h->n_sets) {
     FI_CUDA(cudaMemcpyAsync(h->d_sets[b], h->h_sets[b], h->n_sets * sizeof(fi_index_op), cudaMemcpyHostToDevice, h->s_index));
     h->stats.h2d_bytes += h->n_sets * sizeof(fi_index_op);
     LaunchScope ls(h, h->s_index, K_INDEX);
-    FI_CUDA(launch_index_set(h->ix, h->d_ctr, h->d_sets[b], h->n_sets, h->cfg.endpoint_begin, h->cfg.endpoint_count, h->s_index));
+    FI_CUDA(launch_index_set(h->ix, h->d_ctr, h->d_sets[b], h->n_sets, h->cfg.endpoint_begin, h->cfg.endpoint_count, h->rank,
+                             gl, h->s_index));
   }
   if (h->n_clears) {
     FI_CUDA(cudaMemcpyAsync(h->d_clears[b], h->h_clears[b], h->n_clears * sizeof(fi_index_op), cudaMemcpyHostToDevice, h->s_index));
     h->stats.h2d_bytes += h->n_clears * sizeof(fi_index_op);
     LaunchScope ls(h, h->s_index, K_INDEX);
-    FI_CUDA(launch_index_clear(h->ix, h->d_ctr, h->d_clears[b], h->n_clears, h->cfg.endpoint_begin, h->cfg.endpoint_count, h->s_index));
+    FI_CUDA(launch_index_clear(h->ix, h->d_ctr, h->d_clears[b], h->n_clears, h->cfg.endpoint_begin, h->cfg.endpoint_count,
+                               h->rank, gl, h->s_index));
   }
   h->ops_applied += h->n_sets + h->n_clears;
   FI_CUDA(cudaEventRecord(h->ev_buf[b], h->s_index));
@@ -381,6 +527,68 @@ int flush_ops(fi_epp* h) {
   h->cur_buf ^= 1;
   // the buffer we are about to fill must have been consumed
   FI_CUDA(cudaEventSynchronize(h->ev_buf[h->cur_buf]));
+  return FI_OK;
+}
+
+int nccl_allgather_on(fi_epp* h, const void* send, void* recv, size_t bytes, cudaStream_t s);
+
+// Sharded pools, one gossip round (collective: every rank calls it the same number of times): exchange the
+// transition logs written by this round's SET / CLEAR kernels and replay the other ranks' into the local
+// directory — all APPEARs before all VANISHes, like the SETs and CLEARs that produced them.
+int gossip_round(fi_epp* h) {
+  if (h->world <= 1) return FI_OK;
+  const uint32_t Wd = h->world;
+  int rc = nccl_allgather_on(h, h->d_glog_n, h->d_ghdr, 2 * sizeof(unsigned long long), h->s_index);
+  if (rc != FI_OK) return rc;
+  FI_CUDA(cudaMemcpyAsync(h->h_ghdr, h->d_ghdr, (size_t)Wd * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_index));
+  FI_CUDA(cudaStreamSynchronize(h->s_index));
+  uint64_t na = 0, nv = 0;
+  for (uint32_t g = 0; g < Wd; ++g) {
+    na = std::max<uint64_t>(na, h->h_ghdr[2 * g]);
+    nv = std::max<uint64_t>(nv, h->h_ghdr[2 * g + 1]);
+  }
+  if (na > kOpChunk || nv > kOpChunk) return fail(h, FI_ERR_STATE, "gossip log overflow");
+  if (na) {
+    rc = nccl_allgather_on(h, h->d_glog_a, h->d_ggather, na * sizeof(uint64_t), h->s_index);
+    if (rc != FI_OK) return rc;
+    for (uint32_t g = 0; g < Wd; ++g) {
+      if (g == h->rank || h->h_ghdr[2 * g] == 0) continue;
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_index_remote_appear(h->ix, h->d_ctr, h->d_ggather + (size_t)g * na, h->h_ghdr[2 * g], g, h->s_index));
+    }
+  }
+  if (nv) {
+    rc = nccl_allgather_on(h, h->d_glog_v, h->d_ggather, nv * sizeof(uint64_t), h->s_index);
+    if (rc != FI_OK) return rc;
+    for (uint32_t g = 0; g < Wd; ++g) {
+      if (g == h->rank || h->h_ghdr[2 * g + 1] == 0) continue;
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_index_remote_vanish(h->ix, h->d_ctr, h->d_ggather + (size_t)g * nv, h->h_ghdr[2 * g + 1], g, h->s_index));
+    }
+  }
+  FI_CUDA(cudaMemsetAsync(h->d_glog_n, 0, 2 * sizeof(unsigned long long), h->s_index));
+  if (na || nv) {  // the replays allocate nodes too: refresh the counters the rebuild decision reads
+    FI_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(IndexCounters), cudaMemcpyDeviceToHost, h->s_index));
+    FI_CUDA(cudaEventRecord(h->ev_ctr, h->s_index));
+    h->ctr_pending = true;
+  }
+  FI_CUDA(cudaEventRecord(h->ev_index, h->s_index));
+  return FI_OK;
+}
+
+// Sharded pools: agree on how many gossip rounds a collective index call needs (the ranks' op counts differ)
+int agree_rounds(fi_epp* h, uint64_t mine, uint64_t* rounds) {
+  *rounds = mine;
+  if (h->world <= 1) return FI_OK;
+  unsigned long long v[2] = {mine, 0};
+  FI_CUDA(cudaMemcpyAsync(h->d_ghdr + 2 * (size_t)h->world, v, sizeof(v), cudaMemcpyHostToDevice, h->s_index));
+  int rc = nccl_allgather_on(h, h->d_ghdr + 2 * (size_t)h->world, h->d_ghdr, sizeof(v), h->s_index);
+  if (rc != FI_OK) return rc;
+  FI_CUDA(cudaMemcpyAsync(h->h_ghdr, h->d_ghdr, (size_t)h->world * sizeof(v), cudaMemcpyDeviceToHost, h->s_index));
+  FI_CUDA(cudaStreamSynchronize(h->s_index));
+  uint64_t m = 0;
+  for (uint32_t g = 0; g < h->world; ++g) m = std::max<uint64_t>(m, h->h_ghdr[2 * g]);
+  *rounds = m;
   return FI_OK;
 }
 
@@ -408,7 +616,7 @@ int upload_endpoints(fi_epp* h) {
   {
     LaunchScope ls(h, h->s_main, K_OTHER);
     FI_CUDA(launch_prepare_endpoints(h->d_eps, h->cfg.num_endpoints, h->cfg.endpoint_begin, h->cfg.endpoint_count, h->st,
-                                     h->d_sc, h->d_elig, h->d_zero, h->s_main));
+                                     h->d_sc, h->d_elig, h->d_zero, h->d_ztie, h->s_main));
   }
   // eps is pageable host memory: the copy above has been staged by the time the call returns
   h->eps_dirty = false;
@@ -444,12 +652,13 @@ int run_hash(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
   return FI_OK;
 }
 
-int nccl_allgather(fi_epp* h, const void* send, void* recv, size_t bytes) {
-  int rc = g_nccl.AllGather(send, recv, bytes, ncclInt8, h->comm, h->s_main);
+int nccl_allgather_on(fi_epp* h, const void* send, void* recv, size_t bytes, cudaStream_t s) {
+  int rc = g_nccl.AllGather(send, recv, bytes, ncclInt8, h->comm, s);
   if (rc != ncclSuccess)
     return fail(h, FI_ERR_COMM, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
   return FI_OK;
 }
+int nccl_allgather(fi_epp* h, const void* send, void* recv, size_t bytes) { return nccl_allgather_on(h, send, recv, bytes, h->s_main); }
 
 // Peer-memory exchange set-up (sharded mode): allocate this rank's buffer, exchange its IPC handle over
 // the NCCL communicator, map every peer's buffer.  Falls back to the NCCL all-gather path (px.enabled = 0)
@@ -468,17 +677,12 @@ int setup_peer_exchange(fi_epp* h) {
   const char* mode = std::getenv("FI_EPP_EXCHANGE");
   const bool want = !(mode && std::strcmp(mode, "nccl") == 0) && h->world <= (uint32_t)FI_MAX_RANKS;
   const uint64_t R = h->cfg.max_batch;
-  const uint32_t mask_words = (h->MP + 31) / 32;
   auto up = [](uint64_t v) { return (v + 255) & ~255ull; };
   PeerXchg px{};
   px.world = h->world;
   px.rank = h->rank;
   uint64_t off = 0;
   for (int par = 0; par < 2; ++par) {  // tagged 64-bit words (kernels.cuh PeerXchg)
-    px.off_mask[par] = off;
-    off = up(off + (uint64_t)h->world * R * mask_words * sizeof(uint64_t));
-  }
-  for (int par = 0; par < 2; ++par) {
     px.off_pick[par] = off;
     off = up(off + (uint64_t)h->world * R * h->P * 4 * sizeof(uint64_t));
   }
@@ -586,9 +790,39 @@ struct HostFeed {
   const uint64_t* offsets;  // host, [R+1]
 };
 
+void fill_match_params(fi_epp* h, MatchParams& mp, const uint64_t* chain, const uint32_t* nb, const uint64_t* d_offsets,
+                       const uint64_t* d_h0, const uint64_t* d_adapters, uint32_t R, fi_pick* out, bool local_pd) {
+  mp.chain = chain;
+  mp.nblocks = nb;
+  mp.offsets = d_offsets;
+  mp.adapters = d_adapters;
+  mp.R = R;
+  mp.MP = h->MP;
+  mp.ix = h->ix;
+  mp.st = h->st;
+  mp.ep_begin = h->cfg.endpoint_begin;
+  mp.ep_count = h->cfg.endpoint_count;
+  mp.E_global = h->cfg.num_endpoints;
+  mp.r_base = 0;
+  mp.h0 = d_h0;
+  mp.lpm = h->cfg.match_mode;
+  mp.apply_pd = (h->cfg.pd_enabled && local_pd) ? 1 : 0;
+  mp.pd_decode = h->cfg.pd_decode_profile;
+  mp.pd_prefill = h->cfg.pd_prefill_profile;
+  mp.pd_threshold = h->cfg.pd_threshold;
+  mp.out = out;
+  mp.probed_blocks = h->profiling ? h->d_probed : nullptr;
+  mp.work_counter = h->d_work;
+  mp.zero_work_counter = 1;
+  mp.lane_zero = 0;
+}
+
 // the whole pick on device buffers; result in d_out ([R][P])
 int run_pick_impl(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, const uint64_t* d_h0,
                   const uint64_t* d_adapters, uint32_t R, fi_pick* d_out, const HostFeed* feed) {
+  const bool sharded = h->world > 1;
+  if (sharded && (h->n_sets || h->n_clears))
+    return fail(h, FI_ERR_STATE, "sharded pool: index updates are collective (fi_epp_index_apply / fi_epp_index_add_chains)");
   int rc = flush_ops(h);
   if (rc != FI_OK) return rc;
   rc = check_counters(h);
@@ -607,29 +841,8 @@ int run_pick_impl(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets
   if (h->pipe_seq) {  // a plain pick after pipelined submits: their stage A shares d_pre with ours
     FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_a[(h->pipe_seq - 1) & 1], 0));
   }
-  const bool sharded = h->world > 1;
   MatchParams mp{};
-  mp.chain = h->d_chain;
-  mp.nblocks = h->d_nblocks;
-  mp.offsets = d_offsets;
-  mp.adapters = d_adapters;
-  mp.R = R;
-  mp.MP = h->MP;
-  mp.ix = h->ix;
-  mp.st = h->st;
-  mp.ep_begin = h->cfg.endpoint_begin;
-  mp.lpm = h->cfg.match_mode;
-  mp.apply_pd = (h->cfg.pd_enabled && !sharded) ? 1 : 0;
-  mp.pd_decode = h->cfg.pd_decode_profile;
-  mp.pd_prefill = h->cfg.pd_prefill_profile;
-  mp.pd_threshold = h->cfg.pd_threshold;
-  mp.mask_words = (h->MP + 31) / 32;
-  mp.gmask = nullptr;
-  mp.gmask_ranks = 0;
-  mp.out = sharded ? h->d_local : d_out;
-  mp.probed_blocks = h->profiling ? h->d_probed : nullptr;
-  mp.work_counter = h->d_work;
-  mp.zero_work_counter = 1;
+  fill_match_params(h, mp, h->d_chain, h->d_nblocks, d_offsets, d_h0, d_adapters, R, sharded ? h->d_local : d_out, !sharded);
 
   const uint32_t S = h->feed_slices;
   if (feed && !sharded && h->fast_hash && S > 1 && R >= 64 * S && feed->offsets[R] >= (8ull << 20)) {
@@ -655,6 +868,8 @@ int run_pick_impl(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets
       ms.nblocks = mp.nblocks + r0;
       ms.offsets = mp.offsets ? mp.offsets + r0 : nullptr;
       ms.adapters = mp.adapters ? mp.adapters + r0 : nullptr;
+      ms.h0 = mp.h0 + r0;
+      ms.r_base = r0;
       ms.R = Rk;
       ms.out = mp.out + (size_t)r0 * h->P;
       ms.work_counter = h->d_work + k;
@@ -686,67 +901,71 @@ int run_pick_impl(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets
     return FI_OK;
   }
 
-  rc = run_hash(h, d_prompts, d_offsets, d_h0, 0, R, h->s_main);
-  if (rc != FI_OK) return rc;
+  // ---- endpoint-range sharded pool --------------------------------------------------------------
+  // Hashing: every rank needs every request's chain.  split: rank g hashes requests [g·per, (g+1)·per) and
+  // the chain rows + block counts are all-gathered in place (2 KiB per request over NVLink instead of
+  // re-reading 16 KiB of prompt on every rank); replicated: every rank hashes everything.
+  if (h->split_hash && h->fast_hash && R >= 32 * h->world) {
+    const uint32_t per = (((R + h->world - 1) / h->world) + 31) & ~31u;  // ≤ chain_rows / world
+    const uint32_t r0 = std::min(R, h->rank * per), r1 = std::min(R, r0 + per);
+    if (r1 > r0) {
+      rc = run_hash(h, d_prompts, d_offsets, d_h0, r0, r1 - r0, h->s_main);
+      if (rc != FI_OK) return rc;
+    }
+    rc = nccl_allgather(h, h->d_chain + (size_t)h->rank * per * h->MP, h->d_chain, (size_t)per * h->MP * sizeof(uint64_t));
+    if (rc != FI_OK) return rc;
+    rc = nccl_allgather(h, h->d_nblocks + (size_t)h->rank * per, h->d_nblocks, (size_t)per * sizeof(uint32_t));
+    if (rc != FI_OK) return rc;
+    h->stats.n_other += 2;  // two collectives of the step (not kernels of this library)
+  } else {
+    rc = run_hash(h, d_prompts, d_offsets, d_h0, 0, R, h->s_main);
+    if (rc != FI_OK) return rc;
+  }
   const bool p2p = h->px.enabled != 0;
   if (p2p) {
-    // Peer-memory exchange: the producer kernels store tagged words into every rank's buffer and the
-    // consumer kernels poll per request, so the step has no collective call, no barrier between the
-    // ranks and no host round trip.
-    // a timeout seen by any earlier call is sticky (the kernels set the mapped host word)
-    if (*h->h_xerr) return fail(h, FI_ERR_COMM, "peer exchange timed out waiting for another rank");
+    // Peer-memory exchange: match_pick stores this rank's picks as tagged words into every rank's buffer and
+    // merge_picks polls per request, so the reduction has no collective call, no barrier between the ranks
+    // and no host round trip.  A timeout is reported once (the kernels set the mapped host word).
+    if (*h->h_xerr) {
+      *h->h_xerr = 0;
+      return fail(h, FI_ERR_COMM, "peer exchange timed out waiting for another rank");
+    }
     h->px.step += 1;
     if (h->px.step == 0) h->px.step = 1;  // tag 0 is the zero-initialised buffer
     mp.px = h->px;
-  }
-  if (sharded && h->cfg.match_mode == FI_MATCH_UPSTREAM) {
-    // exact upstream semantics need the global first miss: exchange presence masks
-    {
-      LaunchScope ls(h, h->s_main, K_OTHER);
-      mp.slots = h->d_slots;
-      FI_CUDA(launch_probe_slots(mp, h->d_mask, h->sm_count, h->s_main));
-    }
-    if (p2p) {
-      mp.gmask = reinterpret_cast<const uint32_t*>(h->d_xchg + h->px.off_mask[h->px.step & 1u]);
-    } else {
-      const size_t bytes = (size_t)R * mp.mask_words * sizeof(uint32_t);
-      // gathered layout must be [rank][R][words] with the *call's* R
-      rc = nccl_allgather(h, h->d_mask, h->d_gmask, bytes);
-      if (rc != FI_OK) return rc;
-      mp.gmask = h->d_gmask;
-    }
-    mp.gmask_ranks = h->world;
   }
   {
     LaunchScope ls(h, h->s_main, K_MATCH);
     FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
   }
-  if (sharded) {
-    MergeParams mg{};
-    if (p2p) {
-      mg.gathered = reinterpret_cast<const fi_pick*>(h->d_xchg + h->px.off_pick[h->px.step & 1u]);
-      mg.px = h->px;
-    } else {
-      rc = nccl_allgather(h, h->d_local, h->d_gather, (size_t)R * h->P * sizeof(fi_pick));
-      if (rc != FI_OK) return rc;
-      mg.gathered = h->d_gather;
-    }
-    mg.ranks = h->world;
-    mg.R = R;
-    mg.P = h->P;
-    mg.nblocks = h->d_nblocks;
-    mg.offsets = d_offsets;
-    mg.apply_pd = h->cfg.pd_enabled;
-    mg.pd_decode = h->cfg.pd_decode_profile;
-    mg.pd_prefill = h->cfg.pd_prefill_profile;
-    mg.pd_threshold = h->cfg.pd_threshold;
-    mg.out = d_out;
-    {
-      LaunchScope ls(h, h->s_main, K_OTHER);
-      FI_CUDA(launch_merge_picks(mg, h->s_main));
-    }
-    dump_trace(h, R);
+  MergeParams mg{};
+  if (p2p) {
+    mg.gathered = reinterpret_cast<const fi_pick*>(h->d_xchg + h->px.off_pick[h->px.step & 1u]);
+    mg.px = h->px;
+  } else {
+    rc = nccl_allgather(h, h->d_local, h->d_gather, (size_t)R * h->P * sizeof(fi_pick));
+    if (rc != FI_OK) return rc;
+    mg.gathered = h->d_gather;
   }
+  mg.ranks = h->world;
+  mg.R = R;
+  mg.P = h->P;
+  mg.nblocks = h->d_nblocks;
+  mg.offsets = d_offsets;
+  mg.chain = h->d_chain;
+  mg.h0 = d_h0;
+  mg.MP = h->MP;
+  mg.E_global = h->cfg.num_endpoints;
+  mg.apply_pd = h->cfg.pd_enabled;
+  mg.pd_decode = h->cfg.pd_decode_profile;
+  mg.pd_prefill = h->cfg.pd_prefill_profile;
+  mg.pd_threshold = h->cfg.pd_threshold;
+  mg.out = d_out;
+  {
+    LaunchScope ls(h, h->s_main, K_OTHER);
+    FI_CUDA(launch_merge_picks(mg, h->s_main));
+  }
+  dump_trace(h, R);
   h->stats.pick_calls++;
   h->stats.requests += R;
   return FI_OK;
@@ -816,25 +1035,8 @@ int submit_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, 
   if (rc != FI_OK) return rc;
   FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_a[slot], 0));
   MatchParams mp{};
-  mp.chain = chain;
-  mp.nblocks = nb;
-  mp.offsets = d_offsets;
-  mp.adapters = nullptr;
-  mp.R = R;
-  mp.MP = h->MP;
-  mp.ix = h->ix;
-  mp.st = h->st;
-  mp.ep_begin = h->cfg.endpoint_begin;
-  mp.lpm = h->cfg.match_mode;
-  mp.apply_pd = h->cfg.pd_enabled ? 1 : 0;
-  mp.pd_decode = h->cfg.pd_decode_profile;
-  mp.pd_prefill = h->cfg.pd_prefill_profile;
-  mp.pd_threshold = h->cfg.pd_threshold;
-  mp.mask_words = (h->MP + 31) / 32;
-  mp.out = d_out;
-  mp.probed_blocks = h->profiling ? h->d_probed : nullptr;
+  fill_match_params(h, mp, chain, nb, d_offsets, d_h0, nullptr, R, d_out, true);
   mp.work_counter = h->d_work + 8 + slot;
-  mp.zero_work_counter = 1;
   {
     LaunchScope ls(h, h->s_main, K_MATCH);
     FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
@@ -968,13 +1170,16 @@ void fi_epp_destroy(fi_epp* h) {
   cudaFree(h->d_picks);
   cudaFree(h->d_local);
   cudaFree(h->d_gather);
-  cudaFree(h->d_mask);
-  cudaFree(h->d_gmask);
+  cudaFree(h->d_glog_n);
+  cudaFree(h->d_glog_a);
+  cudaFree(h->d_glog_v);
+  cudaFree(h->d_ghdr);
+  cudaFree(h->d_ggather);
+  if (h->h_ghdr) cudaFreeHost(h->h_ghdr);
   for (int k = 0; k < FI_MAX_RANKS; ++k)
     if (h->peer_ipc[k]) cudaIpcCloseMemHandle(h->peer_ipc[k]);
   cudaFree(h->d_xchg);
   if (h->h_xerr) cudaFreeHost((void*)h->h_xerr);
-  cudaFree(h->d_slots);
   cudaFree(h->d_probed);
   cudaFree(h->d_work);
   cudaFree(h->d_ctr);
@@ -982,10 +1187,13 @@ void fi_epp_destroy(fi_epp* h) {
   cudaFree(h->d_sc);
   cudaFree(h->d_elig);
   cudaFree(h->d_zero);
+  cudaFree(h->d_ztie);
   cudaFree(h->d_lora);
   cudaFree(h->d_adapters);
   if (h->h_adapters) cudaFreeHost(h->h_adapters);
+  h->pool.reset();
   free_index(h->ix);
+  free_index(h->ix_spare);
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->d_sets[b]);
     cudaFree(h->d_clears[b]);
@@ -1052,14 +1260,15 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaGetDeviceProperties(&prop, cfg->device));
   h->sm_count = prop.multiProcessorCount;
   h->P = cfg->n_profiles;
-  h->MP = (cfg->max_blocks + 3) & ~3u;
+  h->MP = (cfg->max_blocks + 7) & ~7u;  // whole groups of 8 links for the chain walker
   h->W = pow2_ceil32((cfg->endpoint_count + 31) / 32);
   h->fast_hash = (cfg->block_bytes % 32) == 0;
   if (const char* e = std::getenv("FI_EPP_TRACE")) h->trace_call = std::strtol(e, nullptr, 10);
   if (h->cfg.max_prompt_bytes == 0)
     h->cfg.max_prompt_bytes = (uint64_t)cfg->max_batch * cfg->block_bytes * cfg->max_blocks;
   if (h->cfg.index_slots == 0) {
-    uint64_t want = 2ull * cfg->endpoint_count * (cfg->lru_capacity ? cfg->lru_capacity : 1024);  // load <= 0.5
+    // load <= 0.5; an endpoint-range shard is a directory of the WHOLE pool's keys (rows for its own endpoints)
+    uint64_t want = 2ull * cfg->num_endpoints * (cfg->lru_capacity ? cfg->lru_capacity : 1024);
     if (want < 4096) want = 4096;
     h->cfg.index_slots = pow2_ceil64(want);
     if (h->cfg.index_slots > 0x80000000ull) h->cfg.index_slots = 0x80000000ull;
@@ -1080,13 +1289,17 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
     FI_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   FI_TRY(cudaEventRecord(h->ev_index, h->s_index));
   const uint64_t R = cfg->max_batch;
-  const uint32_t mask_words = (h->MP + 31) / 32;
+  // rows of the per-request buffers: whole groups of 32 requests (the pre-states are tiled), and — for a shard
+  // of a bigger pool — room for the in-place all-gather of `world` equal slices of 32-aligned length
+  h->chain_rows = (uint32_t)((R + 31) / 32 * 32);
+  if (cfg->endpoint_count < cfg->num_endpoints) h->chain_rows += 32 * (FI_MAX_RANKS + 1);
+  if (const char* e = std::getenv("FI_EPP_SHARD_HASH")) h->split_hash = std::strcmp(e, "replicated") != 0;
   FI_TRY(cudaMalloc(&h->d_prompts, h->cfg.max_prompt_bytes + 64));
   FI_TRY(cudaMalloc(&h->d_offsets, (R + 1) * sizeof(uint64_t)));
   FI_TRY(cudaMalloc(&h->d_h0, R * sizeof(uint64_t)));
-  FI_TRY(cudaMalloc(&h->d_pre, ((R + 31) / 32 * 32) * h->MP * sizeof(uint64_t)));
-  FI_TRY(cudaMalloc(&h->d_chain, R * h->MP * sizeof(uint64_t)));
-  FI_TRY(cudaMalloc(&h->d_nblocks, R * sizeof(uint32_t)));
+  FI_TRY(cudaMalloc(&h->d_pre, (size_t)h->chain_rows * h->MP * sizeof(uint64_t)));
+  FI_TRY(cudaMalloc(&h->d_chain, (size_t)h->chain_rows * h->MP * sizeof(uint64_t)));
+  FI_TRY(cudaMalloc(&h->d_nblocks, (size_t)h->chain_rows * sizeof(uint32_t)));
   FI_TRY(cudaMalloc(&h->d_picks, R * h->P * sizeof(fi_pick)));
   FI_TRY(cudaMalloc(&h->d_probed, sizeof(unsigned long long)));
   FI_TRY(cudaMemset(h->d_probed, 0, sizeof(unsigned long long)));
@@ -1096,7 +1309,6 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaMallocHost(&h->h_offsets, (R + 1) * sizeof(uint64_t)));
   FI_TRY(cudaMallocHost(&h->h_h0, R * sizeof(uint64_t)));
   FI_TRY(cudaMallocHost(&h->h_nblocks, R * sizeof(uint32_t)));
-  (void)mask_words;
 
   // index
   FI_TRY(cudaMalloc(&h->d_ctr, sizeof(IndexCounters)));
@@ -1105,7 +1317,7 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   std::memset(h->h_ctr, 0, sizeof(IndexCounters));
   {
     int rc = alloc_index(h, h->cfg.index_slots, &h->ix);
-    if (rc != FI_OK) return die(rc == FI_ERR_CUDA ? FI_ERR_NOMEM : rc);
+    if (rc != FI_OK) return die(rc);
   }
   for (int b = 0; b < 2; ++b) {
     FI_TRY(cudaMallocHost(&h->h_sets[b], kOpChunk * sizeof(fi_index_op)));
@@ -1124,6 +1336,8 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaMalloc(&h->d_sc, (size_t)FI_EPP_MAX_PROFILES * FI_EPP_MAX_SCORERS * Epad * sizeof(double)));
   FI_TRY(cudaMalloc(&h->d_elig, (size_t)FI_EPP_MAX_PROFILES * h->W * sizeof(uint32_t)));
   FI_TRY(cudaMalloc(&h->d_zero, FI_EPP_MAX_PROFILES * sizeof(ZeroBest)));
+  FI_TRY(cudaMalloc(&h->d_ztie, (size_t)FI_EPP_MAX_PROFILES * h->W * sizeof(uint32_t)));
+  FI_TRY(cudaMemset(h->d_ztie, 0, (size_t)FI_EPP_MAX_PROFILES * h->W * sizeof(uint32_t)));
   FI_TRY(cudaMemset(h->d_sc, 0, (size_t)FI_EPP_MAX_PROFILES * FI_EPP_MAX_SCORERS * Epad * sizeof(double)));
   FI_TRY(cudaMemset(h->d_elig, 0, (size_t)FI_EPP_MAX_PROFILES * h->W * sizeof(uint32_t)));
   h->st.n_profiles = h->P;
@@ -1131,6 +1345,7 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   h->st.sc = h->d_sc;
   h->st.elig = h->d_elig;
   h->st.zero = h->d_zero;
+  h->st.ztie = h->d_ztie;
   h->lora.assign(Epad, LoraDev{});
   FI_TRY(cudaMalloc(&h->d_lora, (size_t)Epad * sizeof(LoraDev)));
   FI_TRY(cudaMemset(h->d_lora, 0, (size_t)Epad * sizeof(LoraDev)));
@@ -1198,22 +1413,54 @@ int fi_epp_endpoints_lora_update(fi_epp* h, const fi_endpoint_lora* s, uint32_t 
   return FI_OK;
 }
 
+// One collective index update of a sharded pool = `rounds` gossip rounds on every rank; `step(i)` stages and
+// flushes this rank's share of round i (nothing if it has fewer).  Single rank: just the steps.
+static int run_rounds(fi_epp* h, uint64_t mine, int my_err, const std::function<int(uint64_t)>& step) {
+  if (h->world <= 1) {
+    if (my_err != FI_OK) return my_err;
+    for (uint64_t i = 0; i < mine; ++i) {
+      int rc = step(i);
+      if (rc != FI_OK) return rc;
+    }
+    return FI_OK;
+  }
+  // a rank whose arguments were rejected still takes part (with zero rounds) so that the others do not hang
+  uint64_t rounds = 0;
+  int rc = agree_rounds(h, my_err == FI_OK ? mine : 0, &rounds);
+  if (rc != FI_OK) return rc;
+  for (uint64_t i = 0; i < rounds; ++i) {
+    if (my_err == FI_OK && i < mine) {
+      rc = step(i);
+      if (rc != FI_OK) return rc;
+    }
+    rc = gossip_round(h);
+    if (rc != FI_OK) return rc;
+  }
+  return my_err;
+}
+
 int fi_epp_index_apply(fi_epp* h, const fi_index_op* ops, uint64_t n) {
   if (!h || (!ops && n)) return FI_ERR_INVALID;
   std::lock_guard<std::mutex> lk(h->mu);
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
-  int rc = check_counters(h);
-  if (rc != FI_OK) return rc;
-  const uint32_t lo = h->cfg.endpoint_begin, cnt = h->cfg.endpoint_count;
-  for (uint64_t i = 0; i < n; ++i) {
-    const fi_index_op& op = ops[i];
-    if (op.op != FI_OP_SET && op.op != FI_OP_CLEAR) return fail(h, FI_ERR_INVALID, "bad index opcode");
-    if (op.endpoint >= h->cfg.num_endpoints) return fail(h, FI_ERR_INVALID, "index op endpoint out of range");
-    if (op.endpoint - lo >= cnt) continue;  // another rank's shard
-    rc = submit_op(h, op.hash, op.endpoint, op.op);
-    if (rc != FI_OK) return rc;
+  int err = check_counters(h);
+  for (uint64_t i = 0; i < n && err == FI_OK; ++i) {
+    if (ops[i].op != FI_OP_SET && ops[i].op != FI_OP_CLEAR) err = fail(h, FI_ERR_INVALID, "bad index opcode");
+    else if (ops[i].endpoint >= h->cfg.num_endpoints) err = fail(h, FI_ERR_INVALID, "index op endpoint out of range");
   }
-  return flush_ops(h);
+  const uint32_t lo = h->cfg.endpoint_begin, cnt = h->cfg.endpoint_count;
+  // rounds of kOpChunk input ops: a round never overflows the staging buffers (or, sharded, the gossip log)
+  const uint64_t rounds = (n + kOpChunk - 1) / kOpChunk;
+  return run_rounds(h, rounds, err, [&](uint64_t i) -> int {
+    const uint64_t i0 = i * kOpChunk, i1 = std::min(n, i0 + kOpChunk);
+    for (uint64_t k = i0; k < i1; ++k) {
+      const fi_index_op& op = ops[k];
+      if (op.endpoint - lo >= cnt) continue;  // another rank's shard
+      int rc = submit_op(h, op.hash, op.endpoint, op.op);
+      if (rc != FI_OK) return rc;
+    }
+    return flush_ops(h);
+  });
 }
 
 int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes, uint32_t n) {
@@ -1221,6 +1468,7 @@ int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes,
   std::lock_guard<std::mutex> lk(h->mu);
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
   if (!h->cfg.lru_capacity) return fail(h, FI_ERR_STATE, "lru_capacity is 0: the host LRU is disabled");
+  if (h->world > 1) return fail(h, FI_ERR_STATE, "sharded pool: use the collective fi_epp_index_add_chains");
   if (endpoint >= h->cfg.num_endpoints) return fail(h, FI_ERR_INVALID, "endpoint out of range");
   const uint32_t e = endpoint - h->cfg.endpoint_begin;
   if (e >= h->cfg.endpoint_count) return FI_OK;  // another rank's shard
@@ -1243,6 +1491,264 @@ int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes,
   // the deltas stay staged: they are launched when the staging buffer fills and, at the latest,
   // by the next pick / sync (one launch group per batch of decisions instead of one per chain)
   return FI_OK;
+}
+
+namespace {
+
+// open-addressed set of 64-bit keys, emptied in O(1) (generation stamps): the hashes one endpoint evicted
+// during the current fi_epp_index_add_chains call
+struct StampSet {
+  std::vector<uint64_t> key;
+  std::vector<uint32_t> gen;
+  uint32_t cur = 0, mask = 0, used = 0;
+  void reset() {
+    if (key.empty()) {
+      key.assign(1u << 12, 0);
+      gen.assign(1u << 12, 0);
+      mask = (1u << 12) - 1;
+    }
+    ++cur;
+    used = 0;
+    if (cur == 0) {  // stamp wrapped
+      std::fill(gen.begin(), gen.end(), 0u);
+      cur = 1;
+    }
+  }
+  static uint32_t mix(uint64_t h) {
+    h ^= h >> 29;
+    h *= 0x9E3779B97F4A7C15ULL;
+    return (uint32_t)(h >> 32);
+  }
+  bool contains(uint64_t k) const {
+    for (uint32_t i = mix(k) & mask;; i = (i + 1) & mask) {
+      if (gen[i] != cur) return false;
+      if (key[i] == k) return true;
+    }
+  }
+  void insert(uint64_t k) {
+    if ((used + 1) * 2 > mask + 1) grow();
+    for (uint32_t i = mix(k) & mask;; i = (i + 1) & mask) {
+      if (gen[i] != cur) {
+        gen[i] = cur;
+        key[i] = k;
+        ++used;
+        return;
+      }
+      if (key[i] == k) return;
+    }
+  }
+  void grow() {
+    std::vector<uint64_t> ok;
+    ok.reserve(used);
+    for (uint32_t i = 0; i <= mask; ++i)
+      if (gen[i] == cur) ok.push_back(key[i]);
+    const uint32_t n = (mask + 1) * 2;
+    key.assign(n, 0);
+    gen.assign(n, 0);
+    mask = n - 1;
+    cur = 1;
+    used = 0;
+    for (uint64_t k : ok) insert(k);
+  }
+};
+
+// ops one worker produced, by segment: within a segment SETs run before CLEARs; a SET that follows a CLEAR of
+// the same (hash, endpoint) pair opens the endpoint's next segment ("last op wins", exactly)
+struct WorkerOps {
+  std::vector<std::vector<fi_index_op>> sets, clears;
+  StampSet evicted;
+  void need(size_t seg) {
+    if (sets.size() <= seg) {
+      sets.resize(seg + 1);
+      clears.resize(seg + 1);
+    }
+  }
+};
+
+struct CopyJob {
+  fi_index_op* dst;
+  const fi_index_op* src;
+  size_t n;
+};
+
+}  // namespace
+
+// Upstream PreRequest for a whole batch of decisions: indexer.Add(chain_r, endpoints[r]) for r = 0..R-1, in
+// request order per endpoint (the endpoints' LRUs are independent of each other, so they are walked in
+// parallel on the host worker pool; the result equals R sequential fi_epp_index_add_chain calls).
+int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains, uint32_t pitch_blocks,
+                            const uint32_t* nblocks, uint32_t R) {
+  if (!h || ((!endpoints || !chains || !nblocks) && R)) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  int err = FI_OK;
+  if (!h->cfg.lru_capacity) err = fail(h, FI_ERR_STATE, "lru_capacity is 0: the host LRU is disabled");
+  for (uint32_t r = 0; r < R && err == FI_OK; ++r) {
+    if (endpoints[r] != FI_NO_ENDPOINT && endpoints[r] >= h->cfg.num_endpoints) err = fail(h, FI_ERR_INVALID, "endpoint out of range");
+    else if (nblocks[r] > pitch_blocks) err = fail(h, FI_ERR_INVALID, "nblocks[r] larger than the chain pitch");
+  }
+  if (err == FI_OK) err = check_counters(h);
+
+  // ---- 1. requests of every local endpoint, in request order (counting sort)
+  const uint32_t lo = h->cfg.endpoint_begin, EL = h->cfg.endpoint_count;
+  std::vector<uint32_t> first(EL + 1, 0), order, active;
+  std::vector<WorkerOps> outs;
+  size_t nseg = 0;
+  if (err == FI_OK) {
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint32_t e = endpoints[r] - lo;
+      if (endpoints[r] != FI_NO_ENDPOINT && e < EL && nblocks[r]) first[e + 1]++;
+    }
+    for (uint32_t e = 0; e < EL; ++e) {
+      if (first[e + 1]) active.push_back(e);
+      first[e + 1] += first[e];
+    }
+    order.resize(first[EL]);
+    std::vector<uint32_t> fill(first.begin(), first.end() - 1);
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint32_t e = endpoints[r] - lo;
+      if (endpoints[r] != FI_NO_ENDPOINT && e < EL && nblocks[r]) order[fill[e]++] = r;
+    }
+    // ---- 2. walk the LRUs: one endpoint per task
+    if (!h->pool) {
+      unsigned t = std::min(usable_cores(), 64u);
+      if (const char* ev = std::getenv("FI_EPP_LRU_THREADS")) t = (unsigned)std::max(1L, std::strtol(ev, nullptr, 10));
+      h->pool.reset(new WorkerPool(t));
+    }
+    outs.resize(h->pool->size());
+    h->pool->run((uint32_t)active.size(), [&](uint32_t task, unsigned w) {
+      const uint32_t e = active[task];
+      LruSet& l = h->lrus[e];
+      WorkerOps& o = outs[w];
+      o.evicted.reset();
+      size_t seg = 0;
+      o.need(0);
+      bool any_evicted = false;
+      for (uint32_t k = first[e]; k < first[e + 1]; ++k) {
+        const uint32_t r = order[k];
+        const uint64_t* c = chains + (size_t)r * pitch_blocks;
+        for (uint32_t i = 0; i < nblocks[r]; ++i) {
+          uint64_t ev = 0;
+          bool did = false;
+          const bool inserted = l.touch(c[i], &ev, &did);
+          if (did) {
+            o.clears[seg].push_back(fi_index_op{ev, e + lo, FI_OP_CLEAR});
+            o.evicted.insert(ev);
+            any_evicted = true;
+          }
+          if (inserted) {
+            if (any_evicted && o.evicted.contains(c[i])) {  // re-added after its eviction in this call
+              ++seg;
+              o.need(seg);
+              o.evicted.reset();
+              any_evicted = false;
+            }
+            o.sets[seg].push_back(fi_index_op{c[i], e + lo, FI_OP_SET});
+          }
+        }
+      }
+    });
+    for (auto& o : outs) nseg = std::max(nseg, o.sets.size());
+  }
+
+  // ---- 3. stage segment by segment (SETs, then CLEARs), flushing whenever a staging buffer is full.
+  // `flushes` is first counted (dry run) so that the ranks of a sharded pool can agree on the rounds.
+  std::vector<CopyJob> jobs;
+  auto run_jobs = [&]() {
+    if (jobs.empty()) return;
+    // big copies into the pinned staging buffers go through the worker pool
+    std::vector<CopyJob> pieces;
+    const size_t kPiece = 1u << 16;
+    for (const CopyJob& j : jobs)
+      for (size_t o = 0; o < j.n; o += kPiece) pieces.push_back(CopyJob{j.dst + o, j.src + o, std::min(kPiece, j.n - o)});
+    h->pool->run((uint32_t)pieces.size(), [&](uint32_t t, unsigned) {
+      std::memcpy(pieces[t].dst, pieces[t].src, pieces[t].n * sizeof(fi_index_op));
+    });
+    jobs.clear();
+  };
+  // walk(dry): returns the number of flushes; !dry performs them through do_flush
+  auto walk = [&](bool dry, const std::function<int()>& do_flush, uint64_t* n_flush) -> int {
+    uint64_t ns = dry ? 0 : h->n_sets, nc = dry ? 0 : h->n_clears, flushes = 0;
+    auto flush = [&]() -> int {
+      ++flushes;
+      if (!dry) {
+        run_jobs();
+        h->n_sets = ns;
+        h->n_clears = nc;
+        int rc = do_flush();
+        if (rc != FI_OK) return rc;
+      }
+      ns = nc = 0;
+      return FI_OK;
+    };
+    for (size_t seg = 0; seg < nseg; ++seg) {
+      for (int kind = 0; kind < 2; ++kind) {
+        for (auto& o : outs) {
+          if (o.sets.size() <= seg) continue;
+          const std::vector<fi_index_op>& v = kind == 0 ? o.sets[seg] : o.clears[seg];
+          size_t done = 0;
+          while (done < v.size()) {
+            uint64_t& fillc = kind == 0 ? ns : nc;
+            const size_t room = (size_t)(kOpChunk - fillc);
+            const size_t take = std::min(room, v.size() - done);
+            if (!dry && take) {
+              fi_index_op* base = kind == 0 ? h->h_sets[h->cur_buf] : h->h_clears[h->cur_buf];
+              jobs.push_back(CopyJob{base + fillc, v.data() + done, take});
+            }
+            fillc += take;
+            done += take;
+            if (fillc == kOpChunk) {
+              int rc = flush();
+              if (rc != FI_OK) return rc;
+            }
+          }
+        }
+      }
+      if (seg + 1 < nseg && (ns || nc)) {  // segment boundary: the next segment's SETs must run after these CLEARs
+        int rc = flush();
+        if (rc != FI_OK) return rc;
+      }
+    }
+    if (!dry) {
+      run_jobs();
+      h->n_sets = ns;
+      h->n_clears = nc;
+    }
+    if (n_flush) *n_flush = flushes;
+    return FI_OK;
+  };
+
+  if (h->world <= 1) {
+    if (err != FI_OK) return err;
+    // the tail stays staged: it is launched with the next flush — at the latest by the next pick / sync
+    return walk(false, [&]() { return flush_ops(h); }, nullptr);
+  }
+  // sharded: every flush is one gossip round, the tail included
+  uint64_t mine = 0;
+  if (err == FI_OK) {
+    walk(true, nullptr, &mine);
+    mine += 1;  // the tail
+  }
+  uint64_t rounds = 0;
+  int rc = agree_rounds(h, err == FI_OK ? mine : 0, &rounds);
+  if (rc != FI_OK) return rc;
+  uint64_t did = 0;
+  if (err == FI_OK) {
+    rc = walk(false, [&]() -> int {
+      int r2 = flush_ops(h);
+      if (r2 != FI_OK) return r2;
+      ++did;
+      return gossip_round(h);
+    }, nullptr);
+    if (rc != FI_OK) return rc;
+    rc = flush_ops(h);  // the tail
+    if (rc != FI_OK) return rc;
+  }
+  for (; did < rounds; ++did) {
+    rc = gossip_round(h);
+    if (rc != FI_OK) return rc;
+  }
+  return err;
 }
 
 int fi_epp_index_sync(fi_epp* h) {
@@ -1345,6 +1851,8 @@ int fi_epp_hash_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets
   if (rc != FI_OK) return rc;
   rc = stage_inputs(h, prompts, offsets, h0, R, total);
   if (rc != FI_OK) return rc;
+  if (h->pipe_seq)  // a pipelined batch's stage A (on s_a) shares d_pre with us
+    FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_a[(h->pipe_seq - 1) & 1], 0));
   rc = run_hash(h, h->d_prompts, h->d_offsets, h->d_h0, 0, R, h->s_main);
   if (rc != FI_OK) return rc;
   if (chains_out) {
@@ -1392,7 +1900,10 @@ int fi_epp_pick_batch_lora(fi_epp* h, const uint8_t* prompts, const uint64_t* of
     if (rc != FI_OK) return rc;
   }
   FI_CUDA(cudaStreamSynchronize(h->s_main));
-  if (h->h_xerr && *h->h_xerr) return fail(h, FI_ERR_COMM, "peer exchange timed out waiting for another rank");
+  if (h->h_xerr && *h->h_xerr) {  // reported once; the tags are monotonic, so later steps can succeed again
+    *h->h_xerr = 0;
+    return fail(h, FI_ERR_COMM, "peer exchange timed out waiting for another rank");
+  }
   std::memcpy(out, h->h_picks, pb);
   return FI_OK;
 }
@@ -1430,8 +1941,12 @@ int fi_epp_pick_batch_device_lora(fi_epp* h, const void* d_prompts, const void* 
 int fi_epp_pick_submit(fi_epp* h, const void* d_prompts, const void* d_offsets, const void* d_h0, uint32_t R,
                        uint64_t total_prompt_bytes, void* d_out, void* stream) {
   if (!h || !d_offsets || (!d_h0 && R) || (!d_out && R)) return FI_ERR_INVALID;
-  if (h->world > 1 || !h->fast_hash)  // sharded pools and odd block sizes: the stream-ordered path
-    return fi_epp_pick_batch_device(h, d_prompts, d_offsets, d_h0, R, total_prompt_bytes, d_out, nullptr, stream);
+  bool plain;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    plain = h->world > 1 || !h->fast_hash;  // sharded pools and odd block sizes: the stream-ordered path
+  }
+  if (plain) return fi_epp_pick_batch_device(h, d_prompts, d_offsets, d_h0, R, total_prompt_bytes, d_out, nullptr, stream);
   std::lock_guard<std::mutex> lk(h->mu);
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
   if (R == 0) return FI_OK;
@@ -1472,6 +1987,9 @@ int fi_epp_comm_init(fi_epp* h, const uint8_t id_bytes[FI_EPP_UNIQUE_ID_BYTES], 
   std::lock_guard<std::mutex> lk(h->mu);
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
   if (h->comm) return fail(h, FI_ERR_STATE, "communicator already initialised");
+  if (world > 32) return fail(h, FI_ERR_INVALID, "more than 32 ranks: the directory keeps one presence bit per rank");
+  if (h->ops_applied || h->n_sets || h->n_clears)
+    return fail(h, FI_ERR_STATE, "fi_epp_comm_init must precede the first index update (the directory is built by gossip)");
   if (world == 1) {
     h->rank = 0;
     h->world = 1;
@@ -1490,12 +2008,16 @@ int fi_epp_comm_init(fi_epp* h, const uint8_t id_bytes[FI_EPP_UNIQUE_ID_BYTES], 
     return fail(h, FI_ERR_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
   }
   const uint64_t R = h->cfg.max_batch;
-  const uint32_t mask_words = (h->MP + 31) / 32;
   FI_CUDA(cudaMalloc(&h->d_local, R * h->P * sizeof(fi_pick)));
   FI_CUDA(cudaMalloc(&h->d_gather, (size_t)world * R * h->P * sizeof(fi_pick)));
-  FI_CUDA(cudaMalloc(&h->d_mask, R * mask_words * sizeof(uint32_t)));
-  FI_CUDA(cudaMalloc(&h->d_gmask, (size_t)world * R * mask_words * sizeof(uint32_t)));
-  FI_CUDA(cudaMalloc(&h->d_slots, R * h->MP * sizeof(uint32_t)));
+  // directory gossip (index_kernels.cu): this rank's transition log + gather buffers
+  FI_CUDA(cudaMalloc(&h->d_glog_n, 2 * sizeof(unsigned long long)));
+  FI_CUDA(cudaMemset(h->d_glog_n, 0, 2 * sizeof(unsigned long long)));
+  FI_CUDA(cudaMalloc(&h->d_glog_a, kOpChunk * sizeof(uint64_t)));
+  FI_CUDA(cudaMalloc(&h->d_glog_v, kOpChunk * sizeof(uint64_t)));
+  FI_CUDA(cudaMalloc(&h->d_ghdr, (size_t)(world + 1) * 2 * sizeof(unsigned long long)));
+  FI_CUDA(cudaMallocHost(&h->h_ghdr, (size_t)(world + 1) * 2 * sizeof(unsigned long long)));
+  FI_CUDA(cudaMalloc(&h->d_ggather, (size_t)world * kOpChunk * sizeof(uint64_t)));
   h->rank = rank;
   h->world = world;
   return setup_peer_exchange(h);

@@ -133,17 +133,24 @@ __global__ void __launch_bounds__(256) hash_blocks_any_kernel(const uint8_t* __r
 }
 
 // One lane per request, one warp per group of 32 requests: h_i = chain_step(pre_i, h_{i-1}), in
-// groups of 8 links.  Pre-states are prefetched kAhead groups ahead with cp.async into a
-// shared-memory ring: register prefetching does not work here — ptxas puts every ring load on
-// one scoreboard slot, and waiting on a (counting) scoreboard also waits for the loads just
-// issued for later groups, so the whole memory latency was exposed every group (measured:
-// 17 of 45 us).  cp.async commit/wait groups have exactly the needed "all but the N newest"
-// semantics.  The 8 hashes a lane produces per group are transposed through shared memory so the
-// chain rows (row-major [r][i]: what the match kernel stages and chains_out returns) are written
-// as full 64-byte segments.  Entries [n, MP) of every row are zeroed.
-constexpr int kRing = 4;       // ring slots
-constexpr int kAhead = 3;      // prefetch distance in groups (= kRing - 1)
-constexpr int kTilePitch = 5;  // 16-byte units per lane in the transpose tile (4 + 1 pad: conflict-free)
+// groups of 8 links.  The walk is a pure dependency chain — 40 integer instructions per link, 5 dependent
+// 64-bit multiplies, ~110 cycles by ptxas' own stall counts — run by ONE warp per scheduler, so every
+// other instruction in the loop and every exposed memory latency adds straight to the batch's critical
+// path (ncu, round 1: 59 instructions and 222 cycles per link).  Hence:
+//   * pre-states are prefetched kAhead groups ahead with cp.async into a shared-memory ring (register
+//     prefetching does not work: ptxas puts every ring load on one counting scoreboard, so waiting for the
+//     oldest also waits for the newest; cp.async commit/wait groups have the needed "all but the N newest"
+//     semantics), and the ring is read into registers one group EARLY, so neither the wait nor the
+//     shared-memory latency sits between two links;
+//   * each lane stores its 8 hashes straight to its chain row as four 16-byte stores (row-major [r][i]:
+//     what the match kernel stages and chains_out returns).  The 32 rows of a warp are 32 separate 64-byte
+//     segments; the stores are posted and L2 merges the half-sector pairs, which costs nothing on the chain —
+//     the round-1 version transposed through shared memory (2 barriers, 8 shared accesses and 4 predicated
+//     stores per group: a third of the kernel's instructions);
+//   * the buffers are padded to whole groups (MP % 8 == 0), so the loop has no per-unit predicates.
+// Entries [n, MP) of every row are zeroed.
+constexpr int kRing = 4;   // ring slots
+constexpr int kAhead = 3;  // prefetch distance in groups (= kRing - 1)
 
 __device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -154,10 +161,11 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void st_row16(ulonglong2* p, const ulonglong2& v) {
+  asm volatile("st.global.v2.u64 [%0], {%1, %2};\n" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
 
-// Four warps (128 requests) per CTA, one per SM sub-partition.  The kernel is bound by the serial
-// arithmetic: ncu shows 1 warp per scheduler, 3.7 cycles per issued instruction (1.9 of them
-// fixed-latency waits), ~50 instructions per link -> ~180 cycles per link, 28 us for 256 links.
+// Four warps (128 requests) per CTA, one per SM sub-partition.
 constexpr int kChainWarps = 4;
 
 __global__ void __launch_bounds__(kChainWarps * 32) chain_finalize_kernel(const uint64_t* __restrict__ pre,
@@ -165,87 +173,96 @@ __global__ void __launch_bounds__(kChainWarps * 32) chain_finalize_kernel(const 
                                                                           const uint64_t* __restrict__ h0, uint32_t R,
                                                                           uint32_t MP, uint64_t* __restrict__ chain) {
   __shared__ __align__(16) ulonglong2 s_ring[kChainWarps][kRing][4][32];
-  __shared__ __align__(16) ulonglong2 s_tile[kChainWarps][32 * kTilePitch];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t grp = blockIdx.x * kChainWarps + warp;
   if (grp * 32 >= R) return;  // whole warp out of range (no block-wide barriers below)
   ulonglong2(*ring)[4][32] = s_ring[warp];
-  ulonglong2* tile = s_tile[warp];
   const uint32_t r = grp * 32 + lane;
   const bool valid = r < R;
   const uint32_t n = valid ? nblocks[r] : 0;
   uint64_t h = valid ? h0[r] : 0;
-  const uint32_t MP2 = MP / 2;  // 16-byte units per row
+  const uint32_t MP2 = MP / 2;  // 16-byte units per row; MP % 8 == 0: whole groups of 4 units
   const ulonglong2* p = reinterpret_cast<const ulonglong2*>(pre) + ((uint64_t)grp * MP2) * 32 + lane;  // unit u at p[u*32]
-  const uint32_t ng_max = (MP2 + 3) / 4;  // every group of the row is written (zeros past n)
-  uint32_t ng_warp = (n + 7) / 8;         // groups that need arithmetic, warp-uniform maximum
+  ulonglong2* out = reinterpret_cast<ulonglong2*>(chain) + (uint64_t)(valid ? r : 0) * MP2;
+  const uint32_t ng_tot = MP2 / 4;
+  uint32_t ng_warp = (n + 7) / 8;           // groups that need arithmetic: warp-uniform maximum ...
+  uint32_t ng_full = valid ? n / 8 : 0;     // ... and the groups in which every lane has 8 blocks: minimum
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) ng_warp = max(ng_warp, __shfl_xor_sync(0xFFFFFFFFu, ng_warp, d));
+  for (int d = 16; d > 0; d >>= 1) {
+    ng_warp = max(ng_warp, __shfl_xor_sync(0xFFFFFFFFu, ng_warp, d));
+    ng_full = min(ng_full, __shfl_xor_sync(0xFFFFFFFFu, ng_full, d));
+  }
 
   auto issue = [&](uint32_t g) {  // one commit group per call, empty or not: keeps the count uniform
     if (g < ng_warp) {
-      const uint32_t slot = g % kRing;
+      ulonglong2* dst = &ring[g % kRing][0][lane];
+      const ulonglong2* src = p + (uint64_t)g * 128;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (g * 4 + k < MP2) cp_async16_cg(&ring[slot][k][lane], p + (uint64_t)(g * 4 + k) * 32);
+      for (int k = 0; k < 4; ++k) cp_async16_cg(dst + k * 32, src + k * 32);
     }
     cp_async_commit();
   };
 #pragma unroll
   for (int s = 0; s < kAhead; ++s) issue((uint32_t)s);
 
-  // store role of this lane in the transposed write-out: request (lane/4 + 8j), unit lane%4
-  const uint32_t sk = lane & 3, sq = lane >> 2;
+  ulonglong2 cur[4], nxt[4];
+  cp_async_wait<kAhead - 1>();  // group 0 has landed (a lane reads only its own copies: no barrier)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cur[k] = ring[0][k][lane];
+
+  uint32_t g = 0;
+  // ---- groups in which every lane of the warp has all 8 blocks: nothing but the links on the chain
 #pragma unroll 1
-  for (uint32_t g = 0; g < ng_max; ++g) {
-    ulonglong2 o[4];
-    if (g < ng_warp) {
-      issue(g + kAhead);        // refills the slot consumed in the previous iteration
-      cp_async_wait<kAhead>();  // group g has landed (this lane reads only its own copies)
-      const uint32_t slot = g % kRing;
-      ulonglong2 cur[4];
+  for (; g < ng_full; ++g) {
+    issue(g + kAhead);            // refills the slot whose registers were taken one iteration ago
+    cp_async_wait<kAhead - 1>();  // group g + 1 has landed; its registers are needed only next iteration
 #pragma unroll
-      for (int k = 0; k < 4; ++k) cur[k] = ring[slot][k][lane];
-      const uint32_t i0 = g * 8;
-      if (i0 + 8 <= n) {  // full group: nothing but the serial links on the dependency chain
+    for (int k = 0; k < 4; ++k) nxt[k] = ring[(g + 1) % kRing][k][lane];
+    ulonglong2* o = out + g * 4;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          h = chain_step(cur[k].x, h);
-          o[k].x = h;
-          h = chain_step(cur[k].y, h);
-          o[k].y = h;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t t = chain_step(cur[k].x, h);
-          const bool v0 = i0 + 2 * k < n;
-          h = v0 ? t : h;
-          o[k].x = v0 ? t : 0;
-          t = chain_step(cur[k].y, h);
-          const bool v1 = i0 + 2 * k + 1 < n;
-          h = v1 ? t : h;
-          o[k].y = v1 ? t : 0;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = make_ulonglong2(0, 0);
+    for (int k = 0; k < 4; ++k) {
+      ulonglong2 v;
+      h = chain_step(cur[k].x, h);
+      v.x = h;
+      h = chain_step(cur[k].y, h);
+      v.y = h;
+      if (valid) st_row16(o + k, v);
     }
-    // transpose: lane-major in, request-major out (4 lanes per request, 64 contiguous bytes)
-    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tile[lane * kTilePitch + k] = o[k];
-    __syncwarp();
+    for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+  }
+  // ---- ragged groups: some lane's chain ends inside
+#pragma unroll 1
+  for (; g < ng_warp; ++g) {
+    issue(g + kAhead);
+    cp_async_wait<kAhead - 1>();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t q = sq + 8 * j;  // request within the group
-      const uint32_t rr = grp * 32 + q;
-      const uint32_t u = g * 4 + sk;
-      if (rr < R && u < MP2) reinterpret_cast<ulonglong2*>(chain + (uint64_t)rr * MP)[u] = tile[q * kTilePitch + sk];
+    for (int k = 0; k < 4; ++k) nxt[k] = ring[(g + 1) % kRing][k][lane];
+    ulonglong2* o = out + g * 4;
+    const uint32_t i0 = g * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ulonglong2 v;
+      uint64_t t = chain_step(cur[k].x, h);
+      const bool v0 = i0 + 2 * k < n;
+      h = v0 ? t : h;
+      v.x = v0 ? t : 0;
+      t = chain_step(cur[k].y, h);
+      const bool v1 = i0 + 2 * k + 1 < n;
+      h = v1 ? t : h;
+      v.y = v1 ? t : 0;
+      if (valid) st_row16(o + k, v);
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
   }
   cp_async_wait<0>();
+  // ---- the rest of every row is zero
+  if (valid) {
+    const ulonglong2 z = make_ulonglong2(0, 0);
+    for (uint32_t u = g * 4; u < MP2; ++u) st_row16(out + u, z);
+  }
+  (void)ng_tot;
 }
 
 // Fully serial path for block sizes that are not a multiple of 32.

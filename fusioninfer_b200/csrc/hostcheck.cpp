@@ -7,6 +7,7 @@
 
 #include "bitslice.cuh"
 #include "lru.h"
+#include "tiebreak.cuh"
 #include "xxh64.cuh"
 
 extern "C" {
@@ -75,6 +76,23 @@ void fihc_bitcount_merge(const uint32_t* wa, uint32_t na, const uint32_t* wb, ui
   fi::bc_merge(a, b);
   for (uint32_t bit = 0; bit < 32; ++bit) counts[bit] = fi::bc_get(a, bit);
   *nonzero = fi::bc_nonzero(a);
+}
+
+// tie rotation (tiebreak.cuh): start of a request's rotation, rotated distance of an endpoint, and the first
+// member of a local tie set (bit words) in rotation order — the per-word arithmetic the match kernel uses
+uint32_t fihc_tie_start(uint32_t n_blocks, uint64_t first_hash, uint64_t h0, uint32_t r, uint32_t E) {
+  return fi::tie_start(fi::tie_seed(n_blocks, first_hash, h0, r), E);
+}
+uint32_t fihc_tie_rot(uint32_t e, uint32_t start, uint32_t E) { return fi::tie_rot(e, start, E); }
+uint32_t fihc_tie_first_local(const uint32_t* words, uint32_t W, uint32_t start, uint32_t ep_begin, uint32_t ep_count) {
+  const uint32_t p = fi::tie_local_origin(start, ep_begin, ep_count);
+  const uint32_t mask = W * 32u - 1u;
+  uint32_t best = 0xFFFFFFFFu;
+  for (uint32_t wi = 0; wi < W; ++wi) {
+    const uint32_t d = fi::tie_word_min(words[wi], wi, p, mask);
+    if (d < best) best = d;
+  }
+  return best == 0xFFFFFFFFu ? 0xFFFFFFFFu : ((best + p) & mask);
 }
 
 // LRU trace: for each key report (inserted, did_evict, evicted)

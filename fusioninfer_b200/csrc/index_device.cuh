@@ -2,8 +2,9 @@
 //
 // Two levels: the open-addressed TABLE (keys[slot], node_of[slot]; buckets of 4 keys = one 32-byte
 // sector, linear probing over buckets) maps a block hash to a NODE; nodes are numbered in insertion
-// order and own the data: klog[node] = the key, rows[node] = the membership bitset, cnt[node] = its
-// popcount.  Lookups return node ids.  Because a prompt's block hashes are inserted in chain order
+// order and own the data: klog[node] = the key, rows[node] = the membership bitset over the LOCAL endpoints,
+// cnt[node] = its popcount, rmask[node] = the ranks whose row of this key is non-empty (key present ⇔
+// rmask != 0; a single rank: rmask = (cnt > 0)).  Lookups return node ids.  Because a prompt's block hashes are inserted in chain order
 // (upstream PreRequest: indexer.Add(hashes, pod)), the nodes of a cached prefix are consecutive: the
 // match kernel verifies "node of block i+1 == node of block i + 1" with one coalesced read of klog
 // instead of hashing into the table for every block (index_kernels.cu, match_kernels.cu).
@@ -82,31 +83,18 @@ __device__ __forceinline__ uint32_t index_find_key(const IndexView& ix, uint64_t
   return index_resolve(ix, h, bucket_load(ix, h & ix.bmask));
 }
 
-// node of h if at least one local endpoint holds it, else SLOT_MISS
+// node of h if at least one endpoint of the pool holds it (rmask != 0 ⇔ the key is in the table), else SLOT_MISS
 __device__ __forceinline__ uint32_t index_find(const IndexView& ix, uint64_t h) {
   if (key_is_special(h)) {
     const uint64_t s = ix.C + (h == KEY_TOMB ? 1 : 0);
-    return ix.cnt[s] ? (uint32_t)s : SLOT_MISS;
+    return ix.rmask[s] ? (uint32_t)s : SLOT_MISS;
   }
   return index_resolve(ix, h, bucket_load(ix, h & ix.bmask));
 }
 
-// Presence filter (kernels.cuh IndexView::filt): a clear bit proves that the regular key h was never
-// claimed since the last rebuild.  The filter is small enough to stay L2-resident (C bytes), so a pass that
-// mostly probes absent blocks pays an L2 hit instead of a DRAM transaction for them.
-__device__ __forceinline__ uint64_t filter_bit(const IndexView& ix, uint64_t h) { return h >> (64 - ix.log2F); }
-__device__ __forceinline__ void filter_set(const IndexView& ix, uint64_t h) {
-  const uint64_t b = filter_bit(ix, h);
-  atomicOr(ix.filt + (b >> 5), 1u << (b & 31));
-}
-__device__ __forceinline__ const uint32_t* filter_word(const IndexView& ix, uint64_t h) { return ix.filt + (filter_bit(ix, h) >> 5); }
-__device__ __forceinline__ bool filter_test(const IndexView& ix, uint64_t h, uint32_t word) {
-  return (word >> (filter_bit(ix, h) & 31)) & 1u;
-}
-
-// Bulk variant for passes that probe many blocks most of which are absent (the sharded mode looks every
-// block up on every rank): keys only, the node is fetched with a second, dependent read on a hit — a miss
-// costs one DRAM transaction instead of two.
+// Keys-only variant for the fallback where every lane of a chunk probes the table (a prefix whose nodes are
+// scattered): the node is fetched with a second, dependent read on a hit — a miss costs one DRAM transaction
+// instead of two.
 __device__ __forceinline__ BucketRegs bucket_load_keys(const IndexView& ix, uint64_t b) {
   const uint4* p = reinterpret_cast<const uint4*>(ix.keys + b * BUCKET_KEYS);
   BucketRegs r;
@@ -118,7 +106,7 @@ __device__ __forceinline__ BucketRegs bucket_load_keys(const IndexView& ix, uint
 __device__ __forceinline__ uint32_t index_find_lazy(const IndexView& ix, uint64_t h) {
   if (key_is_special(h)) {
     const uint64_t s = ix.C + (h == KEY_TOMB ? 1 : 0);
-    return ix.cnt[s] ? (uint32_t)s : SLOT_MISS;
+    return ix.rmask[s] ? (uint32_t)s : SLOT_MISS;
   }
   uint64_t b = h & ix.bmask;
   for (uint64_t it = 0; it <= ix.bmask; ++it) {
@@ -130,9 +118,6 @@ __device__ __forceinline__ uint32_t index_find_lazy(const IndexView& ix, uint64_
   }
   return SLOT_MISS;
 }
-
-// out-of-line index_find for the rare paths of callers that keep several lookups in flight
-static __device__ __noinline__ uint32_t index_find_slow(const IndexView ix, uint64_t h) { return index_find_lazy(ix, h); }
 
 // Speculation: is `cand` the node of the regular key h?  (klog of a free or retired node is 0, and a
 // regular key is never 0.)

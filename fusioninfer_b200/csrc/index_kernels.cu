@@ -8,10 +8,17 @@
 // Inserts claim an EMPTY key with atomicCAS and give it the next NODE: nodes are
 // numbered in insertion order and own the key's row (index_device.cuh), so a chain
 // inserted in order occupies consecutive rows.  Membership bits flip with
-// atomicOr/atomicAnd, cnt tracks the row popcount so that "key present ⇔ row
-// non-empty" holds: a key whose row empties becomes a tombstone and its node is
-// retired (neither is reused until a rebuild compacts the live nodes in order),
-// which keeps lookups exact without reading the row.
+// atomicOr/atomicAnd, cnt tracks the row popcount.
+//
+// Key presence is rmask[node] != 0: bit g says "rank g's row of this key is non-empty".
+// With one rank that is just cnt > 0.  With an endpoint-range sharded pool every rank's
+// table is a directory of the WHOLE pool's keys (rows only for its own endpoints): the
+// owner of an endpoint applies the SET / CLEAR exactly (the row bit makes it idempotent)
+// and logs the transitions of its row, empty -> non-empty (APPEAR) and back (VANISH); the
+// other ranks replay those into their rmask (index_remote_*).  A key nobody holds any more
+// becomes a tombstone and its node is retired (neither is reused until a rebuild compacts
+// the live nodes in order), which keeps lookups exact without reading the row — and lets
+// every rank find upstream's stopping point, the first block NO pod holds, on its own.
 #include "index_device.cuh"
 #include "kernels.cuh"
 
@@ -34,7 +41,6 @@ __device__ uint32_t table_find_or_claim(const IndexView& ix, IndexCounters* ctr,
         unsigned long long old = atomicCAS(kb + j, (unsigned long long)KEY_EMPTY, (unsigned long long)h);
         if (old == KEY_EMPTY) {
           *claimed = true;
-          filter_set(ix, h);
           return (uint32_t)(b * BUCKET_KEYS + j);
         }
         if (old == h) return (uint32_t)(b * BUCKET_KEYS + j);
@@ -47,14 +53,15 @@ __device__ uint32_t table_find_or_claim(const IndexView& ix, IndexCounters* ctr,
   return SLOT_MISS;
 }
 
-// Node allocation of one CTA pass: the threads that claimed a new key get CONSECUTIVE nodes in thread
-// (= op) order — one atomicAdd per CTA — so the keys of a chain that arrives as consecutive ops sit
-// next to each other in klog / rows.  Returns the node of a claiming thread (NODE_INVALID on overflow).
-__device__ uint32_t alloc_nodes_cta(const IndexView& ix, IndexCounters* ctr, bool claimed) {
+// Ordered reservation of one CTA pass: the flagged threads get CONSECUTIVE positions of *counter in
+// thread (= op) order — one atomicAdd per CTA.  Used for the node numbers of new keys (the keys of a chain
+// that arrives as consecutive ops end up next to each other in klog / rows) and for the APPEAR log (so that
+// the ranks replaying it allocate consecutive nodes too).  Every thread of the CTA must call it.
+__device__ unsigned long long cta_reserve(bool flag, unsigned long long* counter) {
   __shared__ uint32_t s_warp[8];
   __shared__ unsigned long long s_base;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned m = __ballot_sync(0xFFFFFFFFu, claimed);
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, flag);
   const uint32_t rank_in_warp = __popc(m & ((1u << lane) - 1u));
   if (lane == 0) s_warp[warp] = __popc(m);
   __syncthreads();
@@ -65,17 +72,12 @@ __device__ uint32_t alloc_nodes_cta(const IndexView& ix, IndexCounters* ctr, boo
       s_warp[w] = tot;
       tot += c;
     }
-    s_base = tot ? atomicAdd(&ctr->used, (unsigned long long)tot) : 0ull;
+    s_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
   }
   __syncthreads();
-  uint32_t node = NODE_INVALID;
-  if (claimed) {
-    const unsigned long long n = s_base + s_warp[warp] + rank_in_warp;
-    if (n < ix.C) node = (uint32_t)n;
-    else atomicExch(&ctr->overflow, 1ull);
-  }
-  __syncthreads();  // s_warp / s_base are reused by the next pass
-  return node;
+  const unsigned long long pos = flag ? s_base + s_warp[warp] + rank_in_warp : ~0ull;
+  __syncthreads();  // s_warp / s_base are reused by the next reservation
+  return pos;
 }
 
 // node of a slot some other thread claimed: wait until that thread has published it
@@ -86,46 +88,74 @@ __device__ __forceinline__ uint32_t wait_node(const IndexView& ix, uint32_t slot
   return n;
 }
 
-__global__ void __launch_bounds__(256) index_set_kernel(IndexView ix, IndexCounters* ctr,
-                                                        const fi_index_op* __restrict__ ops, uint64_t n,
-                                                        uint32_t ep_begin, uint32_t ep_count) {
+// REMOTE = false: this rank's own SET ops (row bit, popcount, APPEAR log).
+// REMOTE = true:  replay of rank `rank`'s APPEAR log: directory entry only (rmask bit of that rank).
+template <bool REMOTE>
+__global__ void __launch_bounds__(256) index_set_kernel(IndexView ix, IndexCounters* ctr, const fi_index_op* __restrict__ ops,
+                                                        const uint64_t* __restrict__ hashes, uint64_t n, uint32_t ep_begin,
+                                                        uint32_t ep_count, uint32_t rank, GossipLog log) {
+  const uint32_t rbit = 1u << rank;
+  const uint32_t zero_node = (uint32_t)(ix.C + 2);
   // every thread of a CTA runs the same number of passes (block-wide barriers inside)
   for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t i = base + threadIdx.x;
-    fi_index_op op{};
+    uint64_t hsh = 0;
     bool active = false;
     uint32_t e = 0;
     if (i < n) {
-      op = ops[i];
-      e = op.endpoint - ep_begin;
-      active = op.op == FI_OP_SET && e < ep_count;
+      if (REMOTE) {
+        hsh = hashes[i];
+        active = true;
+      } else {
+        const fi_index_op op = ops[i];
+        hsh = op.hash;
+        e = op.endpoint - ep_begin;
+        active = op.op == FI_OP_SET && e < ep_count;
+      }
     }
     // 1. table slot (claim an empty one for a new key)
     bool claimed = false;
     uint32_t slot = SLOT_MISS, node = NODE_INVALID;
     if (active) {
-      if (key_is_special(op.hash)) node = (uint32_t)(ix.C + (op.hash == KEY_TOMB ? 1 : 0));
-      else slot = table_find_or_claim(ix, ctr, op.hash, &claimed);
+      if (key_is_special(hsh)) node = (uint32_t)(ix.C + (hsh == KEY_TOMB ? 1 : 0));
+      else slot = table_find_or_claim(ix, ctr, hsh, &claimed);
     }
     // 2. new keys get consecutive nodes in op order and publish them
-    const uint32_t mine = alloc_nodes_cta(ix, ctr, claimed);
+    const unsigned long long mine = cta_reserve(claimed, &ctr->used);
     if (claimed) {
-      if (mine != NODE_INVALID) {
-        node = mine;
-        ix.klog[node] = op.hash;
+      if (mine < ix.C) {
+        node = (uint32_t)mine;
+        ix.klog[node] = hsh;
         __threadfence();
         *reinterpret_cast<volatile uint32_t*>(ix.node_of + slot) = node;
-      } else {  // out of nodes (reported through ctr->overflow): park the key on the zero row
-        *reinterpret_cast<volatile uint32_t*>(ix.node_of + slot) = (uint32_t)(ix.C + 2);
+      } else {
+        // out of nodes (reported through ctr->overflow): retire the slot again so that "key in the table ⇔
+        // some rank holds it" keeps holding, and release the threads waiting for its node
+        atomicExch(&ctr->overflow, 1ull);
+        ix.keys[slot] = KEY_TOMB;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(ix.node_of + slot) = zero_node;
       }
     }
     // 3. keys that were already there (possibly claimed by another CTA a moment ago): their node.  No
     // thread waits before it has published its own nodes, so the waits cannot form a cycle.
     if (active && !claimed && slot != SLOT_MISS) node = wait_node(ix, slot);
-    if (active && node != NODE_INVALID && node != (uint32_t)(ix.C + 2)) {
-      const uint32_t bit = 1u << (e & 31);
-      const uint32_t old = atomicOr(ix.rows + ((uint64_t)node << ix.logW) + (e >> 5), bit);
-      if (!(old & bit)) atomicAdd(ix.cnt + node, 1u);
+    bool appear = false;
+    if (active && node != NODE_INVALID && node != zero_node) {
+      if (REMOTE) {
+        atomicOr(ix.rmask + node, rbit);
+      } else {
+        const uint32_t bit = 1u << (e & 31);
+        const uint32_t old = atomicOr(ix.rows + ((uint64_t)node << ix.logW) + (e >> 5), bit);
+        if (!(old & bit) && atomicAdd(ix.cnt + node, 1u) == 0u) {  // this rank's row: empty -> non-empty
+          atomicOr(ix.rmask + node, rbit);
+          appear = true;
+        }
+      }
+    }
+    if (!REMOTE && log.n_appear) {  // warp-uniform: sharded pools only
+      const unsigned long long pos = cta_reserve(appear, log.n_appear);
+      if (appear && pos < log.cap) log.appear[pos] = hsh;
     }
   }
 }
@@ -143,29 +173,54 @@ __device__ uint32_t table_find_slot(const IndexView& ix, uint64_t h) {
   return SLOT_MISS;
 }
 
-__global__ void __launch_bounds__(256) index_clear_kernel(IndexView ix, IndexCounters* ctr,
-                                                          const fi_index_op* __restrict__ ops, uint64_t n,
-                                                          uint32_t ep_begin, uint32_t ep_count) {
+// rank `rbit`'s row of the key at (slot, node) has emptied: drop its directory bit; if no rank holds the key
+// any more retire the key and its node
+__device__ __forceinline__ void rank_vanished(const IndexView& ix, IndexCounters* ctr, uint32_t slot, uint32_t node,
+                                              uint32_t rbit) {
+  const uint32_t oldm = atomicAnd(ix.rmask + node, ~rbit);
+  if ((oldm & rbit) && (oldm & ~rbit) == 0u && slot != SLOT_MISS) {
+    ix.keys[slot] = KEY_TOMB;
+    ix.klog[node] = 0;
+    atomicAdd(&ctr->tombstones, 1ull);
+  }
+}
+
+template <bool REMOTE>
+__global__ void __launch_bounds__(256) index_clear_kernel(IndexView ix, IndexCounters* ctr, const fi_index_op* __restrict__ ops,
+                                                          const uint64_t* __restrict__ hashes, uint64_t n, uint32_t ep_begin,
+                                                          uint32_t ep_count, uint32_t rank, GossipLog log) {
+  const uint32_t rbit = 1u << rank;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const fi_index_op op = ops[i];
-    const uint32_t e = op.endpoint - ep_begin;
-    if (op.op != FI_OP_CLEAR || e >= ep_count) continue;
-    uint32_t slot = SLOT_MISS, node;
-    if (key_is_special(op.hash)) {
-      node = (uint32_t)(ix.C + (op.hash == KEY_TOMB ? 1 : 0));
+    uint64_t hsh;
+    uint32_t e = 0;
+    if (REMOTE) {
+      hsh = hashes[i];
     } else {
-      slot = table_find_slot(ix, op.hash);
+      const fi_index_op op = ops[i];
+      e = op.endpoint - ep_begin;
+      if (op.op != FI_OP_CLEAR || e >= ep_count) continue;
+      hsh = op.hash;
+    }
+    uint32_t slot = SLOT_MISS, node;
+    if (key_is_special(hsh)) {
+      node = (uint32_t)(ix.C + (hsh == KEY_TOMB ? 1 : 0));
+    } else {
+      slot = table_find_slot(ix, hsh);
       if (slot == SLOT_MISS) continue;
       node = ix.node_of[slot];
+      if (node >= ix.C) continue;  // a slot parked by a node overflow
+    }
+    if (REMOTE) {
+      rank_vanished(ix, ctr, slot, node, rbit);
+      continue;
     }
     const uint32_t bit = 1u << (e & 31);
     const uint32_t old = atomicAnd(ix.rows + ((uint64_t)node << ix.logW) + (e >> 5), ~bit);
-    if (old & bit) {
-      const uint32_t c = atomicSub(ix.cnt + node, 1u);
-      if (c == 1u && slot != SLOT_MISS) {  // row emptied: retire the key and its node
-        ix.keys[slot] = KEY_TOMB;
-        ix.klog[node] = 0;
-        atomicAdd(&ctr->tombstones, 1ull);
+    if ((old & bit) && atomicSub(ix.cnt + node, 1u) == 1u) {  // this rank's row emptied
+      rank_vanished(ix, ctr, slot, node, rbit);
+      if (log.n_vanish) {
+        const unsigned long long pos = atomicAdd(log.n_vanish, 1ull);
+        if (pos < log.cap) log.vanish[pos] = hsh;
       }
     }
   }
@@ -181,21 +236,23 @@ __global__ void __launch_bounds__(256) index_rebuild_kernel(IndexView from, Inde
     bool claimed = false;
     uint32_t slot = SLOT_MISS;
     if (h != 0) slot = table_find_or_claim(to, ctr, h, &claimed);  // keys are unique: always a fresh claim
-    const uint32_t d = alloc_nodes_cta(to, ctr, claimed);
-    if (claimed && d != NODE_INVALID) {
+    const unsigned long long d = cta_reserve(claimed, &ctr->used);
+    if (claimed && d < to.C) {
       to.klog[d] = h;
-      to.node_of[slot] = d;
+      to.node_of[slot] = (uint32_t)d;
       to.cnt[d] = from.cnt[s];
+      to.rmask[d] = from.rmask[s];
       const uint32_t* src = from.rows + (s << from.logW);
-      uint32_t* dst = to.rows + ((uint64_t)d << to.logW);
+      uint32_t* dst = to.rows + (d << to.logW);
       for (uint32_t w = 0; w < from.W; ++w) dst[w] = src[w];
     }
   }
   // the two special nodes keep their place
   if (blockIdx.x == 0 && threadIdx.x < 2) {
     const uint64_t s = from.C + threadIdx.x;
-    if (from.cnt[s]) {
+    if (from.rmask[s]) {
       to.cnt[s] = from.cnt[s];
+      to.rmask[s] = from.rmask[s];
       for (uint32_t w = 0; w < from.W; ++w) to.rows[(s << to.logW) + w] = from.rows[(s << from.logW) + w];
     }
   }
@@ -226,16 +283,30 @@ inline unsigned grid_for(uint64_t n) {
 }  // namespace
 
 cudaError_t launch_index_set(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n, uint32_t ep_begin,
-                             uint32_t ep_count, cudaStream_t s) {
+                             uint32_t ep_count, uint32_t rank, GossipLog log, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  index_set_kernel<<<grid_for(n), 256, 0, s>>>(ix, ctr, ops, n, ep_begin, ep_count);
+  index_set_kernel<false><<<grid_for(n), 256, 0, s>>>(ix, ctr, ops, nullptr, n, ep_begin, ep_count, rank, log);
   return cudaGetLastError();
 }
 
 cudaError_t launch_index_clear(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n,
-                               uint32_t ep_begin, uint32_t ep_count, cudaStream_t s) {
+                               uint32_t ep_begin, uint32_t ep_count, uint32_t rank, GossipLog log, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  index_clear_kernel<<<grid_for(n), 256, 0, s>>>(ix, ctr, ops, n, ep_begin, ep_count);
+  index_clear_kernel<false><<<grid_for(n), 256, 0, s>>>(ix, ctr, ops, nullptr, n, ep_begin, ep_count, rank, log);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_index_remote_appear(IndexView ix, IndexCounters* ctr, const uint64_t* hashes, uint64_t n, uint32_t rank,
+                                       cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  index_set_kernel<true><<<grid_for(n), 256, 0, s>>>(ix, ctr, nullptr, hashes, n, 0, 0, rank, GossipLog{});
+  return cudaGetLastError();
+}
+
+cudaError_t launch_index_remote_vanish(IndexView ix, IndexCounters* ctr, const uint64_t* hashes, uint64_t n, uint32_t rank,
+                                       cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  index_clear_kernel<true><<<grid_for(n), 256, 0, s>>>(ix, ctr, nullptr, hashes, n, 0, 0, rank, GossipLog{});
   return cudaGetLastError();
 }
 

@@ -11,9 +11,12 @@
 //                             nodes C, C+1 belong to the hashes 0 and ~0, node C+2 is a never-written row
 //             rows    [C+3][W] u32, row n = membership bitset of node n over the local endpoints
 //                             (bit e%32 of word e/32)
-//             cnt     [C+3]   u32 popcount of the row (key present ⇔ cnt > 0)
-//             filt    [C/4]   u32 presence filter, 8 bits per slot: bit (hash >> (64 - log2F)) is set when a key
-//                             is claimed; a clear bit proves absence (bulk probing of mostly-absent blocks)
+//             cnt     [C+3]   u32 popcount of the row (this rank's endpoints holding the block)
+//             rmask   [C+3]   u32 bit g set ⇔ rank g's row of this key is non-empty; key present ⇔ rmask != 0.
+//                             One rank: rmask = (cnt > 0).  Endpoint-range shards: every rank's table is a
+//                             DIRECTORY of the whole pool's keys (rows only for its own endpoints), kept exact by
+//                             gossiping the owners' APPEAR / VANISH transitions (index_kernels.cu), so the first
+//                             block NO endpoint holds — upstream's stopping point — is found locally.
 //   picks     [R][P]        fi_pick
 #pragma once
 #include <cuda_runtime.h>
@@ -34,9 +37,8 @@ struct IndexView {
   uint64_t* klog;
   uint32_t* rows;
   uint32_t* cnt;
-  uint32_t* filt;  // presence filter: one bit per 1/8 slot, set when a key is claimed (never cleared until a rebuild)
-  uint32_t log2F;  // filter bits = 1 << log2F = 8 * C
-  uint64_t bmask;  // buckets - 1
+  uint32_t* rmask;  // per node: ranks whose local row is non-empty (bit = rank); key present ⇔ rmask != 0
+  uint64_t bmask;   // buckets - 1
   uint64_t C;      // regular slots = buckets * BUCKET_KEYS
   uint32_t W;      // words per row (power of two)
   uint32_t logW;
@@ -45,9 +47,20 @@ struct IndexView {
 // device-side counters of the index (one cache line)
 struct IndexCounters {
   unsigned long long used;        // slots claimed = nodes allocated (keys + tombstones)
-  unsigned long long tombstones;  // keys retired because their row emptied
+  unsigned long long tombstones;  // keys retired because no rank holds them any more
   unsigned long long overflow;    // != 0: an insert found no free slot
   unsigned long long pad;
+};
+
+// Transition log of one gossip round (sharded pools): the hashes whose LOCAL row went empty -> non-empty
+// (appear) or non-empty -> empty (vanish) while this rank applied its own SET / CLEAR ops.  The other ranks
+// replay them into their directories (rmask bit of this rank).
+struct GossipLog {
+  unsigned long long* n_appear;  // device counters (null: single rank, nothing is logged)
+  unsigned long long* n_vanish;
+  uint64_t* appear;              // [cap]
+  uint64_t* vanish;              // [cap]
+  uint64_t cap;
 };
 
 struct ProfileDev {
@@ -57,10 +70,11 @@ struct ProfileDev {
   double weight[FI_EPP_MAX_SCORERS];
 };
 
-// best endpoint of a profile when no prefix block matches (per batch constant)
+// best total of a profile when no prefix block matches (per batch constant); the endpoints that attain it
+// are the bit words ScoreTables::ztie — which of them wins depends on the request's tie rotation
 struct ZeroBest {
   double score;
-  uint32_t e_local;  // FI_NO_ENDPOINT if no eligible local endpoint
+  uint32_t any;  // 0: no eligible local endpoint
   uint32_t pad;
 };
 
@@ -85,6 +99,7 @@ struct ScoreTables {
   const double* sc;     // [P][S][Epad] clamp01'd per-endpoint scores of the non-prefix scorers
   const uint32_t* elig; // [P][W] eligibility bit words
   const ZeroBest* zero; // [P]
+  const uint32_t* ztie; // [P][W] eligible local endpoints whose zero-match total equals zero[p].score
   const LoraDev* lora;  // [Epad] or null
   uint32_t has_lora;    // some profile has a lora-affinity-scorer: scores depend on the request's adapter,
   uint32_t pad;         // so every eligible endpoint is scored per request (no zero-match shortcut)
@@ -93,11 +108,10 @@ struct ScoreTables {
 // Peer-memory exchange of the endpoint-range sharded mode (one buffer per rank, every rank's buffer
 // mapped into every process over NVLink / CUDA IPC).  Low-latency protocol: every 32-bit datum travels
 // in one aligned 64-bit store together with a 32-bit tag = the step number of the pick call, so a word is
-// valid exactly when its tag matches — no fences, no flags, no barrier between the ranks.  Producers
-// (probe_slots_kernel: presence masks; match_pick_kernel: local picks) store each word into slot
-// [parity][own rank] of EVERY rank's buffer as soon as it exists; consumers (match_pick_kernel,
-// merge_picks_kernel) poll only the words of the request they are about to process, so the transfer of
-// later requests overlaps the work on earlier ones.  Parity double-buffers consecutive steps (a rank can
+// valid exactly when its tag matches — no fences, no flags, no barrier between the ranks.  The producer
+// (match_pick_kernel: this rank's local pick) stores each word into slot [parity][own rank] of EVERY rank's
+// buffer as soon as it exists; the consumer (merge_picks_kernel) polls only the words of the request it is
+// about to reduce, so the transfer of later requests overlaps the work on earlier ones.  Parity double-buffers consecutive steps (a rank can
 // be at most one step ahead of a peer, because its merge needs that peer's picks of the previous step).
 constexpr int FI_MAX_RANKS = 16;
 struct PeerXchg {
@@ -105,7 +119,6 @@ struct PeerXchg {
   uint32_t step;                // tag of this pick call (monotonic, starts at 1; buffers start zeroed)
   uint32_t enabled;             // 0: the NCCL all-gather path is used instead
   uint8_t* base[FI_MAX_RANKS];  // base[k] = rank k's exchange buffer as mapped here (base[rank] is local)
-  uint64_t off_mask[2];         // u64 {tag:mask word}  [world][R][mask_words]   (R = the call's batch)
   uint64_t off_pick[2];         // u64 {tag:word}       [world][R][P][4]  endpoint, match_blocks, score lo, hi
   uint32_t* err;                // local: set to 1 if a poll timed out
 };
@@ -120,19 +133,19 @@ struct MatchParams {
   IndexView ix;
   ScoreTables st;
   uint32_t ep_begin;
+  uint32_t ep_count;
+  uint32_t E_global;  // pool size: ties rotate over the whole pool (tie_start)
+  uint32_t r_base;    // index of this launch's request 0 within the caller's batch (sliced host feed)
+  const uint64_t* h0; // [R] chain seeds (tie rotation of prompts shorter than one block)
   uint32_t lpm;  // fi_match_mode
   // pd-profile-handler
   uint32_t apply_pd, pd_decode, pd_prefill;
   double pd_threshold;
-  // sharded exact-upstream mode: presence masks of all ranks [ranks][R][mask_words]
-  const uint32_t* gmask;
-  uint32_t gmask_ranks;
-  uint32_t mask_words;
-  uint32_t* slots;                    // [R][MP] index node of every block (probe_slots_kernel -> match GMASK)
   fi_pick* out;                       // [R][P]
   unsigned long long* probed_blocks;  // optional Σ N_probe
   uint32_t* work_counter;             // dynamic request queue of the launch
   uint32_t zero_work_counter;         // launcher zeroes it first (0: the caller already did)
+  uint32_t lane_zero;                 // always 0: makes the ticket address formally lane-dependent (match_kernels.cu take_ticket)
   PeerXchg px;                        // sharded mode, peer-memory exchange (px.enabled)
 };
 
@@ -141,6 +154,9 @@ struct MergeParams {
   uint32_t ranks, R, P;
   const uint32_t* nblocks;
   const uint64_t* offsets;
+  const uint64_t* chain;  // [R][MP]  (tie rotation: first block hash)
+  const uint64_t* h0;     // [R]
+  uint32_t MP, E_global;
   uint32_t apply_pd, pd_decode, pd_prefill;
   double pd_threshold;
   fi_pick* out;  // [R][P]
@@ -157,19 +173,23 @@ cudaError_t launch_hash_generic(const uint8_t* prompts, const uint64_t* offsets,
                                 uint32_t* nblocks, cudaStream_t s);
 
 cudaError_t launch_index_set(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n,
-                             uint32_t ep_begin, uint32_t ep_count, cudaStream_t s);
+                             uint32_t ep_begin, uint32_t ep_count, uint32_t rank, GossipLog log, cudaStream_t s);
 cudaError_t launch_index_clear(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n,
-                               uint32_t ep_begin, uint32_t ep_count, cudaStream_t s);
+                               uint32_t ep_begin, uint32_t ep_count, uint32_t rank, GossipLog log, cudaStream_t s);
+// replay another rank's transitions into this rank's directory (n hashes; bit = that rank)
+cudaError_t launch_index_remote_appear(IndexView ix, IndexCounters* ctr, const uint64_t* hashes, uint64_t n,
+                                       uint32_t rank, cudaStream_t s);
+cudaError_t launch_index_remote_vanish(IndexView ix, IndexCounters* ctr, const uint64_t* hashes, uint64_t n,
+                                       uint32_t rank, cudaStream_t s);
 cudaError_t launch_index_rebuild(IndexView from, IndexView to, IndexCounters* ctr, cudaStream_t s);
 cudaError_t launch_index_contains(IndexView ix, const fi_index_op* q, uint64_t n, uint32_t ep_begin,
                                   uint32_t ep_count, uint8_t* out, cudaStream_t s);
 
 cudaError_t launch_prepare_endpoints(const EndpointDev* eps, uint32_t E_global, uint32_t ep_begin,
                                      uint32_t ep_count, ScoreTables st, double* sc, uint32_t* elig,
-                                     ZeroBest* zero, cudaStream_t s);
+                                     ZeroBest* zero, uint32_t* ztie, cudaStream_t s);
 
 cudaError_t launch_match_pick(const MatchParams& p, int sm_count, cudaStream_t s);
-cudaError_t launch_probe_slots(const MatchParams& p, uint32_t* mask_out, int sm_count, cudaStream_t s);
 cudaError_t launch_merge_picks(const MergeParams& p, cudaStream_t s);
 
 }  // namespace fi

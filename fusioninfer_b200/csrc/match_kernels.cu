@@ -19,19 +19,25 @@
 //      share the per-batch "zero-match best" precomputed by prepare_endpoints —
 //      valid because every scorer weight is >= 0, so a total is monotone in the
 //      match count;
-//   5. warp-shuffle argmax, ties to the lowest endpoint index (Appendix A.5), then
-//      the pd-profile-handler threshold rule (Appendix A.6,
+//   5. warp-shuffle argmax; equal totals are resolved by the request's tie rotation (tiebreak.cuh — upstream's
+//      MaxScorePicker shuffles, Appendix A.5), then the pd-profile-handler threshold rule (Appendix A.6,
 //      /root/reference/pkg/router/strategy.go:129-133).
 //
 // Rows narrower than 32 words (fewer than 1024 local endpoints, e.g. an
 // endpoint-range shard of a multi-GPU pool) are read G = 32/L rows per load
 // instruction by G lane groups whose counters are merged at the end.
+//
+// Sharded pools run the SAME kernel: every rank's table is a directory of the whole pool's keys
+// (index_kernels.cu), so "the first block no pod holds" is a local lookup; the only exchange of the step is
+// the rank's (score, endpoint) pick, stored straight into every rank's memory (PeerXchg) and reduced by
+// merge_picks_kernel.
 #include <climits>
 #include <cstdlib>
 
 #include "bitslice.cuh"
 #include "index_device.cuh"
 #include "kernels.cuh"
+#include "tiebreak.cuh"
 
 namespace fi {
 
@@ -47,10 +53,30 @@ struct Best {
   double score;
   uint32_t e;  // local endpoint or FI_NO_ENDPOINT
   uint32_t m;
+  uint32_t k;  // tie key of e: its distance from the request's rotation start (smaller wins among equal totals)
 };
 
-__device__ __forceinline__ bool better(double s, uint32_t e, const Best& b) {
-  return s > b.score || (s == b.score && e < b.e);
+// the request's tie rotation (tiebreak.cuh), in this rank's local endpoint numbering
+struct TieRot {
+  uint32_t start;     // global rotation start in [0, E)
+  uint32_t E;         // pool size
+  uint32_t ep_begin;  // first global endpoint of this rank
+  __device__ __forceinline__ uint32_t key(uint32_t e_local) const { return tie_rot(e_local + ep_begin, start, E); }
+};
+
+__device__ __forceinline__ bool better(double s, uint32_t k, const Best& b) { return s > b.score || (s == b.score && k < b.k); }
+
+// First member, in rotation order, of a set of LOCAL endpoints given as W bit words (warp-cooperative; every
+// lane gets the result; FI_NO_ENDPOINT if the set is empty); the word arithmetic is tiebreak.cuh's.
+__device__ __forceinline__ uint32_t tie_first_local(const uint32_t* __restrict__ T, uint32_t W, const TieRot& tr,
+                                                    uint32_t ep_count, int lane) {
+  const uint32_t p = tie_local_origin(tr.start, tr.ep_begin, ep_count);
+  const uint32_t mask = W * 32u - 1u;  // W is a power of two
+  uint32_t best = 0xFFFFFFFFu;         // smallest (position - p) mod (32 W)
+  for (uint32_t wi = lane; wi < W; wi += 32) best = min(best, tie_word_min(__ldg(T + wi), wi, p, mask));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, d));
+  return best == 0xFFFFFFFFu ? FI_NO_ENDPOINT : ((best + p) & mask);
 }
 
 // SURVEY.md Appendix A.4 — identical operation order to oracle/epp_oracle.cpp:total_score
@@ -92,9 +118,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-// fire-and-forget: pull a line into L2, no destination register, no scoreboard wait
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
-
 // ---- peer-memory exchange (sharded mode): tagged 64-bit words, see PeerXchg in kernels.cuh ------
 __device__ __forceinline__ void ll_store(uint64_t* p, uint32_t data, uint32_t tag) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(((uint64_t)tag << 32) | data) : "memory");
@@ -105,23 +128,6 @@ __device__ __forceinline__ uint64_t ll_load(const uint64_t* p) {
   return v;
 }
 constexpr long long kPollTimeoutCycles = 20000000000ll;  // ~10 s: a peer died or never launched
-// poll one tagged word until it belongs to this step
-__device__ __forceinline__ uint32_t ll_wait(const uint64_t* p, uint32_t tag, uint32_t* err) {
-  uint64_t v = ll_load(p);
-  if ((uint32_t)(v >> 32) != tag) {
-    const long long t0 = clock64();
-    do {
-      __nanosleep(64);
-      v = ll_load(p);
-      if (clock64() - t0 > kPollTimeoutCycles) {
-        *err = 1;
-        break;
-      }
-    } while ((uint32_t)(v >> 32) != tag);
-  }
-  return (uint32_t)v;
-}
-
 // PD rule shared by the single-GPU kernel and the multi-GPU merge kernel
 __device__ __forceinline__ bool pd_prefill_runs(uint32_t dec_endpoint, uint32_t dec_match, uint32_t n, uint64_t len,
                                                 double threshold) {
@@ -189,10 +195,20 @@ __device__ __forceinline__ uint32_t resolve_chunk_nodes(const IndexView& ix, uin
   return node;
 }
 
+// next request of the launch's dynamic queue.  Plain PTX on purpose: for `if (lane == 0) atomicAdd(..)` the
+// compiler emits its warp-aggregated form — ATOMG followed at once by a SHFL of the result — which makes every
+// request wait out the atomic's round trip (15 % of the kernel's stall samples in round 1).  Here the result
+// register is not touched until the shuffle at the end of the request.
+__device__ __forceinline__ uint32_t take_ticket(uint32_t* counter, uint32_t opaque_zero) {
+  uint32_t t;
+  asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(t) : "l"(counter + opaque_zero) : "memory");
+  return t;
+}
+
 // LPR lanes read one row (VEC words each, LPR*VEC = words per row); a load
-// instruction therefore covers G = 32/LPR rows.  E = 1024 → LPR 8, VEC 4: a 128-byte
-// row is 8 × 16-byte loads and one instruction brings in 4 rows; 32 rows in flight.
-template <int LPR, int VEC, bool LPM, bool GMASK, bool LORA>
+// instruction therefore covers G = 32/LPR rows.  E = 1024 → LPR 16, VEC 2: a 128-byte
+// row is 16 × 8-byte loads and one instruction brings in 2 rows; 16 rows in flight.
+template <int LPR, int VEC, bool LPM, bool LORA>
 __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS : FI_MATCH_MIN_BLOCKS + 1))
     match_pick_kernel(const MatchParams p) {
   constexpr int G = 32 / LPR;                 // rows per load instruction
@@ -212,39 +228,19 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
   // dynamic work queue (requests differ a lot in how many rows they touch); the next item is
   // fetched while the current one is processed so the atomic's round trip is off the critical path
   uint32_t r_next = 0;
-  if (lane == 0) r_next = atomicAdd(p.work_counter, 1u);
+  if (lane == 0) r_next = take_ticket(p.work_counter, threadIdx.x & p.lane_zero);
   r_next = __shfl_sync(FULL, r_next, 0);
   for (;;) {
     const uint32_t r = r_next;
     if (r >= p.R) break;
-    if (lane == 0) r_next = atomicAdd(p.work_counter, 1u);
+    if (lane == 0) r_next = take_ticket(p.work_counter, threadIdx.x & p.lane_zero);
     const uint32_t n = p.nblocks[r];
-    // ---- 1. stage the chain (sharded upstream mode reads the nodes probe_slots_kernel found instead)
-    if (!GMASK) {
+    // ---- 1. stage the chain
+    {
       const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
       for (uint32_t u = lane; 2 * u < n; u += 32) cp_async16(s_chain + 2 * u, crow + 2 * u);
       cp_async_wait_all();
       __syncwarp();
-    }
-    // ---- global first miss from the ranks' presence masks (sharded upstream mode)
-    uint32_t kg = n;
-    if (GMASK) {
-      uint32_t orv = 0;
-      if ((uint32_t)lane < p.mask_words) {
-        if (p.px.enabled) {  // tagged words stored by every rank's probe_slots_kernel: wait for this request's only
-          const uint64_t* gm = reinterpret_cast<const uint64_t*>(p.px.base[p.px.rank] + p.px.off_mask[p.px.step & 1u]);
-          for (uint32_t rk = 0; rk < p.gmask_ranks; ++rk)
-            orv |= ll_wait(gm + ((uint64_t)rk * p.R + r) * p.mask_words + lane, p.px.step, p.px.err);
-        } else {
-          for (uint32_t rk = 0; rk < p.gmask_ranks; ++rk)
-            orv |= __ldcg(p.gmask + ((uint64_t)rk * p.R + r) * p.mask_words + lane);
-        }
-      }
-      uint32_t inv = ~orv;
-      uint32_t pos = ((uint32_t)lane < p.mask_words && inv) ? lane * 32 + (__ffs(inv) - 1) : 0xFFFFFFFFu;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) pos = min(pos, __shfl_xor_sync(FULL, pos, d));
-      kg = min(n, pos);
     }
 
     BitCounter cnt[VEC];
@@ -258,20 +254,16 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
     bool real_miss = false;
 
     // ---- 2./3. probe + row reads, 32 blocks per chunk ---------------------------
-    const uint32_t nchunks = (kg + 31) / 32;
-    uint32_t slot = SLOT_MISS;  // node of this lane's block of the current chunk
-    if (GMASK) {
-      if ((uint32_t)lane < kg) slot = __ldcg(p.slots + (uint64_t)r * p.MP + lane);
-    } else {
-      const bool v0 = (uint32_t)lane < kg;
+    const uint32_t nchunks = (n + 31) / 32;
+    uint32_t slot;  // node of this lane's block of the current chunk
+    {
+      const bool v0 = (uint32_t)lane < n;
       slot = resolve_chunk_nodes(ix, v0 ? s_chain[lane] : 0ull, v0, SLOT_MISS, false, lane);
     }
     for (uint32_t c = 0; c < nchunks; ++c) {
       uint32_t rows_here;
       bool stop = false;
-      if (GMASK) {
-        rows_here = min(32u, kg - c * 32);
-      } else {
+      {
         const unsigned mm = __ballot_sync(FULL, slot == SLOT_MISS);
         rows_here = mm ? (uint32_t)(__ffs(mm) - 1) : 32u;
         if (mm) {
@@ -285,21 +277,19 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
       bool validn = false, spec = false;
       uint32_t cand = SLOT_MISS;
       uint32_t slot_next = SLOT_MISS;
-      bool resolved = GMASK;
+      bool resolved = false;
       if (!stop && c + 1 < nchunks) {
         const uint32_t idx = (c + 1) * 32 + lane;
-        validn = idx < kg;
-        if (GMASK) {
-          if (validn) slot_next = __ldcg(p.slots + (uint64_t)r * p.MP + idx);
-        } else {
-          const uint32_t last = __shfl_sync(FULL, slot, 31);
-          if (validn) {
-            hn = s_chain[idx];
-            cand = last + 1u + (uint32_t)lane;
-            spec = last < ix.C && cand < ix.C && !key_is_special(hn);
-            if (spec) kspec = __ldg(ix.klog + cand);
-          }
+        validn = idx < n;
+        const uint32_t last = __shfl_sync(FULL, slot, 31);
+        if (validn) {
+          hn = s_chain[idx];
+          cand = last + 1u + (uint32_t)lane;
+          spec = last < ix.C && cand < ix.C && !key_is_special(hn);
+          if (spec) kspec = __ldg(ix.klog + cand);
         }
+      } else {
+        resolved = true;
       }
       // rows of this chunk; rows past the first miss read the permanently-zero row instead of being
       // predicated off (decided once per chunk, so a row load is shuffle + multiply-add + load)
@@ -386,6 +376,10 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
     }
 
     // ---- 4./5. score candidates, argmax, PD rule ---------------------------------
+    TieRot tr;
+    tr.E = p.E_global;
+    tr.ep_begin = p.ep_begin;
+    tr.start = tie_start(tie_seed(n, n ? s_chain[0] : 0ull, n ? 0ull : p.h0[r], p.r_base + r), p.E_global);
     uint32_t dec_e = FI_NO_ENDPOINT, dec_m = 0;
 #pragma unroll
     for (int pi = 0; pi < (int)FI_EPP_MAX_PROFILES; ++pi) {
@@ -396,6 +390,7 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
         b.score = -1.0;
         b.e = FI_NO_ENDPOINT;
         b.m = 0;
+        b.k = 0xFFFFFFFFu;
         if (LORA) {
           // The lora-affinity score depends on the request's adapter, so there is no per-batch
           // zero-match best: score every eligible endpoint.  After the merge every lane group holds the
@@ -413,10 +408,12 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
               const uint32_t e = wi * 32 + bit;
               const uint32_t m = bc_get(cnt[x], bit);
               const double s = total_score(pr, sc_p, p.st.Epad, e, m, n, lora_score(p.st.lora[e], adapter));
-              if (better(s, e, b)) {
+              const uint32_t k = tr.key(e);
+              if (better(s, k, b)) {
                 b.score = s;
                 b.e = e;
                 b.m = m;
+                b.k = k;
               }
             }
           }
@@ -431,10 +428,12 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
               const uint32_t e = wi * 32 + bit;
               const uint32_t m = bc_get(cnt[x], bit);
               const double s = total_score(pr, sc_p, p.st.Epad, e, m, n);
-              if (better(s, e, b)) {
+              const uint32_t k = tr.key(e);
+              if (better(s, k, b)) {
                 b.score = s;
                 b.e = e;
                 b.m = m;
+                b.k = k;
               }
             }
           }
@@ -445,18 +444,30 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
             const double os = __shfl_xor_sync(FULL, b.score, d);
             const uint32_t oe = __shfl_xor_sync(FULL, b.e, d);
             const uint32_t om = __shfl_xor_sync(FULL, b.m, d);
-            if (better(os, oe, b)) {
+            const uint32_t ok = __shfl_xor_sync(FULL, b.k, d);
+            if (better(os, ok, b)) {
               b.score = os;
               b.e = oe;
               b.m = om;
+              b.k = ok;
             }
           }
         }
+        // Endpoints without a matched block share the per-batch zero-match total; which of the endpoints
+        // attaining it comes first depends on this request's rotation.  (Skipped when a matched candidate
+        // already beats that total: every scorer weight is >= 0.)
         const ZeroBest zb = p.st.zero[pi];
-        if (!LORA && zb.e_local != FI_NO_ENDPOINT && better(zb.score, zb.e_local, b)) {
-          b.score = zb.score;
-          b.e = zb.e_local;
-          b.m = 0;
+        if (!LORA && zb.any && !(b.score > zb.score)) {
+          const uint32_t ez = tie_first_local(p.st.ztie + (uint64_t)pi * ix.W, ix.W, tr, p.ep_count, lane);
+          if (ez != FI_NO_ENDPOINT) {
+            const uint32_t kz = tr.key(ez);
+            if (better(zb.score, kz, b)) {
+              b.score = zb.score;
+              b.e = ez;
+              b.m = 0;
+              b.k = kz;
+            }
+          }
         }
         if (pi == (int)p.pd_decode) {
           dec_e = b.e;
@@ -505,97 +516,20 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
   }
 }
 
-
-// Sharded upstream mode, first pass: probe every block of every request once.  The slot of each block is
-// kept for the match pass (which then never touches the table), and the presence mask of the request
-// goes out to every rank — tagged words into peer memory, or a plain array for the NCCL all-gather.
-__global__ void __launch_bounds__(kWarps * 32, 4) probe_slots_kernel(const MatchParams p, uint32_t* __restrict__ mask_out) {
-  constexpr int D = 4;  // chunks of 32 blocks whose home-bucket loads are in flight together (per lane)
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  for (uint32_t r = blockIdx.x * kWarps + warp; r < p.R; r += gridDim.x * kWarps) {
-    const uint32_t n = p.nblocks[r];
-    const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
-    for (uint32_t c0 = 0; c0 < p.mask_words; c0 += D) {
-      uint64_t hk[D];
-      BucketRegs br[D];
-      bool valid[D], plain[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const uint32_t idx = (c0 + d) * 32 + lane;
-        valid[d] = idx < n;
-        hk[d] = valid[d] ? crow[idx] : 0;
-      }
-      // presence filter first (L2-resident): three quarters of the blocks a rank is asked about are not
-      // in its shard, and a clear bit spares them the table probe (a DRAM transaction each)
-      uint32_t fw[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        plain[d] = valid[d] && !key_is_special(hk[d]);
-        fw[d] = plain[d] ? __ldg(filter_word(p.ix, hk[d])) : 0u;
-      }
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        plain[d] = plain[d] && filter_test(p.ix, hk[d], fw[d]);  // from here on: "plain key that may be present"
-#pragma unroll
-        for (int qq = 0; qq < BUCKET_KEYS / 2; ++qq) br[d].q[qq] = make_uint4(0, 0, 0, 0);
-        br[d].nodes = make_uint4(0, 0, 0, 0);
-        if (plain[d]) br[d] = bucket_load_keys(p.ix, hk[d] & p.ix.bmask);
-      }
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const uint32_t c = c0 + d;
-        if (c >= p.mask_words) break;  // warp-uniform
-        const uint32_t idx = c * 32 + lane;
-        // `slot` ends up as the block's NODE.  A table hit in the home bucket only yields the table slot; the
-        // hits of a chunk are mostly one run of consecutive nodes, so the first of them reads node_of[] and
-        // the others confirm "that node + my distance" against klog (coalesced) before falling back to it.
-        uint32_t slot = SLOT_MISS;
-        uint64_t tslot = ~0ull;  // table slot of a home-bucket hit whose node is not known yet
-        if (plain[d]) {
-          const int j = bucket_scan(br[d], hk[d]);
-          if (j < BUCKET_KEYS) tslot = (hk[d] & p.ix.bmask) * BUCKET_KEYS + j;
-          else if (j > BUCKET_KEYS) slot = index_find_slow(p.ix, hk[d]);
-        } else if (valid[d] && key_is_special(hk[d])) {
-          slot = index_find_slow(p.ix, hk[d]);
-        }
-        const unsigned hm = __ballot_sync(FULL, tslot != ~0ull);
-        if (hm) {
-          const int f = __ffs(hm) - 1;
-          uint32_t nf = 0;
-          if (lane == f) nf = __ldg(p.ix.node_of + tslot);
-          nf = __shfl_sync(FULL, nf, f);
-          if (tslot != ~0ull) {
-            const uint32_t cand = nf + (uint32_t)(lane - f);
-            slot = (lane == f || node_holds(p.ix, cand, hk[d])) ? cand : __ldg(p.ix.node_of + tslot);
-          }
-        }
-        if (idx < p.MP) p.slots[(uint64_t)r * p.MP + idx] = slot;
-        const unsigned m = __ballot_sync(FULL, slot != SLOT_MISS);
-        if (p.px.enabled) {
-          for (uint32_t k = lane; k < p.px.world; k += 32)
-            ll_store(reinterpret_cast<uint64_t*>(p.px.base[k] + p.px.off_mask[p.px.step & 1u]) +
-                         ((uint64_t)p.px.rank * p.R + r) * p.mask_words + c,
-                     m, p.px.step);
-        } else if (lane == 0) {
-          mask_out[(uint64_t)r * p.mask_words + c] = m;
-        }
-      }
-    }
-  }
-}
-
-// multi-GPU: reduce the ranks' local picks (score desc, endpoint asc), then the PD rule
+// multi-GPU: reduce the ranks' local picks (score desc, then the request's tie rotation), then the PD rule
 __global__ void __launch_bounds__(256) merge_picks_kernel(const MergeParams p) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= p.R) return;
+  const uint32_t n = p.nblocks[r];
+  const uint32_t ts = tie_start(tie_seed(n, n ? p.chain[(uint64_t)r * p.MP] : 0ull, n ? 0ull : p.h0[r], r), p.E_global);
   fi_pick best[FI_EPP_MAX_PROFILES];
   for (uint32_t pi = 0; pi < p.P; ++pi) {
     fi_pick b;
     b.endpoint = FI_NO_ENDPOINT;
     b.match_blocks = 0;
-    b.n_blocks = (uint16_t)p.nblocks[r];
+    b.n_blocks = (uint16_t)n;
     b.score = 0.0;
+    uint32_t bk = 0xFFFFFFFFu;
     for (uint32_t rk = 0; rk < p.ranks; ++rk) {
       fi_pick c;
       if (p.px.enabled) {  // four tagged words per pick, valid when all carry this step's tag
@@ -617,20 +551,24 @@ __global__ void __launch_bounds__(256) merge_picks_kernel(const MergeParams p) {
         }
         c.endpoint = (uint32_t)v0;
         c.match_blocks = (uint16_t)v1;
-        c.n_blocks = (uint16_t)p.nblocks[r];
+        c.n_blocks = (uint16_t)n;
         c.score = __longlong_as_double((long long)((v3 << 32) | (v2 & 0xFFFFFFFFull)));
       } else {
         c = p.gathered[((uint64_t)rk * p.R + r) * p.P + pi];
       }
       if (c.endpoint == FI_NO_ENDPOINT) continue;
-      if (b.endpoint == FI_NO_ENDPOINT || c.score > b.score || (c.score == b.score && c.endpoint < b.endpoint)) b = c;
+      const uint32_t ck = tie_rot(c.endpoint, ts, p.E_global);
+      if (b.endpoint == FI_NO_ENDPOINT || c.score > b.score || (c.score == b.score && ck < bk)) {
+        b = c;
+        bk = ck;
+      }
     }
     best[pi] = b;
   }
   if (p.apply_pd) {
     const fi_pick d = best[p.pd_decode];
     const uint64_t len = p.offsets[r + 1] - p.offsets[r];
-    if (!pd_prefill_runs(d.endpoint, d.match_blocks, p.nblocks[r], len, p.pd_threshold)) {
+    if (!pd_prefill_runs(d.endpoint, d.match_blocks, n, len, p.pd_threshold)) {
       best[p.pd_prefill].endpoint = FI_NO_ENDPOINT;
       best[p.pd_prefill].match_blocks = 0;
       best[p.pd_prefill].score = 0.0;
@@ -640,35 +578,33 @@ __global__ void __launch_bounds__(256) merge_picks_kernel(const MergeParams p) {
 }
 
 // Per-batch constants of the non-prefix scorers: eligibility
-// words, clamp01'd kv / queue scores of the local endpoints, and the best endpoint
-// of each profile when nothing matches.  One CTA.
+// words, clamp01'd kv / queue scores of the local endpoints, the best total of each profile when
+// nothing matches, and the local endpoints that attain it (the tie set).  One CTA.
 __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointDev* __restrict__ eps, uint32_t E_global,
                                                                  uint32_t ep_begin, uint32_t ep_count, ScoreTables st,
                                                                  double* __restrict__ sc, uint32_t* __restrict__ elig,
-                                                                 ZeroBest* __restrict__ zero) {
+                                                                 ZeroBest* __restrict__ zero, uint32_t* __restrict__ ztie) {
   __shared__ int s_min[32], s_max[32];
   __shared__ double s_bs[32];
-  __shared__ uint32_t s_be[32];
   __shared__ int s_minq, s_maxq;
+  __shared__ double s_best;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t W = st.Epad / 32;
   for (uint32_t pi = 0; pi < st.n_profiles; ++pi) {
     const ProfileDev pr = st.prof[pi];
     // queue min/max over the eligible endpoints of the WHOLE pool
-    int mn = INT_MAX, mx = INT_MIN, any = 0;
+    int mn = INT_MAX, mx = INT_MIN;
     for (uint32_t e = tid; e < E_global; e += blockDim.x) {
       const EndpointDev s = eps[e];
       if ((s.flags & FI_ENDPOINT_ALIVE) && (pr.role_mask == 0 || (s.role_mask & pr.role_mask))) {
         mn = min(mn, s.queue_depth);
         mx = max(mx, s.queue_depth);
-        any = 1;
       }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       mn = min(mn, __shfl_xor_sync(FULL, mn, d));
       mx = max(mx, __shfl_xor_sync(FULL, mx, d));
-      any |= __shfl_xor_sync(FULL, any, d);
     }
     if (lane == 0) {
       s_min[warp] = mn;
@@ -687,11 +623,8 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointD
     __syncthreads();
     const int minq = s_minq, maxq = s_maxq;
     double* sc_p = sc + (uint64_t)pi * FI_EPP_MAX_SCORERS * st.Epad;
-    Best b;
-    b.score = -1.0;
-    b.e = FI_NO_ENDPOINT;
-    b.m = 0;
-    for (uint32_t e = tid; e < st.Epad; e += blockDim.x) {  // blockDim multiple of 32, Epad multiple of 32
+    // zero-match total of one local endpoint (the prefix scorer contributes 0·w); also fills the tables
+    auto zero_total = [&](uint32_t e, bool* ok_out, bool store) -> double {
       bool ok = false;
       EndpointDev s;
       s.kv_util = 0.0;
@@ -702,8 +635,6 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointD
         s = eps[ep_begin + e];
         ok = (s.flags & FI_ENDPOINT_ALIVE) && (pr.role_mask == 0 || (s.role_mask & pr.role_mask));
       }
-      const unsigned word = __ballot_sync(FULL, ok);
-      if (lane == 0) elig[(uint64_t)pi * W + e / 32] = word;
       double tot = 0.0;
       for (uint32_t k = 0; k < pr.n_scorers; ++k) {
         double v = 0.0;
@@ -716,43 +647,41 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointD
         }
         v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
         if (!ok) v = 0.0;
-        sc_p[(uint64_t)k * st.Epad + e] = v;
-        tot = __dadd_rn(tot, __dmul_rn(v, pr.weight[k]));  // prefix scorer contributes 0·w at zero match
+        if (store) sc_p[(uint64_t)k * st.Epad + e] = v;
+        tot = __dadd_rn(tot, __dmul_rn(v, pr.weight[k]));
       }
-      if (ok && better(tot, e, b)) {
-        b.score = tot;
-        b.e = e;
-      }
+      *ok_out = ok;
+      return tot;
+    };
+    double best = -1.0;  // totals are >= 0
+    for (uint32_t e = tid; e < st.Epad; e += blockDim.x) {  // blockDim multiple of 32, Epad multiple of 32
+      bool ok;
+      const double tot = zero_total(e, &ok, true);
+      const unsigned word = __ballot_sync(FULL, ok);
+      if (lane == 0) elig[(uint64_t)pi * W + e / 32] = word;
+      if (ok && tot > best) best = tot;
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const double os = __shfl_xor_sync(FULL, b.score, d);
-      const uint32_t oe = __shfl_xor_sync(FULL, b.e, d);
-      if (better(os, oe, b)) {
-        b.score = os;
-        b.e = oe;
-      }
-    }
-    if (lane == 0) {
-      s_bs[warp] = b.score;
-      s_be[warp] = b.e;
-    }
+    for (int d = 16; d > 0; d >>= 1) best = fmax(best, __shfl_xor_sync(FULL, best, d));
+    if (lane == 0) s_bs[warp] = best;
     __syncthreads();
     if (tid == 0) {
-      Best z;
-      z.score = -1.0;
-      z.e = FI_NO_ENDPOINT;
-      z.m = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
-        if (better(s_bs[w], s_be[w], z)) {
-          z.score = s_bs[w];
-          z.e = s_be[w];
-        }
+      double z = -1.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) z = fmax(z, s_bs[w]);
+      s_best = z;
       ZeroBest zb;
-      zb.score = z.e == FI_NO_ENDPOINT ? 0.0 : z.score;
-      zb.e_local = z.e;
+      zb.any = z >= 0.0 ? 1u : 0u;
+      zb.score = zb.any ? z : 0.0;
       zb.pad = 0;
       zero[pi] = zb;
+    }
+    __syncthreads();
+    const double zbest = s_best;
+    for (uint32_t e = tid; e < st.Epad; e += blockDim.x) {  // the tie set: same arithmetic, same bits
+      bool ok;
+      const double tot = zero_total(e, &ok, false);
+      const unsigned word = __ballot_sync(FULL, ok && tot == zbest);
+      if (lane == 0) ztie[(uint64_t)pi * W + e / 32] = word;
     }
     __syncthreads();
   }
@@ -794,13 +723,8 @@ cudaError_t launch_match_t(const MatchParams& p, int sm_count, cudaStream_t s) {
     return cudaGetLastError();
   };
   const bool lpm = p.lpm == FI_MATCH_LPM;
-  const bool gm = p.gmask != nullptr;
-  if (p.st.has_lora) {
-    if (lpm) return gm ? go(match_pick_kernel<LPR, VEC, true, true, true>) : go(match_pick_kernel<LPR, VEC, true, false, true>);
-    return gm ? go(match_pick_kernel<LPR, VEC, false, true, true>) : go(match_pick_kernel<LPR, VEC, false, false, true>);
-  }
-  if (lpm) return gm ? go(match_pick_kernel<LPR, VEC, true, true, false>) : go(match_pick_kernel<LPR, VEC, true, false, false>);
-  return gm ? go(match_pick_kernel<LPR, VEC, false, true, false>) : go(match_pick_kernel<LPR, VEC, false, false, false>);
+  if (p.st.has_lora) return lpm ? go(match_pick_kernel<LPR, VEC, true, true>) : go(match_pick_kernel<LPR, VEC, false, true>);
+  return lpm ? go(match_pick_kernel<LPR, VEC, true, false>) : go(match_pick_kernel<LPR, VEC, false, false>);
 }
 
 }  // namespace
@@ -825,15 +749,6 @@ cudaError_t launch_match_pick(const MatchParams& p, int sm_count, cudaStream_t s
   }
 }
 
-cudaError_t launch_probe_slots(const MatchParams& p, uint32_t* mask_out, int sm_count, cudaStream_t s) {
-  if (p.R == 0) return cudaSuccess;
-  uint32_t grid = (p.R + kWarps - 1) / kWarps;
-  const uint32_t cap = (uint32_t)sm_count * 8;
-  if (grid > cap) grid = cap;
-  probe_slots_kernel<<<grid, kWarps * 32, 0, s>>>(p, mask_out);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_merge_picks(const MergeParams& p, cudaStream_t s) {
   if (p.R == 0) return cudaSuccess;
   merge_picks_kernel<<<(p.R + 255) / 256, 256, 0, s>>>(p);
@@ -841,8 +756,9 @@ cudaError_t launch_merge_picks(const MergeParams& p, cudaStream_t s) {
 }
 
 cudaError_t launch_prepare_endpoints(const EndpointDev* eps, uint32_t E_global, uint32_t ep_begin, uint32_t ep_count,
-                                     ScoreTables st, double* sc, uint32_t* elig, ZeroBest* zero, cudaStream_t s) {
-  prepare_endpoints_kernel<<<1, 1024, 0, s>>>(eps, E_global, ep_begin, ep_count, st, sc, elig, zero);
+                                     ScoreTables st, double* sc, uint32_t* elig, ZeroBest* zero, uint32_t* ztie,
+                                     cudaStream_t s) {
+  prepare_endpoints_kernel<<<1, 1024, 0, s>>>(eps, E_global, ep_begin, ep_count, st, sc, elig, zero, ztie);
   return cudaGetLastError();
 }
 

@@ -164,6 +164,17 @@ class EndpointPicker:
             self._lib.fi_epp_index_add_chain(self._h, endpoint, _ptr(hashes), len(hashes)), "fi_epp_index_add_chain"
         )
 
+    def index_add_chains(self, endpoints: np.ndarray, chains: np.ndarray, nblocks: np.ndarray):
+        """indexer.Add(chains[r, :nblocks[r]], endpoints[r]) for a whole batch of decisions (upstream PreRequest);
+        chains: [R, pitch] u64 as returned by pick_batch(want_chains=True).  Collective on a sharded pool."""
+        endpoints = np.ascontiguousarray(endpoints, dtype=np.uint32)
+        nblocks = np.ascontiguousarray(nblocks, dtype=np.uint32)
+        chains = np.ascontiguousarray(chains, dtype=np.uint64)
+        R = len(endpoints)
+        pitch = chains.shape[1] if chains.ndim == 2 else (chains.size // max(R, 1))
+        self._check(self._lib.fi_epp_index_add_chains(self._h, _ptr(endpoints), _ptr(chains), pitch, _ptr(nblocks), R),
+                    "fi_epp_index_add_chains")
+
     def index_sync(self):
         self._check(self._lib.fi_epp_index_sync(self._h), "fi_epp_index_sync")
 

@@ -24,7 +24,8 @@
  *   ------------------------------------------------------------------------
  *   config loader for the YAML of strategy.go:52-67 → fi_epp_config_from_yaml
  *   prefix.Plugin hashPrompt (xxhash chain)         → fi_epp_hash_batch
- *   prefix indexer.Add / LRU eviction (PreRequest)  → fi_epp_index_add_chain,
+ *   prefix indexer.Add / LRU eviction (PreRequest)  → fi_epp_index_add_chains (a batch
+ *                                                     of decisions), fi_epp_index_add_chain,
  *                                                     fi_epp_index_apply
  *   datastore pod metrics refresh (kv, queue, role) → fi_epp_endpoints_update
  *   SchedulerProfile.Run: filter → scorers → picker → fi_epp_pick_batch
@@ -37,6 +38,16 @@
  * serialised by a mutex (concurrency comes from batching); library threads
  * never call back into the host language.  There is NO CPU fallback: without
  * a CUDA device fi_epp_create fails with FI_ERR_CUDA.
+ *
+ * Ties.  Upstream's MaxScorePicker shuffles the candidates before its stable sort, i.e. equal totals are
+ * resolved at random.  Here the order among endpoints with equal totals is a rotation
+ * of the pool that starts at a position derived from the request, so that picks are reproducible (and
+ * bit-comparable with the CPU oracle) yet spread over the tied pods the way upstream's shuffle does:
+ *     seed  = n_blocks > 0 ? h_1 (the first chained block hash) : h0[r] ^ (r + 1) * 0x9E3779B97F4A7C15
+ *     x     = seed;  x ^= x >> 30;  x *= 0xBF58476D1CE4E5B9;  x ^= x >> 27;  x *= 0x94D049BB133111EB;  x ^= x >> 31
+ *     start = ((x >> 32) * num_endpoints) >> 32
+ *     among equal totals the endpoint with the smallest (endpoint - start) mod num_endpoints wins
+ * (r = index of the request within the call).
  */
 #ifndef FI_EPP_H_
 #define FI_EPP_H_
@@ -48,7 +59,7 @@
 extern "C" {
 #endif
 
-#define FI_EPP_ABI_VERSION 1u
+#define FI_EPP_ABI_VERSION 2u
 #define FI_EPP_MAX_PROFILES 4u
 #define FI_EPP_MAX_SCORERS 4u
 #define FI_EPP_MAX_BLOCKS 1023u /* counts are kept in 10 bit-planes on the GPU */
@@ -114,7 +125,8 @@ typedef struct fi_epp_config {
   uint32_t max_batch;  /* largest R accepted by one pick/hash call */
   uint32_t reserved0;
   uint64_t max_prompt_bytes; /* largest total prompt bytes per call (device staging) */
-  uint64_t index_slots;      /* key slots of the GPU index, power of two; 0 = 2x endpoint_count*lru_capacity (load <= 0.5) */
+  uint64_t index_slots;      /* key slots of the GPU index, power of two; 0 = 2x num_endpoints*lru_capacity (load <= 0.5: a shard
+                              * is a directory of the whole pool's keys, with membership rows for its own endpoints) */
   uint32_t n_profiles;
   uint32_t pd_enabled;        /* pd-profile-handler present (strategy.go:129-133) */
   uint32_t pd_decode_profile; /* profile index run first */
@@ -217,13 +229,29 @@ int fi_epp_endpoints_update(fi_epp* h, const fi_endpoint_state* states, uint32_t
 int fi_epp_endpoints_lora_update(fi_epp* h, const fi_endpoint_lora* states, uint32_t n);
 
 /* Asynchronous, ordered: every op submitted before a pick call is visible to
- * that pick.  Ops for endpoints outside this handle's shard are ignored. */
+ * that pick.  Ops for endpoints outside this handle's shard are ignored.
+ *
+ * Sharded pools (after fi_epp_comm_init with world > 1): every rank's index is a directory of the WHOLE pool's
+ * block hashes — membership rows only for its own endpoints — so that "the first block no pod holds" (where
+ * upstream's matchLongestPrefix stops) is a local lookup.  The owner of an endpoint applies its ops and the
+ * resulting key appear/vanish transitions are exchanged between the ranks inside this call: index updates of
+ * a sharded pool are COLLECTIVE — every rank calls fi_epp_index_apply / fi_epp_index_add_chains the same
+ * number of times in the same order, each with its own ops (possibly none). */
 int fi_epp_index_apply(fi_epp* h, const fi_index_op* ops, uint64_t n);
 
 /* Upstream indexer.Add(hashes, pod): touch each hash in `endpoint`'s LRU
  * (capacity lru_capacity), emit SET for new entries and CLEAR for evicted
- * ones.  Requires lru_capacity > 0. */
+ * ones.  Requires lru_capacity > 0.  Single-rank handles only (FI_ERR_STATE on a sharded pool). */
 int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes, uint32_t n);
+
+/* The same for a whole batch of routing decisions — upstream's PreRequest step after a pick batch:
+ * indexer.Add(chains[r*pitch_blocks .. +nblocks[r]), endpoints[r]) for r = 0..R-1 (FI_NO_ENDPOINT and
+ * endpoints of other shards are skipped).  Equal to R fi_epp_index_add_chain calls in request order; the
+ * endpoints' LRUs are walked in parallel on host worker threads (FI_EPP_LRU_THREADS, default = usable
+ * cores, at most 64).  `chains` / `nblocks` are what fi_epp_pick_batch returned (chains_out, picks'
+ * n_blocks).  Collective on a sharded pool. */
+int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains, uint32_t pitch_blocks,
+                            const uint32_t* nblocks, uint32_t R);
 
 int fi_epp_index_sync(fi_epp* h); /* block until submitted ops are applied */
 
@@ -277,10 +305,12 @@ void fi_epp_pinned_free(void* p);
  * the host distributes it out of band, every rank calls comm_init. */
 int fi_epp_comm_unique_id(uint8_t out[FI_EPP_UNIQUE_ID_BYTES]);
 int fi_epp_comm_init(fi_epp* h, const uint8_t id[FI_EPP_UNIQUE_ID_BYTES], uint32_t rank, uint32_t world);
-/* How the sharded pick exchanges presence masks and local picks between ranks: FI_EXCHANGE_NONE (one rank),
- * FI_EXCHANGE_PEER (default: kernels store into every rank's buffer over NVLink peer memory / CUDA IPC and
- * wait on flags in-kernel — no collective call in the step) or FI_EXCHANGE_NCCL (two ncclAllGather per step:
- * env FI_EPP_EXCHANGE=nccl, more than 16 ranks, or a rank that cannot map a peer's buffer). */
+/* Must precede the first index update of the handle.  How the sharded pick reduces the ranks' local
+ * (score, endpoint) picks: FI_EXCHANGE_NONE (one rank), FI_EXCHANGE_PEER (default: the match kernel stores its
+ * pick into every rank's buffer over NVLink peer memory / CUDA IPC and the merge kernel polls tagged words —
+ * no collective call for the reduction) or FI_EXCHANGE_NCCL (one ncclAllGather: env FI_EPP_EXCHANGE=nccl,
+ * more than 16 ranks, or a rank that cannot map a peer's buffer).  Hashing is split over the ranks and the
+ * chains all-gathered (env FI_EPP_SHARD_HASH=replicated: every rank hashes every prompt instead). */
 #define FI_EXCHANGE_NONE 0
 #define FI_EXCHANGE_PEER 1
 #define FI_EXCHANGE_NCCL 2

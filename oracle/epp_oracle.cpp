@@ -21,13 +21,19 @@
 //
 // Build: g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared (oracle/Makefile).
 
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <list>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -342,6 +348,24 @@ inline double total_score(const fi_profile& p, const ProfileCtx& c, const EpStat
   return total;
 }
 
+// ----------------------------------------------------------------------------
+// Tie order — SURVEY.md Appendix A.5.  Upstream's MaxScorePicker shuffles the candidates before its stable
+// sort, so equal totals are resolved at random.  To stay reproducible (and comparable bit for bit with the GPU
+// path) the order among tied endpoints is a rotation of the pool whose start is derived from the request —
+// the rule stated in include/fi_epp.h ("Ties"), restated here independently of the kernels' tiebreak.cuh:
+//   seed  = n_blocks > 0 ? first chained block hash : h0 ^ (r + 1)·0x9E3779B97F4A7C15   (r = index in the call)
+//   start = (splitmix64_finalise(seed) >> 32) · E >> 32
+//   the tied endpoint with the smallest (e − start) mod E wins.
+// ----------------------------------------------------------------------------
+inline uint32_t tie_rotation_start(uint32_t n_blocks, uint64_t first_hash, uint64_t h0, uint32_t r, uint32_t E) {
+  uint64_t x = n_blocks ? first_hash : (h0 ^ ((uint64_t)r + 1) * 0x9E3779B97F4A7C15ULL);
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  x = x ^ (x >> 31);
+  return (uint32_t)(((x >> 32) * (uint64_t)E) >> 32);
+}
+inline uint32_t tie_distance(uint32_t e, uint32_t start, uint32_t E) { return (e + E - start) % E; }
+
 struct Scratch {
   std::vector<uint16_t> match;   // per endpoint
   std::vector<uint32_t> touched;  // endpoints with match > 0
@@ -352,7 +376,7 @@ struct Scratch {
 
 // One request: hash → match (A.3) → score (A.4) → pick (A.5) → PD (A.6).
 void pick_one(const Oracle& o, const std::vector<ProfileCtx>& ctx, const uint8_t* prompt, uint64_t len,
-              uint64_t h0, uint64_t adapter, fi_pick* out, uint64_t* chain_out, Scratch& sc) {
+              uint64_t h0, uint64_t adapter, uint32_t r, fi_pick* out, uint64_t* chain_out, Scratch& sc) {
   const fi_epp_config& cfg = o.cfg;
   const uint32_t E = cfg.num_endpoints;
   sc.chain.resize(cfg.max_blocks);
@@ -399,15 +423,17 @@ void pick_one(const Oracle& o, const std::vector<ProfileCtx>& ctx, const uint8_t
     }
   }
 
+  const uint32_t start = tie_rotation_start(n, n ? sc.chain[0] : 0, h0, r, E);
   for (uint32_t p = 0; p < cfg.n_profiles; ++p) {
     const fi_profile& prof = cfg.profiles[p];
     double best = 0.0;
     uint32_t best_e = FI_NO_ENDPOINT;
-    for (uint32_t e = 0; e < E; ++e) {  // ascending: first strictly-greater wins → lowest index on ties
+    for (uint32_t e = 0; e < E; ++e) {  // max total; equal totals: the request's tie rotation decides
       const EpState& es = o.eps[e];
       if (!eligible(es, prof.role_mask)) continue;
       double t = total_score(prof, ctx[p], es, sc.match[e], n, adapter);
-      if (best_e == FI_NO_ENDPOINT || t > best) {
+      if (best_e == FI_NO_ENDPOINT || t > best ||
+          (t == best && tie_distance(e, start, E) < tie_distance(best_e, start, E))) {
         best = t;
         best_e = e;
       }
@@ -459,6 +485,28 @@ bool validate(const fi_epp_config& c, std::string& err) {
 }  // namespace
 
 extern "C" {
+
+// The defaults of generatePrefixCacheConfig (/root/reference/pkg/router/strategy.go:51-68) with 64-byte blocks
+//  — so that the CPU legs can build their configuration without loading the product library.
+int epo_config_default(fi_epp_config* c) {
+  if (!c) return FI_ERR_INVALID;
+  std::memset(c, 0, sizeof(*c));
+  c->struct_size = sizeof(*c);
+  c->abi_version = FI_EPP_ABI_VERSION;
+  c->block_bytes = 64;
+  c->max_blocks = 256;      // strategy.go:58
+  c->lru_capacity = 31250;  // strategy.go:59
+  c->num_endpoints = 1;
+  c->endpoint_count = 1;
+  c->match_mode = FI_MATCH_UPSTREAM;
+  c->max_batch = 1024;
+  c->n_profiles = 1;
+  std::snprintf(c->profiles[0].name, sizeof(c->profiles[0].name), "default");
+  c->profiles[0].n_scorers = 1;
+  c->profiles[0].scorers[0].kind = FI_SCORER_PREFIX;
+  c->profiles[0].scorers[0].weight = 100;  // strategy.go:66
+  return FI_OK;
+}
 
 uint64_t epo_xxh64(const void* data, uint64_t len, uint64_t seed) {
   return xxh64((const uint8_t*)data, (size_t)len, seed);
@@ -549,6 +597,17 @@ int epo_index_add_chain(void* h, uint32_t endpoint, const uint64_t* hashes, uint
   return FI_OK;
 }
 
+// a batch of decisions, sequentially in request order (what fi_epp_index_add_chains must equal)
+int epo_index_add_chains(void* h, const uint32_t* endpoints, const uint64_t* chains, uint32_t pitch,
+                         const uint32_t* nblocks, uint32_t R) {
+  for (uint32_t r = 0; r < R; ++r) {
+    if (endpoints[r] == FI_NO_ENDPOINT || nblocks[r] == 0) continue;
+    int rc = epo_index_add_chain(h, endpoints[r], chains + (size_t)r * pitch, nblocks[r]);
+    if (rc != FI_OK) return rc;
+  }
+  return FI_OK;
+}
+
 uint64_t epo_index_keys(void* h) { return ((Oracle*)h)->index.keys(); }
 
 // membership probe for tests: 1 if (endpoint, hash) is in the logical index
@@ -578,6 +637,84 @@ int epo_hash_batch(void* h, const uint8_t* prompts, const uint64_t* offsets, con
   return FI_OK;
 }
 
+// host cores this process may actually use: the affinity mask, capped by the cgroup CPU quota if there is one
+static unsigned usable_cores() {
+  unsigned n = std::thread::hardware_concurrency();
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) n = (unsigned)CPU_COUNT(&set);
+  if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {  // cgroup v2: "<quota|max> <period>"
+    char q[64] = {0};
+    long long period = 0;
+    if (std::fscanf(f, "%63s %lld", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0) {
+      const long long quota = std::atoll(q);
+      if (quota > 0) n = std::min<unsigned>(n, (unsigned)std::max<long long>(1, (quota + period - 1) / period));
+    }
+    std::fclose(f);
+  }
+  return n ? n : 1;
+}
+
+// Persistent workers (one pool per process): the timing legs call the batch entry points many times and must
+// not pay a thread spawn per call.
+class Pool {
+ public:
+  static Pool& get(unsigned n) {
+    static std::mutex mu;
+    static std::unique_ptr<Pool> inst;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!inst || inst->n_ != n) inst.reset(new Pool(n));
+    return *inst;
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void run(const std::function<void(unsigned)>& fn) {  // fn(worker) on every worker, the caller is worker 0
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      busy_ = n_ - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    fn(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return busy_ == 0; });
+  }
+
+ private:
+  explicit Pool(unsigned n) : n_(n < 1 ? 1 : n) {
+    for (unsigned w = 1; w < n_; ++w) th_.emplace_back([this, w] {
+      uint64_t seen = 0;
+      for (;;) {
+        {
+          std::unique_lock<std::mutex> lk(mu_);
+          cv_.wait(lk, [&] { return gen_ != seen; });
+          seen = gen_;
+          if (stop_) return;
+        }
+        (*fn_)(w);
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--busy_ == 0) done_.notify_one();
+      }
+    });
+  }
+  unsigned n_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(unsigned)>* fn_ = nullptr;
+  unsigned busy_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 // The whole path for R requests; requests are sharded over `nthreads` host
 // threads (the index is read-only during a batch).  out: R*n_profiles picks.
 static int pick_batch_impl(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,
@@ -593,7 +730,7 @@ static int pick_batch_impl(void* h, const uint8_t* prompts, const uint64_t* offs
     Scratch sc;
     for (uint32_t rep = 0; rep < repeat; ++rep)
       for (uint32_t r = lo; r < hi; ++r) {
-        pick_one(*o, ctx, prompts + offsets[r], offsets[r + 1] - offsets[r], h0[r], adapters ? adapters[r] : 0,
+        pick_one(*o, ctx, prompts + offsets[r], offsets[r + 1] - offsets[r], h0[r], adapters ? adapters[r] : 0, r,
                  out + (size_t)r * P,
                  chains_out ? chains_out + (size_t)r * o->cfg.max_blocks : nullptr, sc);
       }
@@ -602,16 +739,16 @@ static int pick_batch_impl(void* h, const uint8_t* prompts, const uint64_t* offs
     work(0, R);
     return FI_OK;
   }
-  std::vector<std::thread> th;
-  uint32_t per = (R + nthreads - 1) / nthreads;
-  for (uint32_t t = 0; t < nthreads; ++t) {
-    uint32_t lo = t * per, hi = std::min(R, lo + per);
-    if (lo >= hi) break;
-    th.emplace_back(work, lo, hi);
-  }
-  for (auto& t : th) t.join();
+  const uint32_t per = (R + nthreads - 1) / nthreads;
+  Pool::get(nthreads).run([&](unsigned t) {
+    const uint32_t lo = t * per, hi = std::min(R, lo + per);
+    if (lo < hi) work(lo, hi);
+  });
   return FI_OK;
 }
+
+// cores the CPU legs may use (affinity mask ∩ cgroup quota) — what bench.py reports as `cores`
+uint32_t epo_usable_cores(void) { return usable_cores(); }
 
 int epo_pick_batch(void* h, const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0, uint32_t R,
                    fi_pick* out, uint64_t* chains_out, uint32_t nthreads) {

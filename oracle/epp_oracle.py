@@ -60,8 +60,28 @@ def load() -> C.CDLL:
     lib.epo_pick_batch.argtypes = [_P, _P, _P, _P, C.c_uint32, _P, _P, C.c_uint32]
     lib.epo_pick_batch_repeat.restype = C.c_int
     lib.epo_pick_batch_repeat.argtypes = [_P, _P, _P, _P, C.c_uint32, _P, C.c_uint32, C.c_uint32]
+    lib.epo_index_add_chains.restype = C.c_int
+    lib.epo_index_add_chains.argtypes = [_P, _P, _P, C.c_uint32, _P, C.c_uint32]
+    lib.epo_usable_cores.restype = C.c_uint32
+    lib.epo_usable_cores.argtypes = []
+    lib.epo_config_default.restype = C.c_int
+    lib.epo_config_default.argtypes = [C.POINTER(abi.fi_epp_config)]
     _lib = lib
     return lib
+
+
+def usable_cores() -> int:
+    """host cores the CPU legs may use: affinity mask capped by the cgroup CPU quota"""
+    return int(load().epo_usable_cores())
+
+
+def default_config() -> abi.fi_epp_config:
+    """generatePrefixCacheConfig defaults filled by the ORACLE library (the reference arm of bench.py must not
+    load the product library)."""
+    cfg = abi.fi_epp_config()
+    rc = load().epo_config_default(C.byref(cfg))
+    assert rc == 0, rc
+    return cfg
 
 
 def xxh64(data: bytes, seed: int = 0) -> int:
@@ -117,6 +137,13 @@ class Oracle:
     def index_add_chain(self, endpoint: int, hashes):
         hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
         rc = self._lib.epo_index_add_chain(self._h, endpoint, _ptr(hashes), len(hashes))
+        assert rc == 0, rc
+
+    def index_add_chains(self, endpoints, chains, nblocks):
+        endpoints = np.ascontiguousarray(endpoints, dtype=np.uint32)
+        nblocks = np.ascontiguousarray(nblocks, dtype=np.uint32)
+        chains = np.ascontiguousarray(chains, dtype=np.uint64)
+        rc = self._lib.epo_index_add_chains(self._h, _ptr(endpoints), _ptr(chains), chains.shape[1], _ptr(nblocks), len(endpoints))
         assert rc == 0, rc
 
     def index_contains(self, endpoint: int, h: int) -> bool:

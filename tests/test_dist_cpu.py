@@ -2,7 +2,7 @@
 
 Each rank runs the CPU oracle restricted to its shard (other endpoints not alive, only
 its shard's index entries), the ranks exchange their per-request (score, endpoint)
-picks exactly as the GPU path does (all-gather + lowest-index-tie-break max), and the
+picks exactly as the GPU path does (all-gather + max with the request's tie rotation), and the
 merged result must equal the unsharded oracle.  Also covers shard_range, the
 unique-id broadcast and the max-over-ranks timing reduction used by bench.py.
 """
@@ -24,15 +24,19 @@ def _free_port():
     return p
 
 
-def merge_picks_numpy(gathered):
-    """[world, R, P] picks -> [R, P]: score desc, endpoint asc, FI_NO_ENDPOINT never wins."""
+def merge_picks_numpy(gathered, starts, E):
+    """[world, R, P] picks -> [R, P]: score desc, then the request's tie rotation (starts[r]: fi_epp.h "Ties"),
+    FI_NO_ENDPOINT never wins — what merge_picks_kernel does."""
     from fusioninfer_b200 import _abi as abi
 
     out = gathered[0].copy()
+    st = np.asarray(starts, dtype=np.int64)[:, None]
     for g in gathered[1:]:
         none_o = out["endpoint"] == abi.FI_NO_ENDPOINT
         none_g = g["endpoint"] == abi.FI_NO_ENDPOINT
-        better = (~none_g) & (none_o | (g["score"] > out["score"]) | ((g["score"] == out["score"]) & (g["endpoint"] < out["endpoint"])))
+        rot_o = (out["endpoint"].astype(np.int64) - st) % E
+        rot_g = (g["endpoint"].astype(np.int64) - st) % E
+        better = (~none_g) & (none_o | (g["score"] > out["score"]) | ((g["score"] == out["score"]) & (rot_g < rot_o)))
         out[better] = g[better]
     return out
 
@@ -83,9 +87,12 @@ def _worker(rank, world, port, q):
                 mine = ops[(ops["endpoint"] >= begin) & (ops["endpoint"] < begin + count)]
                 o_local.index_apply(mine)
             tok, offs = wl.prompts()
-            local = o_local.pick_batch(tok, offs, wl.h0)
+            local, chains = o_local.pick_batch(tok, offs, wl.h0, want_chains=True)
             gathered = fdist.all_gather_array(local)
-            merged = merge_picks_numpy(list(gathered))
+            from tests import restate
+
+            starts = [restate.tie_start(int(local[q, 0]["n_blocks"]), int(chains[q, 0]), wl.h0, q, wl.E) for q in range(wl.R)]
+            merged = merge_picks_numpy(list(gathered), starts, wl.E)
             want = o_global.pick_batch(tok, offs, wl.h0)
             assert H.picks_equal(merged, want), H.describe_diff(merged, want)
             del cfg

@@ -24,10 +24,17 @@ def _cfg(wl, cfg_id, **kw):
     return H.config_for(wl, profiles=profiles, pd=pd, index_slots=slots, max_prompt_bytes=wl.R * wl.T * 4, **kw)
 
 
-@pytest.mark.parametrize("cfg_id", [2, 3])
+@pytest.mark.parametrize("cfg_id", [2, 3, 5, 50])
 def test_full_size_properties_and_sampled_parity(cfg_id):
+    """cfg 5 = BASELINE.json configs[4] on one GPU (16 384 req x 512 P + 512 D, prefix 50 + kv 25 + queue 25,
+    threshold 0); 50 = the same with a non-zero pd threshold (some prefill picks are skipped)."""
+    thr = None
+    if cfg_id == 50:
+        cfg_id, thr = 5, 6000.0
     wl = synth.baseline_workload(cfg_id)
     cfg = _cfg(wl, cfg_id)
+    if thr is not None:
+        cfg.pd_threshold = thr
     gpu = EndpointPicker(cfg)
     gpu.update_endpoints(wl.endpoint_states())
     tok, offs = wl.prompts()
@@ -42,7 +49,7 @@ def test_full_size_properties_and_sampled_parity(cfg_id):
     # 1. idempotence / batch independence: two halves hashed and picked separately give the same answers
     half = wl.R // 2
     p2 = gpu.pick_batch(tok[half:], offs[: wl.R - half + 1], wl.h0)
-    assert H.picks_equal(p2, picks[half:])
+    assert H.picks_equal(p2, picks[half:])  # (every prompt has blocks: the tie rotation does not involve the index in the call)
     # 2. chain prefix property: same group ⇒ identical chain up to the common shared length; diverges right after
     groups, shared = wl.request_params()
     order = np.argsort(groups, kind="stable")
@@ -57,16 +64,20 @@ def test_full_size_properties_and_sampled_parity(cfg_id):
                 break
     assert checked > 50
     # 3. a match never exceeds the request's shared prefix, fully unique requests match nothing
-    mb = picks[:, 0]["match_blocks"].astype(np.int64)
+    main = cfg.pd_decode_profile if cfg.pd_enabled else 0  # the profile whose pick always stands
+    mb = picks[:, main]["match_blocks"].astype(np.int64)
     assert (mb <= shared // wl.block_tokens).all()
-    assert (picks[:, 0]["n_blocks"] == wl.n_blocks).all()
+    assert (picks[:, main]["n_blocks"] == wl.n_blocks).all()
+    if thr is not None:
+        skipped = picks[:, cfg.pd_prefill_profile]["endpoint"] == abi.FI_NO_ENDPOINT
+        assert 0.02 < skipped.mean() < 0.98
     assert (mb > 0).mean() > 0.5
     # 4. the picked endpoint really holds every matched block (membership round trip through the index)
     sample = np.flatnonzero(mb > 0)[:64]
     q = []
     for r in sample:
         for i in range(mb[r]):
-            q.append((int(chains[r, i]), int(picks[r, 0]["endpoint"]), 0))
+            q.append((int(chains[r, i]), int(picks[r, main]["endpoint"]), 0))
     assert gpu.index_contains(H.ops_array(q)).all()
     # 5. sampled bit-exact parity with the oracle
     S = 768

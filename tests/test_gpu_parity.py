@@ -200,7 +200,7 @@ def test_pick_ties_dead_endpoints_and_empty_pool():
         gpu, cpu = _pair(cfg)
         st = wl.endpoint_states()
         st["flags"] = np.where(alive_fn(np.arange(wl.E)), abi.FI_ENDPOINT_ALIVE, 0)
-        st["queue_depth"] = 4  # all equal → queue score 1.0 everywhere → mass ties → lowest index
+        st["queue_depth"] = 4  # all equal → queue score 1.0 everywhere → mass ties → the requests' rotations decide
         _load(wl, gpu, cpu, states=st)
         got = gpu.pick_batch(tok, offs, wl.h0)
         want = cpu.pick_batch(tok, offs, wl.h0)
@@ -555,4 +555,90 @@ def test_pipelined_submit_equals_oracle_with_index_updates_in_between():
     for k, R in enumerate(sizes):
         got = outs[k].cpu().numpy().view(H.PICK_DTYPE).reshape(R, 2)
         assert H.picks_equal(got, wants[k]), f"batch {k}\n" + H.describe_diff(got, wants[k])
+    gpu.close()
+
+
+def test_tie_rotation_spreads_cold_requests_and_matches_the_rule():
+    """with the reference's default profile (prefix scorer only, strategy.go:51-68) every request
+    without a cached prefix ties on all endpoints; the rotation must spread them (not endpoint 0) and follow the
+    rule of include/fi_epp.h, checked here against the independent python statement of it (tests/restate.py)."""
+    from tests import restate
+
+    wl = H.small_workload(E=200, R=256)
+    cfg = H.config_for(wl)
+    gpu, cpu = _pair(cfg)
+    st = wl.endpoint_states()
+    gpu.update_endpoints(st)
+    cpu.update_endpoints(st)
+    tok, offs = wl.prompts()
+    got, chains = gpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+    want = cpu.pick_batch(tok, offs, wl.h0)
+    assert H.picks_equal(got, want), H.describe_diff(got, want)
+    assert len(np.unique(got[:, 0]["endpoint"])) > 100
+    for r in range(wl.R):
+        assert got[r, 0]["endpoint"] == restate.tie_start(int(got[r, 0]["n_blocks"]), int(chains[r, 0]), wl.h0, r, wl.E)
+    # short prompts (no block): rotation by (h0, request index); sliced and unsliced host feeds agree (r_base)
+    data, offs2 = H.pack_prompts([bytes(10)] * 64)
+    got2 = gpu.pick_batch(data, offs2, wl.h0)
+    assert H.picks_equal(got2, cpu.pick_batch(data, offs2, wl.h0))
+    assert len(np.unique(got2[:, 0]["endpoint"])) > 30
+    gpu.close()
+
+
+@pytest.mark.parametrize("lpm", [False, True])
+def test_gpu_equals_the_second_restatement(lpm):
+    """The kernels against tests/restate.py (python dicts / floats / the xxhash wheel; shares no code with the
+    oracle): cfg 1 of BASELINE.json and a hole-y pool with the weighted PD profiles."""
+    from tests import restate
+
+    for wl, profiles, pd in (
+        (synth.baseline_workload(1, lru_capacity=300),) + synth.baseline_profiles(1),
+        (H.small_workload(E=48, R=96, holes=True, pd=True, lru_capacity=250),) + tuple(
+            x if i == 0 else dict(x, threshold=700.0) for i, x in enumerate(synth.baseline_profiles(5))),
+    ):
+        cfg = H.config_for(wl, profiles=profiles, pd=pd, match_mode=abi.FI_MATCH_LPM if lpm else abi.FI_MATCH_UPSTREAM)
+        gpu = EndpointPicker(cfg)
+        ref = restate.from_config(cfg)
+        st = wl.endpoint_states()
+        gpu.update_endpoints(st)
+        ref.update_endpoints(st)
+        for ops in wl.index_ops():
+            gpu.index_apply(ops)
+            ref.apply(ops)
+        tok, offs = wl.prompts()
+        got = gpu.pick_batch(tok, offs, wl.h0)
+        want = ref.pick(tok, offs, wl.h0)
+        assert H.picks_equal(got, want), H.describe_diff(got, want)
+        gpu.close()
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_add_chains_batch_equals_sequential_oracle(threads, monkeypatch):
+    """fi_epp_index_add_chains (host LRU walked on a worker pool, segments where a hash is re-added after its
+    eviction inside the same batch) equals the oracle adding the chains one request at a time — over several
+    steps with LRU churn (capacity far below one batch's inserts per endpoint, so the same-batch re-add path
+    runs), and the picks stay bit-exact."""
+    monkeypatch.setenv("FI_EPP_LRU_THREADS", threads)
+    wl = H.small_workload(E=12, R=160, T=768, max_blocks=48, lru_capacity=70)
+    prof = [{"name": "d", "scorers": [(P, 100), (K, 9), (Q, 5)]}]
+    cfg = H.config_for(wl, profiles=prof, lru_capacity=70, index_slots=1 << 16)
+    gpu, cpu = _pair(cfg)
+    st = wl.endpoint_states()
+    gpu.update_endpoints(st)
+    cpu.update_endpoints(st)
+    for step in range(6):
+        tok, offs = wl.prompts(batch=step % 3)  # batches recur: prefixes are re-touched after evictions
+        got, ch = gpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+        want, wch = cpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+        assert H.picks_equal(got, want), f"step {step}\n" + H.describe_diff(got, want)
+        gpu.index_add_chains(got[:, 0]["endpoint"], ch, got[:, 0]["n_blocks"])
+        cpu.index_add_chains(want[:, 0]["endpoint"], wch, want[:, 0]["n_blocks"])
+    gpu.index_sync()
+    # membership round trip on a sample of (endpoint, hash) pairs both ways
+    q = [(int(wch[r, i]), int(e), 0) for r in range(0, wl.R, 7) for i in range(0, 48, 5) for e in range(wl.E)]
+    have = gpu.index_contains(H.ops_array(q))
+    for (hh, e, _), g in zip(q, have):
+        assert bool(g) == cpu.index_contains(e, hh)
+    stt = gpu.index_stats()
+    assert stt.lru_entries <= wl.E * 70 and stt.tombstones > 0
     gpu.close()

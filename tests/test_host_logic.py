@@ -37,6 +37,12 @@ def hc():
     lib.fihc_lru_size.argtypes = [C.c_void_p]
     lib.fihc_lru_contains.argtypes = [C.c_void_p, C.c_uint64]
     lib.fihc_lru_touch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fihc_tie_start.restype = C.c_uint32
+    lib.fihc_tie_start.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+    lib.fihc_tie_rot.restype = C.c_uint32
+    lib.fihc_tie_rot.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.fihc_tie_first_local.restype = C.c_uint32
+    lib.fihc_tie_first_local.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     return lib
 
 
@@ -303,3 +309,36 @@ def test_config_rejects_bad_documents(bad, frag):
     with pytest.raises(FiEppError) as ei:
         config_from_yaml(bad)
     assert ei.value.status == abi.FI_ERR_CONFIG and frag in str(ei.value)
+
+
+def test_tie_rotation_arithmetic_of_the_kernels(hc):
+    """tiebreak.cuh (what the match / merge kernels compile) against the python statement of the rule in
+    tests/restate.py: rotation start, rotated distance, and — the part with the bit tricks — the first member
+    of a LOCAL tie set in rotation order for shards anywhere in the pool."""
+    from tests import restate
+
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        E = int(rng.integers(1, 5000))
+        n = int(rng.integers(0, 3))
+        fh, h0, r = int(rng.integers(0, 2**63)) * 2 + 1, int(rng.integers(0, 2**63)), int(rng.integers(0, 70000))
+        start = hc.fihc_tie_start(n, fh, h0, r, E)
+        assert start == restate.tie_start(n, fh, h0, r, E) and start < E
+        e = int(rng.integers(0, E))
+        assert hc.fihc_tie_rot(e, start, E) == (e - start) % E
+    for _ in range(400):
+        W = int(2 ** rng.integers(0, 8))
+        world = int(rng.integers(1, 9))
+        ep_count = int(rng.integers(1, W * 32 + 1))
+        rank = int(rng.integers(0, world))
+        ep_begin = rank * ep_count
+        E = world * ep_count
+        start = int(rng.integers(0, E))
+        dens = rng.choice([0.0, 0.02, 0.5, 1.0])
+        members = [e for e in range(ep_count) if rng.random() < dens]
+        words = np.zeros(W, dtype=np.uint32)
+        for e in members:
+            words[e // 32] |= np.uint32(1 << (e % 32))
+        got = hc.fihc_tie_first_local(words.ctypes.data, W, start, ep_begin, ep_count)
+        want = min(members, key=lambda e: (e + ep_begin - start) % E) if members else 0xFFFFFFFF
+        assert got == want, (W, ep_begin, ep_count, start, members[:8], got, want)

@@ -101,14 +101,32 @@ def test_upstream_stops_at_first_global_miss():
     assert pk["score"] == 100.0 * (1.0 / 4.0)
 
 
-def test_tie_break_lowest_index_and_dead_endpoints():
-    blob = bytes(128)
-    data, offs = H.pack_prompts([blob])
+def test_tie_break_rotation_and_dead_endpoints():
+    """Equal totals: the alive endpoint nearest after the request's rotation start wins (fi_epp.h "Ties";
+    upstream shuffles).  The start is worked out here from the rule, not taken from the oracle."""
+    from tests import restate
+
     o, _ = _oracle(E=6)
     st = H.states_array(6, alive=np.array([0, 0, 1, 1, 1, 0], dtype=np.uint32))
     o.update_endpoints(st)
-    pk = o.pick_batch(data, offs, 5)[0, 0]
-    assert pk["endpoint"] == 2 and pk["score"] == 0.0  # all tie at 0 → lowest alive index
+    seen = set()
+    for k in range(12):
+        blob = bytes([k]) * 128
+        data, offs = H.pack_prompts([blob])
+        pk = o.pick_batch(data, offs, 5)[0, 0]
+        start = restate.tie_start(2, _chain(blob, h0=5)[0], 5, 0, 6)
+        want = min((2, 3, 4), key=lambda e: (e - start) % 6)
+        assert pk["endpoint"] == want and pk["score"] == 0.0
+        seen.add(int(pk["endpoint"]))
+    assert len(seen) > 1  # different prompts rotate differently
+    # a prompt shorter than one block rotates by (h0, request index)
+    data, offs = H.pack_prompts([bytes(10), bytes(10)])
+    pk = o.pick_batch(data, offs, 5)
+    for r in range(2):
+        start = restate.tie_start(0, 0, 5, r, 6)
+        assert pk[r, 0]["endpoint"] == min((2, 3, 4), key=lambda e: (e - start) % 6)
+    blob = bytes(128)
+    data, offs = H.pack_prompts([blob])
     o2, _ = _oracle(E=3)
     o2.update_endpoints(H.states_array(3, alive=np.zeros(3, dtype=np.uint32)))
     pk = o2.pick_batch(data, offs, 5)[0, 0]
@@ -243,7 +261,10 @@ def test_lora_affinity_scorer_classes():
     data, offs = H.pack_prompts([bytes(64)] * 3)
     pk = o.pick_batch(data, offs, 1, adapters=np.array([77, 11, 99], dtype=np.uint64))
     assert (pk[0, 0]["endpoint"], pk[0, 0]["score"]) == (2, 100.0)   # active beats room (0.8) and queued (0.6)
-    assert (pk[1, 0]["endpoint"], pk[1, 0]["score"]) == (0, 100.0)   # lowest index among the endpoints with 11 active
+    from tests import restate
+
+    start = restate.tie_start(1, _chain(bytes(64), h0=1)[0], 1, 1, 5)  # endpoints 0 and 1 both have 11 active: rotation
+    assert (pk[1, 0]["endpoint"], pk[1, 0]["score"]) == (min((0, 1), key=lambda e: (e - start) % 5), 100.0)
     assert (pk[2, 0]["endpoint"], pk[2, 0]["score"]) == (1, 80.0)    # only endpoint 1 has room
     # without room anywhere the queued endpoint wins
     o.update_endpoints_lora(_lora_states(5, {1: (1, [11], [])}))
