@@ -174,22 +174,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def build_config(wl, cfg_id, begin, count, device, max_batch, mode):
+def build_config(wl, cfg_id, begin, count, device, max_batch, mode, lru_capacity=0, base=None):
     from fusioninfer_b200 import make_config, synth
 
     profiles, pd = synth.baseline_profiles(cfg_id)
     slots = 4096
     mult = int(os.environ.get("FI_BENCH_SLOT_MULT", "2"))  # index load factor <= 1/mult
-    while slots < mult * count * wl.lru_capacity:
+    # an endpoint-range shard is a directory of the WHOLE pool's keys (membership rows for its own endpoints)
+    while slots < mult * (wl.E if mode == "sharded" else count) * wl.lru_capacity:
         slots *= 2
-    return make_config(num_endpoints=wl.E, block_bytes=wl.block_bytes, max_blocks=wl.max_blocks, lru_capacity=0,
+    return make_config(num_endpoints=wl.E, block_bytes=wl.block_bytes, max_blocks=wl.max_blocks, lru_capacity=lru_capacity,
                        max_batch=max_batch, max_prompt_bytes=max_batch * wl.T * 4, index_slots=slots, device=device,
-                       endpoint_begin=begin, endpoint_count=count, profiles=profiles, pd=pd)
+                       endpoint_begin=begin, endpoint_count=count, profiles=profiles, pd=pd, base=base)
 
 
-def algorithmic_bytes(wl, picks_nprobe_total, R, E_local):
-    """A = 4·T + N_probe·(8 + E_local/8) + 16 per decision."""
-    return {"hash_blocks": R * 4 * wl.T, "match_pick": picks_nprobe_total * (8 + E_local / 8.0) + 16.0 * R}
+def algorithmic_bytes(wl, picks_nprobe_total, R, E_local, hashed_requests=None):
+    """A = 4·T + N_probe·(8 + E_local/8) + 16 per decision (hashed_requests: the requests THIS
+    GPU hashes — R/world when a sharded pool splits the hashing)."""
+    hr = R if hashed_requests is None else hashed_requests
+    return {"hash_blocks": hr * 4 * wl.T, "match_pick": picks_nprobe_total * (8 + E_local / 8.0) + 16.0 * R}
 
 
 def load_traffic():
@@ -202,33 +205,54 @@ def load_traffic():
         return {}
 
 
+def host_cores():
+    """Cores the CPU legs may use: the affinity mask capped by the cgroup CPU quota (os.cpu_count() ignores both)."""
+    from oracle import epp_oracle as eo
+
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    return {"usable": eo.usable_cores(), "affinity": aff, "os_cpu_count": os.cpu_count() or 1}
+
+
+def build_oracle(wl, cfg_id, ops_iter, log_label="oracle"):
+    """The CPU restatement with the given index content; its configuration is filled by the oracle library."""
+    from oracle import epp_oracle as eo
+
+    t0 = time.time()
+    o = eo.Oracle(build_config(wl, cfg_id, 0, wl.E, 0, max(wl.R, 1), "replicas", base=eo.default_config()))
+    o.update_endpoints(wl.endpoint_states())
+    for ops in ops_iter:
+        o.index_apply(ops)
+    log(f"{log_label} index built in {time.time() - t0:.1f}s")
+    return o
+
+
 def run_reference(args, wl, cfg_id):
-    """--impl reference: the CPU restatement on the box's host cores, bounded sample per step."""
+    """--impl reference: the CPU restatement on the box's host cores, bounded sample per step.  Nothing of the
+    product library is loaded in this process."""
     from fusioninfer_b200 import synth
-    from oracle.epp_oracle import Oracle
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ncores = os.cpu_count() or 1
-    cfg = build_config(wl, cfg_id, 0, wl.E, 0, max(wl.R, 1), "replicas")
-    t0 = time.time()
-    o = Oracle(cfg)
-    o.update_endpoints(wl.endpoint_states())
+    cores = host_cores()
+    ncores = cores["usable"]
+    o = build_oracle(wl, cfg_id, [], "oracle (empty)")
     o.index_reserve(wl.E * wl.lru_capacity)
+    t0 = time.time()
     for ops in wl.index_ops(chunk_endpoints=128):
         o.index_apply(ops)
     log(f"oracle index built in {time.time() - t0:.1f}s")
     S = args.cpu_sample
     sub = synth.Workload(**{**wl.__dict__, "R": S})
     tok, offs = sub.prompts(batch=100)
-    # Every thread walks its shard `rep` times per step so that thread start-up (~50 us x cores)
-    # does not dominate a bounded sample: calibrate rep for up to ~1 s of wall time per step.
-    S_eff = S
+    # Every thread walks its shard `rep` times per step (persistent worker pool, no thread spawn per call):
+    # calibrate rep for up to ~1 s of wall time per step.
     t0 = time.perf_counter()
     o.pick_batch_repeat(tok, offs, wl.h0, nthreads=ncores, repeat=2)
     per_pass = (time.perf_counter() - t0) / 2
-    # per-step wall time: ~1 s, less when many steps are asked for (the whole run stays around a minute)
     target = min(1.0, 60.0 / max(args.steps + args.warmup, 1))
     rep = int(max(1, min(64, target / max(per_pass, 1e-6))))
     for _ in range(args.warmup):
@@ -237,15 +261,15 @@ def run_reference(args, wl, cfg_id):
     for _ in range(args.steps):
         o.pick_batch_repeat(tok, offs, wl.h0, nthreads=ncores, repeat=rep)
     dt = time.perf_counter() - t0
-    val = S_eff * rep * args.steps / dt
+    val = S * rep * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "decisions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(wl, cfg_id, "cpu"),
-        "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": ncores, "kind": "port",
-                         "sample": f"{S_eff} requests x {rep} passes of the same workload per step, full {wl.E}-endpoint index "
-                                   f"({wl.E * wl.lru_capacity} entries); {ORACLE_LABEL}"},
+        "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": ncores, "cores_detail": cores, "kind": "port",
+                         "sample": f"{S} requests x {rep} passes of the same workload per step, full {wl.E}-endpoint index "
+                                   f"({wl.E * wl.lru_capacity} entries), {ncores} persistent worker threads; {ORACLE_LABEL}"},
         "e2e": {"value": val, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -276,6 +300,318 @@ def workload_config(wl, cfg_id, parallelism):
     }
 
 
+def bind_to_gpu_numa(local):
+    """Run this rank on the cores of its GPU's NUMA node while it allocates and fills its pinned host buffers
+    (pages are placed where the allocating thread runs), so that they are local to the GPU's PCIe root: on the
+    8-GPU node GPUs 4-7 hang off NUMA node 1 (round 1: e2e 6.19 ms/step at N = 8 vs 5.04 at N = 1).
+    Returns (note for the JSON line, function that restores the original affinity)."""
+    try:
+        original = os.sched_getaffinity(0)
+    except Exception:  # noqa: BLE001
+        return "numa: affinity not available", (lambda: None)
+
+    def restore():
+        try:
+            os.sched_setaffinity(0, original)
+        except Exception:  # noqa: BLE001
+            pass
+
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa: single node", restore
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa: pinned buffers allocated from node {node} ({len(allowed)} cpus), the node of GPU {local}", restore
+        return f"numa: node {node} has no allowed cpu", restore
+    except Exception as e:  # noqa: BLE001
+        return f"numa: not bound ({type(e).__name__})", restore
+
+
+def measure_h2d_gbs(nbytes):
+    """The PCIe yardstick of the e2e leg: a pinned cudaMemcpyAsync of the same size in this process (best of 5)."""
+    import torch
+
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del src, dst
+    return best
+
+
+class Scenario:
+    """One workload on one picker: index build, device-resident timing, per-kernel split, sampled parity."""
+
+    def __init__(self, args, cfg_id, mode, rank, world, local, order="chain", R_override=None, batches=None):
+        from fusioninfer_b200 import synth
+
+        self.args, self.cfg_id, self.mode, self.rank, self.world, self.local, self.order = args, cfg_id, mode, rank, world, local, order
+        self.wl = synth.baseline_workload(cfg_id)
+        if R_override:
+            self.wl.R = R_override
+        self.nb = batches or max(1, args.batches)
+        self.split_hash = True
+
+    # -- sampled requests whose picks the oracle re-derives (known BEFORE the index is built, so that every rank
+    # can keep just the index entries those requests can touch: for them that is equivalent to the full index)
+    def _plan_sample(self, tok0, S):
+        from oracle import epp_oracle as eo
+
+        wl = self.wl
+        self.sample_idx = np.linspace(0, wl.R - 1, S).astype(np.int64)
+        o = eo.Oracle(build_config(wl, self.cfg_id, 0, wl.E, 0, S, "replicas", base=eo.default_config()))
+        sub_offs = np.arange(S + 1, dtype=np.uint64) * np.uint64(wl.T * 4)
+        self.sample_tok = np.ascontiguousarray(tok0[self.sample_idx])
+        self.sample_offs = sub_offs
+        ch, _ = o.hash_batch(self.sample_tok, sub_offs, wl.h0)
+        self.needed = np.unique(ch)
+        self.kept_ops = []
+
+    def build(self, sample=0):
+        import torch
+
+        from fusioninfer_b200 import EndpointPicker
+        from fusioninfer_b200 import dist as fdist
+
+        wl, rank, world, local, mode = self.wl, self.rank, self.world, self.local, self.mode
+        t0 = time.time()
+        self.begin, self.count = fdist.shard_range(wl.E, rank, world) if mode == "sharded" else (0, wl.E)
+        churn = self.order == "churned"
+        cfg = build_config(wl, self.cfg_id, self.begin, self.count, local, wl.R, mode, lru_capacity=wl.lru_capacity if churn else 0)
+        self.picker = EndpointPicker(cfg)
+        if mode == "sharded" and world > 1:
+            uid = EndpointPicker.comm_unique_id() if rank == 0 else None
+            with stdout_to_stderr():  # the library's own communicator
+                self.picker.comm_init(fdist.broadcast_bytes(uid, 128), rank, world)
+        self.exchange = self.picker.comm_exchange()
+        self.picker.update_endpoints(wl.endpoint_states())
+        # request batches: replicas serve different batches per rank, shards all see the same requests
+        self.d_tok, self.d_off, self.host0 = [], [], None
+        for b in range(self.nb):
+            bid = b if mode == "sharded" else rank * self.nb + b
+            tok, offs = wl.prompts(batch=bid)
+            self.d_tok.append(torch.from_numpy(tok.view(np.int32)).cuda())
+            self.d_off.append(torch.from_numpy(offs.view(np.int64)).cuda())
+            if b == 0:
+                self.host0 = (tok, offs)
+        if sample:
+            self._plan_sample(self.host0[0], min(sample, wl.R))
+        n_ops = 0
+        rng = np.random.default_rng(0xF051 + self.cfg_id)
+        if churn:
+            n_ops = self._build_through_lru()
+        else:
+            for ops in wl.index_ops(ep_lo=self.begin, ep_hi=self.begin + self.count, chunk_endpoints=128):
+                if sample:
+                    self.kept_ops.append(ops[np.isin(ops["hash"], self.needed)])
+                if self.order == "shuffled":
+                    ops = ops[rng.permutation(len(ops))]
+                self.picker.index_apply(ops)
+                n_ops += len(ops)
+        self.picker.index_sync()
+        ist = self.picker.index_stats()
+        self.index_stats = {"entries": int(n_ops), "keys": int(ist.used - ist.tombstones), "slots": int(ist.slots),
+                            "tombstones": int(ist.tombstones), "rebuilds": int(ist.rebuilds)}
+        R, P = wl.R, self.picker.n_profiles
+        self.P = P
+        self.d_h0 = torch.full((R,), int(np.uint64(wl.h0).astype(np.int64)), dtype=torch.int64, device="cuda")
+        self.d_out = torch.zeros(R * P * 16, dtype=torch.uint8, device="cuda")
+        self.d_outs = [torch.zeros(R * P * 16, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        self.stream = torch.cuda.current_stream().cuda_stream
+        log(f"rank {rank}: cfg{self.cfg_id}/{mode}/{self.order}: {n_ops} index entries -> {ist.used} keys in {ist.slots} slots, "
+            f"{self.nb} batch(es) of {R} requests resident ({time.time() - t0:.1f}s)")
+        return self
+
+    def _build_through_lru(self):
+        """An AGED index: the initial state enters through the host LRU (filler first, then the shared group
+        chains), then K pick + indexer.Add(chain, picked endpoint) rounds evict filler and scatter new chains over
+        retired nodes' successors — what a live picker's index looks like (tombstones, maybe a rebuild)."""
+        wl, pk = self.wl, self.picker
+        nb = wl.n_blocks
+        n = 0
+        for ops in wl.index_ops(ep_lo=self.begin, ep_hi=self.begin + self.count, chunk_endpoints=64):
+            # one pseudo-request per run of <= n_blocks ops of one endpoint, filler before the group chains
+            e = ops["endpoint"]
+            h = ops["hash"]
+            out_e, rows = [], []
+            for ep in np.unique(e):
+                he = h[e == ep]
+                grp, fil = he[: wl.groups_per_endpoint * nb], he[wl.groups_per_endpoint * nb:]
+                seq = np.concatenate([fil, grp])
+                pad = (-len(seq)) % nb
+                seq = np.concatenate([seq, np.zeros(pad, dtype=np.uint64)])
+                rows.append(seq.reshape(-1, nb))
+                out_e.append(np.full(rows[-1].shape[0], ep, dtype=np.uint32))
+            ch = np.concatenate(rows)
+            ee = np.concatenate(out_e)
+            valid = (ch != 0).sum(axis=1).astype(np.uint32)  # the padded tail row of an endpoint carries fewer hashes
+            pk.index_add_chains(ee, ch, valid)
+            n += int(valid.sum())
+        for k in range(self.args.churn_rounds):
+            tok, offs = wl.prompts(batch=1000 + k)
+            picks, chains = pk.pick_batch(tok, offs, wl.h0, want_chains=True)
+            pk.index_add_chains(picks[:, 0]["endpoint"], chains, picks[:, 0]["n_blocks"])
+        return n
+
+    # -- timing -------------------------------------------------------------------------------------
+    def step(self, i):
+        b = i % self.nb
+        wl = self.wl
+        self.picker.pick_batch_device(self.d_tok[b].data_ptr(), self.d_off[b].data_ptr(), self.d_h0.data_ptr(), wl.R,
+                                      wl.R * wl.T * 4, self.d_out.data_ptr(), 0, self.stream)
+
+    def submit(self, i):
+        b = i % self.nb
+        wl = self.wl
+        self.picker.pick_submit(self.d_tok[b].data_ptr(), self.d_off[b].data_ptr(), self.d_h0.data_ptr(), wl.R,
+                                wl.R * wl.T * 4, self.d_outs[i & 1].data_ptr(), self.stream)
+
+    def run_steps(self, k, pipelined=False):
+        if pipelined:
+            for i in range(k):
+                self.submit(i)
+            self.picker.pick_wait(self.stream)
+        else:
+            for i in range(k):
+                self.step(i)
+
+    def time_steps(self, steps, warmup, pipelined=False, clocks=None):
+        """-> (ms per step: CUDA events on the launching stream, max over ranks; launches of this library)"""
+        import torch
+
+        from fusioninfer_b200 import dist as fdist
+
+        self.run_steps(max(warmup, 3), pipelined)
+        torch.cuda.synchronize()
+        fdist.barrier()
+        torch.cuda.synchronize()
+        self.picker.reset_stats()
+        if clocks is not None:
+            clocks.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        self.run_steps(steps, pipelined)
+        ev1.record()
+        torch.cuda.synchronize()
+        fdist.barrier()
+        ms = fdist.max_over_ranks(ev0.elapsed_time(ev1)) / steps
+        return ms, int(self.picker.stats().kernel_launches)
+
+    def kernel_split(self, steps):
+        """per-kernel CUDA-event durations + N_probe from a profiled pass (not part of any reported step time)"""
+        import torch
+
+        pk = self.picker
+        pk.reset_stats()
+        pk.set_profiling(True)
+        n = min(steps, 8)
+        for i in range(n):
+            self.step(i)
+        torch.cuda.synchronize()
+        st = pk.stats()
+        pk.set_profiling(False)
+        kern = {"hash_blocks": (st.ms_hash_blocks, st.n_hash_blocks), "chain_finalize": (st.ms_chain_probe, st.n_chain_probe),
+                "match_pick": (st.ms_match_pick, st.n_match_pick), "other": (st.ms_other, st.n_other)}
+        # "other" counts the sharded step's two chain all-gathers as launches without time: per-launch average
+        # only over launches that were timed
+        avg = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in kern.items()}
+        return avg, st.probed_blocks / max(n, 1)
+
+    def picks_of_batch0(self):
+        """the device path's picks of batch 0, as records [R, P] (+ the chains)"""
+        import torch
+
+        wl = self.wl
+        d_chain = torch.zeros(wl.R * wl.max_blocks, dtype=torch.int64, device="cuda")
+        self.picker.pick_batch_device(self.d_tok[0].data_ptr(), self.d_off[0].data_ptr(), self.d_h0.data_ptr(), wl.R,
+                                      wl.R * wl.T * 4, self.d_out.data_ptr(), d_chain.data_ptr(), self.stream)
+        torch.cuda.synchronize()
+        picks = self.d_out.cpu().numpy().view(np.dtype(
+            [("endpoint", "<u4"), ("match_blocks", "<u2"), ("n_blocks", "<u2"), ("score", "<f8")])).reshape(wl.R, self.P)
+        return picks, d_chain.cpu().numpy().view(np.uint64).reshape(wl.R, wl.max_blocks)
+
+    def sampled_parity(self):
+        """bit-exact check of the sampled requests' picks against the oracle (whole pool, unsharded).  Sharded:
+        the ranks' kept index entries are gathered on rank 0."""
+        from fusioninfer_b200 import dist as fdist
+
+        picks, _ = self.picks_of_batch0()
+        kept = np.concatenate(self.kept_ops) if self.kept_ops else np.zeros(0, dtype=self.kept_ops_dtype())
+        if self.mode == "sharded" and self.world > 1:
+            import torch.distributed as dist
+
+            parts = [None] * self.world
+            dist.all_gather_object(parts, kept)
+            kept = np.concatenate(parts)
+        if self.rank != 0:
+            return None
+        o = build_oracle(self.wl, self.cfg_id, [kept], f"cfg{self.cfg_id} sample oracle")
+        want = o.pick_batch(self.sample_tok, self.sample_offs, self.wl.h0, nthreads=host_cores()["usable"])
+        same = picks[self.sample_idx].tobytes() == want.tobytes()
+        if not same:
+            log(f"PARITY FAILURE cfg{self.cfg_id} {self.mode}")
+        return {"checked_requests": int(len(self.sample_idx)), "bit_exact": bool(same)}
+
+    @staticmethod
+    def kept_ops_dtype():
+        from fusioninfer_b200 import _abi as abi
+
+        return abi.np_dtypes()[1]
+
+    def close(self):
+        import torch
+
+        self.picker.close()
+        self.d_tok = self.d_off = None
+        self.d_out = self.d_outs = self.d_h0 = None
+        torch.cuda.empty_cache()
+
+
+def sub_record(sc, steps, warmup, peak, with_parity=True):
+    """A compact result of one extra configuration (BASELINE.json configs 2, 4, 5) for the line's roofline dict."""
+    wl = sc.wl
+    ms, _ = sc.time_steps(steps, warmup)
+    avg, nprobe = sc.kernel_split(steps)
+    hashed = None
+    if sc.mode == "sharded" and sc.world > 1 and sc.split_hash:
+        hashed = wl.R / sc.world
+    alg = algorithmic_bytes(wl, nprobe, wl.R, sc.count, hashed)
+    step_alg = alg["hash_blocks"] + alg["match_pick"]
+    units = wl.R * (sc.world if sc.mode == "replicas" else 1)
+    rec = {
+        "workload": workload_config(wl, sc.cfg_id, f"{sc.mode}{sc.world}")["workload"],
+        "decisions_per_s": units / (ms * 1e-3), "ms_per_step": ms, "kernel_ms": avg,
+        "n_probe_per_decision": nprobe / wl.R,
+        "algorithmic_bytes_per_step_per_gpu": step_alg,
+        "step_algorithmic_gbs_per_gpu": step_alg / (ms * 1e-3) / 1e9,
+        "frac": step_alg / (ms * 1e-3) / 1e9 / peak,
+        "index": sc.index_stats, "exchange": sc.exchange,
+    }
+    if with_parity:
+        rec["parity"] = sc.sampled_parity()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -293,6 +629,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 10)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (tuning runs only)")
+    ap.add_argument("--extras", default="auto", choices=["auto", "none"],
+                    help="auto: the default cfg-3 run also measures BASELINE.json's other configs into the roofline dict — "
+                         "N = 1: cfg 2, cfg 5 on one GPU, and cfg 3 on a shuffled and on an LRU-aged index; N > 1: cfg 4 and "
+                         "cfg 5 with the index sharded by endpoint range (peer-memory and NCCL pick exchange, split and "
+                         "replicated hashing)")
+    ap.add_argument("--index-order", default="chain", choices=["chain", "shuffled", "churned"],
+                    help="how the main run's index was built (the default run reports all three in roofline.index_order)")
+    ap.add_argument("--churn-rounds", type=int, default=6, help="pick + indexer.Add rounds that age the 'churned' index")
+    ap.add_argument("--extra-steps", type=int, default=30)
     args = ap.parse_args()
 
     from fusioninfer_b200 import synth
@@ -315,7 +660,7 @@ def main():
 
     import torch
 
-    from fusioninfer_b200 import EndpointPicker, PinnedBuffer
+    from fusioninfer_b200 import PinnedBuffer
     from fusioninfer_b200 import dist as fdist
 
     if not torch.cuda.is_available():
@@ -334,116 +679,29 @@ def main():
             fdist.barrier()
             torch.cuda.synchronize()
     torch.cuda.set_device(local)
+    numa_note, numa_restore = bind_to_gpu_numa(local)
+    peak, peak_src = measured_peak_gbs()
 
-    # ---- set-up (untimed) ----------------------------------------------------------
-    t_setup = time.time()
-    if mode == "sharded":
-        begin, count = fdist.shard_range(wl.E, rank, world)
-    else:
-        begin, count = 0, wl.E
-    cfg = build_config(wl, cfg_id, begin, count, local, wl.R, mode)
-    picker = EndpointPicker(cfg)
-    if mode == "sharded" and world > 1:
-        uid = EndpointPicker.comm_unique_id() if rank == 0 else None
-        with stdout_to_stderr():  # the library's own communicator
-            picker.comm_init(fdist.broadcast_bytes(uid, 128), rank, world)
-    exchange = picker.comm_exchange()
-    picker.update_endpoints(wl.endpoint_states())
-    n_ops = 0
-    for ops in wl.index_ops(ep_lo=begin, ep_hi=begin + count, chunk_endpoints=128):
-        picker.index_apply(ops)
-        n_ops += len(ops)
-    picker.index_sync()
-    ist = picker.index_stats()
-    log(f"rank {rank}: index {n_ops} entries -> {ist.used} keys in {ist.slots} slots "
-        f"({time.time() - t_setup:.1f}s)")
-
-    # request batches: replicas serve different batches per rank, shards all see the same requests
-    nb = max(1, args.batches)
-    d_tok, d_off, host_batches = [], [], []
-    for b in range(nb):
-        bid = b if mode == "sharded" else rank * nb + b
-        tok, offs = wl.prompts(batch=bid)
-        d_tok.append(torch.from_numpy(tok.view(np.int32)).cuda())
-        d_off.append(torch.from_numpy(offs.view(np.int64)).cuda())
-        if b == 0:
-            host_batches.append((tok, offs))
-    R = wl.R
-    P = picker.n_profiles
-    d_h0 = torch.full((R,), int(np.uint64(wl.h0).astype(np.int64)), dtype=torch.int64, device="cuda")
-    d_out = torch.zeros(R * P * 16, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
-    log(f"rank {rank}: {nb} batches of {R} requests resident in HBM ({time.time() - t_setup:.1f}s)")
-
-    def step(i):
-        b = i % nb
-        picker.pick_batch_device(d_tok[b].data_ptr(), d_off[b].data_ptr(), d_h0.data_ptr(), R, R * wl.T * 4,
-                                 d_out.data_ptr(), 0, stream)
-
-    # --pipeline: the timed steps go through the pipelined device API (two batches in flight: batch k+1 is
-    # hashed while batch k is matched; every batch has its own output buffer).  Measured +3.5 %.
+    # ---- main scenario (untimed set-up) ------------------------------------------------------------
+    sc = Scenario(args, cfg_id, mode, rank, world, local, order=args.index_order, R_override=wl.R if args.scale != 1.0 else None)
+    sc.split_hash = os.environ.get("FI_EPP_SHARD_HASH", "split") != "replicated"
+    sc.build()
+    picker, R, P = sc.picker, sc.wl.R, sc.P
+    wl = sc.wl
     pipelined = args.pipeline and not (mode == "sharded" and world > 1)
-    d_outs = [torch.zeros(R * P * 16, dtype=torch.uint8, device="cuda") for _ in range(2)]
-
-    def submit(i):
-        b = i % nb
-        picker.pick_submit(d_tok[b].data_ptr(), d_off[b].data_ptr(), d_h0.data_ptr(), R, R * wl.T * 4,
-                           d_outs[i & 1].data_ptr(), stream)
-
-    def run_steps(k):
-        if pipelined:
-            for i in range(k):
-                submit(i)
-            picker.pick_wait(stream)
-        else:
-            for i in range(k):
-                step(i)
-
-    parity = None
-    # ---- warm-up ------------------------------------------------------------------------
-    run_steps(max(args.warmup, 3))
-    torch.cuda.synchronize()
 
     # ---- timed region: exactly K steps, device events on the launching stream -----------------
-    fdist.barrier()
-    torch.cuda.synchronize()
-    picker.reset_stats()
     clocks = ClockSampler(local)
-    if rank == 0 and os.environ.get("FI_BENCH_NO_CLOCKS") != "1":
-        clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    run_steps(args.steps)
-    ev1.record()
-    torch.cuda.synchronize()
-    fdist.barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_step, launches = sc.time_steps(args.steps, args.warmup, pipelined,
+                                      clocks if (rank == 0 and os.environ.get("FI_BENCH_NO_CLOCKS") != "1") else None)
     clk = clocks.stop()
-    launches = picker.stats().kernel_launches
-    ms_total = fdist.max_over_ranks(ms_total)
-    ms_step = ms_total / args.steps
     units = R * (world if mode == "replicas" else 1)
     value = units / (ms_step * 1e-3)
 
     # ---- per-kernel durations + N_probe (profiled pass, not part of the number above) -----------
-    picker.reset_stats()
-    picker.set_profiling(True)
-    prof_steps = min(args.steps, 8)
-    for i in range(prof_steps):
-        step(i)
-    torch.cuda.synchronize()
-    st = picker.stats()
-    picker.set_profiling(False)
-    kern = {
-        "hash_blocks": (st.ms_hash_blocks, st.n_hash_blocks),
-        "chain_finalize": (st.ms_chain_probe, st.n_chain_probe),
-        "match_pick": (st.ms_match_pick, st.n_match_pick),
-        "other": (st.ms_other, st.n_other),
-    }
-    avg_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in kern.items()}
-    nprobe_per_step = st.probed_blocks / max(prof_steps, 1)
-    alg = algorithmic_bytes(wl, nprobe_per_step, R, count)
-    peak, peak_src = measured_peak_gbs()
+    avg_ms, nprobe_per_step = sc.kernel_split(args.steps)
+    hashed = R / world if (mode == "sharded" and world > 1 and sc.split_hash) else None
+    alg = algorithmic_bytes(wl, nprobe_per_step, R, sc.count, hashed)
     dom = max(("hash_blocks", "match_pick"), key=lambda k: avg_ms[k])
     achieved = alg[dom] / (avg_ms[dom] * 1e-3) / 1e9 if avg_ms[dom] else 0.0
     traffic = load_traffic() if (cfg_id == 3 and mode == "replicas" and args.scale == 1.0) else {}  # captured for cfg 3 only
@@ -458,10 +716,11 @@ def main():
         "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak,
         "other_kernels": {k: {"achieved": (alg[k] / (avg_ms[k] * 1e-3) / 1e9 if avg_ms[k] else 0.0),
                               "traffic": traffic.get(k)} for k in ("hash_blocks", "match_pick") if k != dom},
+        "index": sc.index_stats, "index_order_of_value": args.index_order,
     }
 
     # ---- e2e: public C-ABI call with host (pinned) buffers, H2D + D2H inside ---------------------
-    tok0, offs0 = host_batches[0]
+    tok0, offs0 = sc.host0
     pin_tok = PinnedBuffer(tok0.nbytes)
     pin_off = PinnedBuffer(offs0.nbytes)
     pin_h0 = PinnedBuffer(8 * R)
@@ -472,43 +731,50 @@ def main():
     e2e_steps = args.e2e_steps or min(args.steps, 10)
     if args.no_e2e:
         e2e_steps = 1
-    picker_e2e = picker
     for _ in range(2):
-        picker_e2e.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr)
+        picker.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr)
     fdist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        picker_e2e.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr)
+        picker.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     dt = fdist.max_over_ranks(dt)
+    h2d_bytes = int(tok0.nbytes + offs0.nbytes + 8 * R)
+    h2d_gbs = measure_h2d_gbs(int(tok0.nbytes)) if not args.no_e2e else None
+    h2d_gbs_min = -fdist.max_over_ranks(-h2d_gbs) if h2d_gbs else None
     e2e = {"value": units * e2e_steps / dt, "unit": "decisions/s",
-           "h2d_bytes_per_step": int(tok0.nbytes + offs0.nbytes + 8 * R), "d2h_bytes_per_step": int(16 * R * P),
+           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(16 * R * P),
            "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
-           "how": "fi_epp_pick_batch on pinned host buffers: H2D prompts+offsets+seeds, kernels, D2H picks, per step"}
+           "how": "fi_epp_pick_batch on pinned host buffers: H2D prompts+offsets+seeds, kernels, D2H picks, per step",
+           "roofline": {"bound": "pcie", "h2d_gbs_measured": h2d_gbs_min, "unit": "GB/s",
+                        "achieved": h2d_bytes / (dt / e2e_steps) / 1e9,
+                        "frac": (h2d_bytes / (dt / e2e_steps) / 1e9 / h2d_gbs_min) if h2d_gbs_min else None,
+                        "how": "achieved = H2D bytes of a step / its wall time; yardstick = pinned cudaMemcpyAsync of the "
+                               "prompt bytes in this process (best of 6, slowest rank)"},
+           "numa": numa_note}
     e2e_picks = pin_out.array(np.uint8).copy().view(np.dtype(
         [("endpoint", "<u4"), ("match_blocks", "<u2"), ("n_blocks", "<u2"), ("score", "<f8")])).reshape(R, P)
+    numa_restore()  # the CPU leg below may use every core again
 
     # ---- cpu_baseline (rank 0, bounded sample) + parity of the e2e picks on that sample ---------------
     cpu = None
-    if rank == 0 and not args.no_cpu:
-        from oracle.epp_oracle import Oracle
-
-        ncores = os.cpu_count() or 1
-        t0 = time.time()
-        o = Oracle(build_config(wl, cfg_id, 0, wl.E, 0, max(wl.R, 1), "replicas"))
-        o.update_endpoints(wl.endpoint_states())
+    parity = None
+    if rank == 0 and not args.no_cpu and args.index_order == "chain":
+        cores = host_cores()
+        ncores = cores["usable"]
+        o = build_oracle(wl, cfg_id, [], "oracle (empty)")
         S = min(args.cpu_sample, R)
         # the FULL index, not just the sampled requests' hashes: a tiny index would make the CPU
         # lookups unrealistically cache-friendly
         o.index_reserve(wl.E * wl.lru_capacity)
+        t0 = time.time()
         for ops in wl.index_ops(chunk_endpoints=128):
             o.index_apply(ops)
         log(f"oracle index built in {time.time() - t0:.1f}s")
         want = o.pick_batch(tok0[:S], offs0[: S + 1], wl.h0, nthreads=ncores)
-        # timing: every thread walks its shard `rep` times so that thread start-up (~50 us x cores) does
-        # not dominate the bounded sample; ~10-20 s of CPU work in total
+        # timing: every worker walks its shard `rep` times (persistent pool); ~10-20 s of CPU work in total
         t1 = time.perf_counter()
         o.pick_batch_repeat(tok0[:S], offs0[: S + 1], wl.h0, nthreads=ncores, repeat=2)
         per_pass = (time.perf_counter() - t1) / 2
@@ -525,17 +791,73 @@ def main():
         t0 = time.perf_counter()
         o.pick_batch(tok0[:S1], offs0[: S1 + 1], wl.h0, nthreads=1)
         t1s = time.perf_counter() - t0
-        cpu = {"value": S / tn, "unit": "decisions/s", "cores": ncores, "kind": "port",
+        cpu = {"value": S / tn, "unit": "decisions/s", "cores": ncores, "cores_detail": cores, "kind": "port",
                "single_thread_value": S1 / t1s,
                "sample": f"first {S} requests of batch 0 x {rep} passes (full {wl.E * wl.lru_capacity}-entry index), "
-                         f"{ncores} threads sharded by request; single-thread figure on the first {S1}; {ORACLE_LABEL}"}
+                         f"{ncores} persistent worker threads sharded by request; single-thread figure on the first {S1}; {ORACLE_LABEL}"}
+        del o
+    sc.close()
+
+    # ---- BASELINE.json's other configurations, into the roofline dict ---------------------------------
+    extras = args.extras == "auto" and cfg_id == 3 and mode == "replicas" and args.scale == 1.0 and args.index_order == "chain"
+    if extras and world == 1:
+        others = {}
+        for cid in (2, 5):
+            x = Scenario(args, cid, "replicas", rank, world, local, batches=2 if cid == 2 else 1).build(sample=512)
+            x.split_hash = True
+            others[f"cfg{cid}"] = sub_record(x, args.extra_steps, 3, peak)
+            x.close()
+        roofline["configs"] = others
+        order = {"chain": {"decisions_per_s": value, "ms_per_step": ms_step, "match_pick_ms": avg_ms["match_pick"]}}
+        for od in ("shuffled", "churned"):
+            x = Scenario(args, 3, "replicas", rank, world, local, order=od, batches=1).build()
+            x.split_hash = True
+            ms, _ = x.time_steps(args.extra_steps, 3)
+            av, _ = x.kernel_split(8)
+            order[od] = {"decisions_per_s": R / (ms * 1e-3), "ms_per_step": ms, "match_pick_ms": av["match_pick"], "index": x.index_stats}
+            x.close()
+        order["how"] = ("chain: every endpoint's chains bulk-loaded back to back (the headline); shuffled: the same entries in a "
+                        f"random order; churned: the state entered through the host LRU, then {args.churn_rounds} rounds of pick + "
+                        "indexer.Add(chain, picked endpoint) with evictions before timing")
+        roofline["index_order"] = order
+    if extras and world > 1:
+        sharded = {}
+        for cid in (4, 5):
+            x = Scenario(args, cid, "sharded", rank, world, local, batches=1)
+            x.split_hash = True
+            x.build(sample=512)
+            rec = sub_record(x, args.extra_steps, 3, peak)
+            variants = {}
+            for name, opts in (("nccl_exchange", {"exchange": 2}), ("replicated_hash", {"shard_hash": 0})):
+                try:
+                    for k, v in opts.items():
+                        x.picker.set_option(k, v)
+                    x.split_hash = "shard_hash" not in opts
+                    ms, _ = x.time_steps(args.extra_steps, 3)
+                    av, _ = x.kernel_split(8)
+                    variants[name] = {"decisions_per_s": x.wl.R / (ms * 1e-3), "ms_per_step": ms, "kernel_ms": av}
+                except Exception as e:  # noqa: BLE001
+                    variants[name] = {"error": str(e)[:200]}
+                finally:
+                    try:
+                        x.picker.set_option("exchange", 1 if x.exchange == "peer" else 2)
+                        x.picker.set_option("shard_hash", 1)
+                    except Exception:  # noqa: BLE001
+                        pass
+            rec["variants"] = variants
+            rec["bound_decisions_per_s"] = {"how": "SURVEY.md §8d worst case per GPU (every GPU hashes every prompt, all blocks hit) at "
+                                                   "the measured HBM peak, lock-step over the ranks",
+                                            "value": peak * 1e9 / (4 * x.wl.T + x.wl.n_blocks * (8 + x.count / 8.0) + 16)}
+            sharded[f"cfg{cid}"] = rec
+            x.close()
+        roofline["sharded"] = sharded
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": dict(workload_config(wl, cfg_id, f"{mode}{world}"), exchange=exchange,
+            "config": dict(workload_config(wl, cfg_id, f"{mode}{world}"), exchange=sc.exchange,
                            pipeline=("fi_epp_pick_submit/pick_wait: 2 batches in flight, batch k+1 hashed while batch k "
                                      "is matched; all K batches complete inside the timed region") if pipelined
                            else "stream-ordered fi_epp_pick_batch_device calls"),
@@ -545,7 +867,6 @@ def main():
         if args.scale != 1.0:
             line["config"]["workload"] += f" [DEBUG scale={args.scale}: NOT the headline config]"
         print(json.dumps(line), flush=True)
-    picker.close()
     if world > 1:
         import torch.distributed as dist
 

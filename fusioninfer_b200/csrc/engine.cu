@@ -267,6 +267,7 @@ struct fi_epp {
   std::unordered_set<PairKey, PairHash> cleared;
   std::vector<LruSet> lrus;
   std::unique_ptr<WorkerPool> pool;  // host LRU workers (fi_epp_index_add_chains), created on first use
+  unsigned lru_threads = 0;          // 0: FI_EPP_LRU_THREADS, else min(usable cores, 64)
 
   // endpoints / score tables
   std::vector<EndpointDev> eps;  // global pool
@@ -1613,6 +1614,7 @@ int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t
     if (!h->pool) {
       unsigned t = std::min(usable_cores(), 64u);
       if (const char* ev = std::getenv("FI_EPP_LRU_THREADS")) t = (unsigned)std::max(1L, std::strtol(ev, nullptr, 10));
+      if (h->lru_threads) t = h->lru_threads;
       h->pool.reset(new WorkerPool(t));
     }
     outs.resize(h->pool->size());
@@ -2028,6 +2030,40 @@ int fi_epp_comm_exchange(fi_epp* h) {
   std::lock_guard<std::mutex> lk(h->mu);
   if (h->world <= 1) return FI_EXCHANGE_NONE;
   return h->px.enabled ? FI_EXCHANGE_PEER : FI_EXCHANGE_NCCL;
+}
+
+int fi_epp_set_option(fi_epp* h, const char* name, int64_t value) {
+  if (!h || !name) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  const std::string n(name);
+  if (n == "exchange") {
+    if (h->world <= 1) return fail(h, FI_ERR_STATE, "exchange: not a sharded pool");
+    if (value == FI_EXCHANGE_NCCL) {
+      h->px.enabled = 0;
+    } else if (value == FI_EXCHANGE_PEER) {
+      if (!h->px.base[h->rank == 0 ? 1 : 0]) return fail(h, FI_ERR_STATE, "exchange: the peers' buffers were never mapped");
+      h->px.enabled = 1;
+    } else {
+      return fail(h, FI_ERR_INVALID, "exchange: FI_EXCHANGE_PEER or FI_EXCHANGE_NCCL");
+    }
+    return FI_OK;
+  }
+  if (n == "shard_hash") {
+    h->split_hash = value != 0;
+    return FI_OK;
+  }
+  if (n == "feed_slices") {
+    if (value < 1 || value > fi_epp::kMaxFeedSlices) return fail(h, FI_ERR_INVALID, "feed_slices: 1..16");
+    h->feed_slices = (uint32_t)value;
+    return FI_OK;
+  }
+  if (n == "lru_threads") {
+    if (value < 1 || value > 1024) return fail(h, FI_ERR_INVALID, "lru_threads: 1..1024");
+    h->lru_threads = (unsigned)value;
+    h->pool.reset();
+    return FI_OK;
+  }
+  return fail(h, FI_ERR_INVALID, "unknown option: " + n);
 }
 
 int fi_epp_set_profiling(fi_epp* h, int on) {

@@ -61,9 +61,12 @@ def make_config(
     endpoint_count: Optional[int] = None,
     profiles: Optional[Sequence[dict]] = None,
     pd: Optional[dict] = None,
+    base: Optional[abi.fi_epp_config] = None,
 ) -> abi.fi_epp_config:
-    """Build a config in code.  profiles: [{"name", "role_mask", "scorers": [(kind, weight), ...]}]."""
-    cfg = default_config()
+    """Build a config in code.  profiles: [{"name", "role_mask", "scorers": [(kind, weight), ...]}].
+    base: a pre-filled struct to start from instead of fi_epp_config_default() (then libfi_epp.so is not touched:
+    bench.py's CPU reference arm builds its configuration without mapping the product library)."""
+    cfg = base if base is not None else default_config()
     cfg.device = device
     cfg.block_bytes = block_bytes
     cfg.max_blocks = max_blocks
@@ -273,6 +276,10 @@ class EndpointPicker:
         if rc < 0:
             raise FiEppError(rc, "fi_epp_comm_exchange")
         return {0: "none", 1: "peer", 2: "nccl"}[rc]
+
+    def set_option(self, name: str, value: int):
+        """Runtime knobs of include/fi_epp.h (fi_epp_set_option): exchange, shard_hash, feed_slices, lru_threads."""
+        self._check(self._lib.fi_epp_set_option(self._h, name.encode(), int(value)), f"fi_epp_set_option({name})")
 
     # -- stats -----------------------------------------------------------------
     def set_profiling(self, on: bool):

@@ -316,6 +316,14 @@ int fi_epp_comm_init(fi_epp* h, const uint8_t id[FI_EPP_UNIQUE_ID_BYTES], uint32
 #define FI_EXCHANGE_NCCL 2
 int fi_epp_comm_exchange(fi_epp* h);
 
+/* Runtime knobs (measurement and tuning; every one has a working default).  Names:
+ *   "exchange"     sharded pick reduction: FI_EXCHANGE_PEER | FI_EXCHANGE_NCCL (PEER only if the peers were mapped)
+ *   "shard_hash"   sharded hashing: 1 = split over the ranks + all-gather of the chains (default), 0 = replicated
+ *   "feed_slices"  slices of a host-buffer pick's prompt copy, 1..16 (default 8)
+ *   "lru_threads"  host worker threads of fi_epp_index_add_chains (takes effect at the next call)
+ * FI_ERR_INVALID for an unknown name or a value out of range. */
+int fi_epp_set_option(fi_epp* h, const char* name, int64_t value);
+
 int fi_epp_set_profiling(fi_epp* h, int on);
 int fi_epp_get_stats(fi_epp* h, fi_epp_stats* out);
 int fi_epp_reset_stats(fi_epp* h);

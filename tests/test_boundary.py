@@ -92,3 +92,28 @@ def test_kernels_are_built_for_sm_100a():
         pytest.skip("cuobjdump not available")
     out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
+
+
+def test_header_is_c_and_links_from_a_c_program(tmp_path):
+    """include/fi_epp.h compiles as strict C99 and a plain C program links libfi_epp.so and drives the
+    configuration entry points (tests/c/abi_check.c) — the binding a cgo file would make, without Go."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "fusioninfer_b200", "lib")
+    exe = str(tmp_path / "abi_check")
+    cmd = [gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "c", "abi_check.c"), "-L", libdir, "-lfi_epp", f"-Wl,-rpath,{libdir}",
+           "-Wl,--allow-shlib-undefined", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ)
+    cuda_lib = "/usr/local/cuda/lib64"
+    env["LD_LIBRARY_PATH"] = cuda_lib + ":" + env.get("LD_LIBRARY_PATH", "")
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "abi_check:" in r.stdout

@@ -1,14 +1,17 @@
 #!/usr/bin/env python
-"""Index-maintenance path under churn: every decision is followed by
-upstream's PreRequest step, indexer.Add(chain, picked endpoint), through the host LRU
-(fi_epp_index_add_chain) whose SET/CLEAR deltas stream to the GPU index on the side stream and are
-ordered before the next pick.  Checks the picks bit-exactly against the oracle doing the same.
+"""Index-maintenance path under churn: every pick batch is followed by upstream's
+PreRequest step for the whole batch — indexer.Add(chain_r, picked endpoint_r) — through
+fi_epp_index_add_chains (host LRUs walked on a worker pool; SET/CLEAR deltas streamed to the GPU index on the
+side stream, ordered before the next pick).  Picks are checked bit-exactly against the oracle doing the same
+work (sequentially, one chain at a time), whose time is reported beside ours.
 
-    python tools/bench_churn.py [--requests 2048] [--endpoints 256] [--steps 6] [--lru 4000]
+    python tools/bench_churn.py [--cfg 3] [--requests N] [--steps 12] [--threads T] [--no-oracle]
 
-Prints one JSON line: decisions/s of pick + add, the split between the two, ops streamed, rebuilds.
-This is NOT the headline metric (bench.py): the exact per-endpoint LRU order is pointer chasing on the
-host (one list + map touch per block), which is what bounds this mode.
+Defaults = BASELINE.json's headline pool: 1 024 endpoints, lruCapacityPerServer 31 250
+(/root/reference/pkg/router/strategy.go:59), 16 384 requests of 4 096 tokens per step.  The index starts
+full (every endpoint's LRU at capacity), so every new block evicts one.  Prints one JSON line:
+decisions/s of pick + add, the split, ops streamed, tombstone growth, rebuilds and the pick-latency
+distribution (p50 / p99 / max over the steps — a rebuild shows up there).
 """
 from __future__ import annotations
 
@@ -26,68 +29,126 @@ import numpy as np  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--requests", type=int, default=2048)
-    ap.add_argument("--endpoints", type=int, default=256)
-    ap.add_argument("--tokens", type=int, default=4096)
-    ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--lru", type=int, default=4000)
+    ap.add_argument("--cfg", type=int, default=3)
+    ap.add_argument("--requests", type=int, default=0)
+    ap.add_argument("--endpoints", type=int, default=0)
+    ap.add_argument("--lru", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--oracle-steps", type=int, default=2, help="steps the oracle mirrors (it is ~100x slower)")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--slot-mult", type=int, default=2)
     args = ap.parse_args()
 
-    from fusioninfer_b200 import EndpointPicker, make_config, synth
-    from fusioninfer_b200 import _abi as abi
+    from fusioninfer_b200 import EndpointPicker, PinnedBuffer, make_config, synth
 
-    wl = synth.Workload(R=args.requests, E=args.endpoints, T=args.tokens, seed=synth.SEEDS[2], lru_capacity=args.lru)
-    P, K, Q = abi.FI_SCORER_PREFIX, abi.FI_SCORER_KV_UTIL, abi.FI_SCORER_QUEUE
+    over = {}
+    if args.requests:
+        over["R"] = args.requests
+    if args.endpoints:
+        over["E"] = args.endpoints
+    if args.lru:
+        over["lru_capacity"] = args.lru
+    wl = synth.baseline_workload(args.cfg, **over)
+    profiles, pd = synth.baseline_profiles(args.cfg)
     slots = 4096
-    while slots < 4 * wl.E * args.lru:
+    while slots < args.slot_mult * wl.E * wl.lru_capacity:
         slots *= 2
-    cfg = make_config(num_endpoints=wl.E, block_bytes=wl.block_bytes, max_blocks=wl.max_blocks, lru_capacity=args.lru,
-                      max_batch=wl.R, max_prompt_bytes=wl.R * wl.T * 4, index_slots=slots,
-                      profiles=[{"name": "default", "scorers": [(P, 100), (K, 10), (Q, 10)]}])
+    cfg = make_config(num_endpoints=wl.E, block_bytes=wl.block_bytes, max_blocks=wl.max_blocks, lru_capacity=wl.lru_capacity,
+                      max_batch=max(wl.R, 8192), max_prompt_bytes=max(wl.R, 8192) * wl.T * 4, index_slots=slots,
+                      profiles=profiles, pd=pd)
     gpu = EndpointPicker(cfg)
+    if args.threads:
+        gpu.set_option("lru_threads", args.threads)
     gpu.update_endpoints(wl.endpoint_states())
     cpu = None
     if not args.no_oracle:
-        from oracle.epp_oracle import Oracle
+        from oracle import epp_oracle as eo
 
-        cpu = Oracle(cfg)
+        cpu = eo.Oracle(cfg)
         cpu.update_endpoints(wl.endpoint_states())
+        cpu.index_reserve(2 * wl.E * wl.lru_capacity)
 
-    t_pick = t_add = 0.0
-    exact = True
-    hits = 0
+    # ---- initial state THROUGH the LRUs (filler first, then the shared group chains: the filler is the oldest)
+    t0 = time.time()
+    nb = wl.n_blocks
+    for ops in wl.index_ops(chunk_endpoints=64):
+        e, h = ops["endpoint"], ops["hash"]
+        rows, eps = [], []
+        for ep in np.unique(e):
+            he = h[e == ep]
+            seq = np.concatenate([he[wl.groups_per_endpoint * nb:], he[: wl.groups_per_endpoint * nb]])
+            seq = np.concatenate([seq, np.zeros((-len(seq)) % nb, dtype=np.uint64)])
+            rows.append(seq.reshape(-1, nb))
+            eps.append(np.full(rows[-1].shape[0], ep, dtype=np.uint32))
+        ch, ee = np.concatenate(rows), np.concatenate(eps)
+        valid = (ch != 0).sum(axis=1).astype(np.uint32)
+        gpu.index_add_chains(ee, ch, valid)
+        if cpu is not None:
+            cpu.index_add_chains(ee, ch, valid)
+    gpu.index_sync()
+    st0 = gpu.index_stats()
+    print(f"[churn] initial state: {st0.lru_entries} LRU entries, {st0.used} keys ({time.time() - t0:.1f}s)", file=sys.stderr)
+
+    R, P = wl.R, gpu.n_profiles
+    main_p = cfg.pd_decode_profile if cfg.pd_enabled else 0
+    pin_tok, pin_off, pin_h0 = PinnedBuffer(R * wl.T * 4), PinnedBuffer(8 * (R + 1)), PinnedBuffer(8 * R)
+    pin_out, pin_ch = PinnedBuffer(16 * R * P), PinnedBuffer(8 * R * wl.max_blocks)
+    pin_h0.array(np.uint64)[:] = np.uint64(wl.h0)
+    picks_v = pin_out.array(np.uint8).view(np.dtype([("endpoint", "<u4"), ("match_blocks", "<u2"), ("n_blocks", "<u2"),
+                                                      ("score", "<f8")])).reshape(R, P)
+    chains_v = pin_ch.array(np.uint64).reshape(R, wl.max_blocks)
+    t_pick, t_add, exact, hits = [], [], True, 0
+    t_cpu_pick = t_cpu_add = 0.0
+    tomb = []
     for step in range(args.steps):
         tok, offs = wl.prompts(batch=step)
+        pin_tok.array(np.uint32)[:] = tok.reshape(-1)
+        pin_off.array(np.uint64)[:] = offs
         t0 = time.perf_counter()
-        picks, chains = gpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+        gpu.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr, pin_ch.ptr)
         t1 = time.perf_counter()
-        for r in range(wl.R):
-            gpu.index_add_chain(int(picks[r, 0]["endpoint"]), chains[r, : int(picks[r, 0]["n_blocks"])])
-        gpu.index_sync()
+        ends = np.ascontiguousarray(picks_v[:, main_p]["endpoint"])
+        nbl = np.ascontiguousarray(picks_v[:, main_p]["n_blocks"]).astype(np.uint32)
+        gpu.index_add_chains(ends, chains_v, nbl)
         t2 = time.perf_counter()
-        if step:  # step 0 fills an empty index
-            t_pick += t1 - t0
-            t_add += t2 - t1
-        hits += int((picks["match_blocks"] > 0).sum())
-        if cpu is not None:
+        t_pick.append(t1 - t0)
+        t_add.append(t2 - t1)
+        hits += int((picks_v[:, main_p]["match_blocks"] > 0).sum())
+        if cpu is not None and step < args.oracle_steps:
+            c0 = time.perf_counter()
             want, wch = cpu.pick_batch(tok, offs, wl.h0, want_chains=True, nthreads=os.cpu_count() or 1)
-            exact = exact and picks.tobytes() == want.tobytes()
-            for r in range(wl.R):
-                cpu.index_add_chain(int(want[r, 0]["endpoint"]), wch[r, : int(want[r, 0]["n_blocks"])])
+            c1 = time.perf_counter()
+            exact = exact and picks_v.tobytes() == want.tobytes()
+            cpu.index_add_chains(want[:, main_p]["endpoint"], wch, want[:, main_p]["n_blocks"])
+            t_cpu_pick += c1 - c0
+            t_cpu_add += time.perf_counter() - c1
+        if step % 3 == 2 or step == args.steps - 1:
+            s = gpu.index_stats()  # (synchronises the index stream: kept out of the timed calls)
+            tomb.append({"step": step, "used": int(s.used), "tombstones": int(s.tombstones), "rebuilds": int(s.rebuilds)})
+    gpu.index_sync()
     st = gpu.index_stats()
-    n = wl.R * (args.steps - 1)
-    print(json.dumps({
-        "mode": "churn: pick + indexer.Add(chain, picked endpoint) per decision",
-        "requests_per_step": wl.R, "endpoints": wl.E, "prompt_tokens": wl.T, "lru_capacity": args.lru,
-        "steps_timed": args.steps - 1,
-        "decisions_per_s": n / (t_pick + t_add), "pick_ms_per_step": 1e3 * t_pick / (args.steps - 1),
-        "add_ms_per_step": 1e3 * t_add / (args.steps - 1),
-        "lru_touches_per_s": n * wl.n_blocks / t_add,
-        "index": {"slots": st.slots, "used": st.used, "tombstones": st.tombstones, "rebuilds": st.rebuilds,
-                  "ops_applied": st.ops_applied, "lru_entries": st.lru_entries},
-        "requests_with_prefix_hit": hits, "bit_exact_vs_oracle": (exact if cpu is not None else None),
-    }), flush=True)
+    tp, ta = np.array(t_pick[1:]), np.array(t_add[1:])  # step 0 warms the worker pool / first-touch pages
+    n = R * len(tp)
+    out = {
+        "mode": "churn: pick + indexer.Add(chain, picked endpoint) for every decision, LRUs at capacity",
+        "workload": f"cfg{args.cfg}: {R} req/step x {wl.E} endpoints x {wl.T}-token prompts, lruCapacityPerServer {wl.lru_capacity}",
+        "steps_timed": len(tp), "lru_threads": args.threads or "default (usable cores, <= 64)",
+        "decisions_per_s": n / float(tp.sum() + ta.sum()),
+        "pick_ms": {"p50": 1e3 * float(np.median(tp)), "p99": 1e3 * float(np.quantile(tp, 0.99)), "max": 1e3 * float(tp.max())},
+        "add_ms": {"p50": 1e3 * float(np.median(ta)), "p99": 1e3 * float(np.quantile(ta, 0.99)), "max": 1e3 * float(ta.max())},
+        "lru_touches_per_s": n * wl.n_blocks / float(ta.sum()),
+        "index": {"slots": int(st.slots), "used": int(st.used), "tombstones": int(st.tombstones), "rebuilds": int(st.rebuilds),
+                  "ops_applied": int(st.ops_applied), "lru_entries": int(st.lru_entries), "growth": tomb},
+        "requests_with_prefix_hit": hits,
+        "oracle": None if cpu is None else {
+            "steps_mirrored": min(args.oracle_steps, args.steps), "bit_exact": bool(exact),
+            "pick_ms_per_step": 1e3 * t_cpu_pick / max(min(args.oracle_steps, args.steps), 1),
+            "add_ms_per_step": 1e3 * t_cpu_add / max(min(args.oracle_steps, args.steps), 1),
+            "decisions_per_s": R * min(args.oracle_steps, args.steps) / max(t_cpu_pick + t_cpu_add, 1e-9),
+            "how": "oracle: multi-threaded pick, then indexer.Add one chain at a time on one thread (std::list + unordered_map LRU)"},
+    }
+    print(json.dumps(out), flush=True)
     gpu.close()
 
 
