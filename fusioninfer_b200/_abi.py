@@ -14,6 +14,9 @@ import os
 FI_EPP_ABI_VERSION = 2
 FI_EPP_MAX_PROFILES = 4
 FI_EPP_MAX_SCORERS = 4
+FI_EPP_MAX_FILTERS = 4
+FI_EPP_MAX_LABELS = 24
+FI_ROLE_FIRST_FREE = 8
 FI_EPP_MAX_BLOCKS = 1023
 FI_NO_ENDPOINT = 0xFFFFFFFF
 FI_EPP_UNIQUE_ID_BYTES = 128
@@ -54,6 +57,17 @@ class fi_profile(C.Structure):
         ("role_mask", C.c_uint32),
         ("n_scorers", C.c_uint32),
         ("scorers", fi_scorer * FI_EPP_MAX_SCORERS),
+        ("n_more_filters", C.c_uint32),
+        ("more_filters", C.c_uint32 * (FI_EPP_MAX_FILTERS - 1)),
+    ]
+
+
+class fi_label_bit(C.Structure):
+    _fields_ = [
+        ("label", C.c_char * 64),
+        ("value", C.c_char * 56),
+        ("bit", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -79,6 +93,9 @@ class fi_epp_config(C.Structure):
         ("pd_prefill_profile", C.c_uint32),
         ("pd_threshold", C.c_double),
         ("profiles", fi_profile * FI_EPP_MAX_PROFILES),
+        ("n_labels", C.c_uint32),
+        ("reserved1", C.c_uint32),
+        ("labels", fi_label_bit * FI_EPP_MAX_LABELS),
     ]
 
 

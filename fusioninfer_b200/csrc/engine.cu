@@ -1068,6 +1068,9 @@ int validate_config(const fi_epp_config& c, std::string* err) {
   if (c.n_profiles == 0 || c.n_profiles > FI_EPP_MAX_PROFILES) return bad("n_profiles out of range");
   for (uint32_t p = 0; p < c.n_profiles; ++p) {
     if (c.profiles[p].n_scorers > FI_EPP_MAX_SCORERS) return bad("n_scorers out of range");
+    if (c.profiles[p].n_more_filters > FI_EPP_MAX_FILTERS - 1) return bad("n_more_filters out of range");
+    for (uint32_t f = 0; f < c.profiles[p].n_more_filters; ++f)
+      if (c.profiles[p].more_filters[f] == 0) return bad("a by-label filter without label bits admits nothing");
     for (uint32_t s = 0; s < c.profiles[p].n_scorers; ++s) {
       const uint32_t k = c.profiles[p].scorers[s].kind;
       if (k != FI_SCORER_PREFIX && k != FI_SCORER_KV_UTIL && k != FI_SCORER_QUEUE && k != FI_SCORER_LORA)
@@ -1360,7 +1363,9 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   for (uint32_t p = 0; p < h->P; ++p) {
     ProfileDev& d = h->st.prof[p];
     d.n_scorers = cfg->profiles[p].n_scorers;
-    d.role_mask = cfg->profiles[p].role_mask;
+    d.n_filters = 0;
+    if (cfg->profiles[p].role_mask) d.filter[d.n_filters++] = cfg->profiles[p].role_mask;
+    for (uint32_t f = 0; f < cfg->profiles[p].n_more_filters; ++f) d.filter[d.n_filters++] = cfg->profiles[p].more_filters[f];
     for (uint32_t s = 0; s < d.n_scorers; ++s) {
       d.kind[s] = cfg->profiles[p].scorers[s].kind;
       d.weight[s] = (double)cfg->profiles[p].scorers[s].weight;

@@ -254,6 +254,32 @@ void set_err(char* err, size_t err_len, const std::string& m) {
 
 }  // namespace
 
+// role_mask bit of one (label, value) pair of a by-label filter; a new pair is appended to cfg.labels
+static uint32_t label_bit(fi_epp_config& cfg, const std::string& label, const std::string& value, uint32_t& next_bit) {
+  for (uint32_t i = 0; i < cfg.n_labels; ++i)
+    if (label == cfg.labels[i].label && value == cfg.labels[i].value) return cfg.labels[i].bit;
+  uint32_t bit = 0;
+  if (label == "fusioninfer.io/component-type") {
+    if (value == "worker") bit = FI_ROLE_WORKER;
+    else if (value == "prefiller") bit = FI_ROLE_PREFILLER;
+    else if (value == "decoder") bit = FI_ROLE_DECODER;
+  }
+  if (!bit) {
+    if (next_bit == 0) throw ParseError{"by-label: more than 29 distinct (label, value) pairs"};
+    bit = next_bit;
+    next_bit <<= 1;  // 0 after bit 31
+  }
+  if (cfg.n_labels >= FI_EPP_MAX_LABELS) throw ParseError{"by-label: too many (label, value) pairs"};
+  fi_label_bit& lb = cfg.labels[cfg.n_labels];
+  if (label.size() >= sizeof(lb.label)) throw ParseError{"by-label: label too long: " + label};
+  if (value.size() >= sizeof(lb.value)) throw ParseError{"by-label: value too long: " + value};
+  std::snprintf(lb.label, sizeof(lb.label), "%s", label.c_str());
+  std::snprintf(lb.value, sizeof(lb.value), "%s", value.c_str());
+  lb.bit = bit;
+  ++cfg.n_labels;
+  return bit;
+}
+
 extern "C" int fi_epp_config_from_yaml(const char* yaml, size_t len, fi_epp_config* cfg, char* err, size_t err_len) {
   if (!yaml || !cfg) {
     set_err(err, err_len, "null argument");
@@ -350,6 +376,9 @@ extern "C" int fi_epp_config_from_yaml(const char* yaml, size_t len, fi_epp_conf
     if (!sp || sp->kind != Node::LIST || sp->list.empty()) throw ParseError{"schedulingProfiles: must be a non-empty sequence"};
     if (sp->list.size() > FI_EPP_MAX_PROFILES) throw ParseError{"too many scheduling profiles"};
     bool have_decode = false, have_prefill = false;
+    uint32_t next_bit = FI_ROLE_FIRST_FREE;
+    out.n_labels = 0;
+    std::memset(out.labels, 0, sizeof(out.labels));
     for (auto& e : sp->list) {
       if (e->kind != Node::MAP) throw ParseError{"schedulingProfiles: entries must be mappings"};
       fi_profile& prof = out.profiles[out.n_profiles];
@@ -386,22 +415,26 @@ extern "C" int fi_epp_config_from_yaml(const char* yaml, size_t len, fi_epp_conf
         } else if (p->type == "max-score-picker") {
           has_picker = true;
         } else if (p->type == "by-label") {
-          // strategy.go:135-144: label "fusioninfer.io/component-type", validValues [prefiller|decoder]
+          // strategy.go:135-144 shows the schema: `label` + `validValues`.  Every (label, value) pair stands for
+          // one bit of the endpoints' role_mask: the component-type values keep their fixed bits, any other pair
+          // gets the next free one, recorded in cfg->labels for the host.  Filters of a profile are ANDed.
           if (!p->params) throw ParseError{"by-label " + p->name + ": missing parameters"};
           const Node* lab = p->params->get("label");
-          if (!lab || lab->scalar != "fusioninfer.io/component-type")
-            throw ParseError{"by-label " + p->name + ": only label fusioninfer.io/component-type is supported"};
+          if (!lab || lab->scalar.empty()) throw ParseError{"by-label " + p->name + ": missing label"};
           const Node* vv = p->params->get("validValues");
           if (!vv || vv->kind != Node::LIST || vv->list.empty())
             throw ParseError{"by-label " + p->name + ": validValues must be a non-empty sequence"};
           uint32_t mask = 0;
           for (auto& val : vv->list) {
-            if (val->scalar == "worker") mask |= FI_ROLE_WORKER;
-            else if (val->scalar == "prefiller") mask |= FI_ROLE_PREFILLER;
-            else if (val->scalar == "decoder") mask |= FI_ROLE_DECODER;
-            else throw ParseError{"by-label " + p->name + ": unknown component type " + val->scalar};
+            if (val->scalar.empty()) throw ParseError{"by-label " + p->name + ": empty value"};
+            mask |= label_bit(out, lab->scalar, val->scalar, next_bit);
           }
-          prof.role_mask = prof.role_mask ? (prof.role_mask & mask) : mask;
+          if (prof.role_mask == 0 && prof.n_more_filters == 0) {
+            prof.role_mask = mask;
+          } else {
+            if (prof.n_more_filters >= FI_EPP_MAX_FILTERS - 1) throw ParseError{"profile " + name + ": too many by-label filters"};
+            prof.more_filters[prof.n_more_filters++] = mask;
+          }
         } else {
           throw ParseError{"profile " + name + ": plugin " + p->name + " (" + p->type + ") cannot be used in a profile"};
         }

@@ -65,10 +65,19 @@ struct GossipLog {
 
 struct ProfileDev {
   uint32_t n_scorers;
-  uint32_t role_mask;
+  uint32_t n_filters;                    // by-label filters, ANDed (fi_profile: role_mask first, then more_filters)
+  uint32_t filter[FI_EPP_MAX_FILTERS];
   uint32_t kind[FI_EPP_MAX_SCORERS];
   double weight[FI_EPP_MAX_SCORERS];
 };
+
+// alive and carrying, for every filter of the profile, at least one of its label bits
+__host__ __device__ inline bool profile_admits(const ProfileDev& pr, uint32_t ep_flags, uint32_t ep_role_mask) {
+  if (!(ep_flags & FI_ENDPOINT_ALIVE)) return false;
+  for (uint32_t f = 0; f < pr.n_filters; ++f)
+    if (!(ep_role_mask & pr.filter[f])) return false;
+  return true;
+}
 
 // best total of a profile when no prefix block matches (per batch constant); the endpoints that attain it
 // are the bit words ScoreTables::ztie — which of them wins depends on the request's tie rotation

@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointD
     int mn = INT_MAX, mx = INT_MIN;
     for (uint32_t e = tid; e < E_global; e += blockDim.x) {
       const EndpointDev s = eps[e];
-      if ((s.flags & FI_ENDPOINT_ALIVE) && (pr.role_mask == 0 || (s.role_mask & pr.role_mask))) {
+      if (profile_admits(pr, s.flags, s.role_mask)) {
         mn = min(mn, s.queue_depth);
         mx = max(mx, s.queue_depth);
       }
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointD
       s.flags = 0;
       if (e < ep_count) {
         s = eps[ep_begin + e];
-        ok = (s.flags & FI_ENDPOINT_ALIVE) && (pr.role_mask == 0 || (s.role_mask & pr.role_mask));
+        ok = profile_admits(pr, s.flags, s.role_mask);
       }
       double tot = 0.0;
       for (uint32_t k = 0; k < pr.n_scorers; ++k) {

@@ -63,7 +63,7 @@ def make_config(
     pd: Optional[dict] = None,
     base: Optional[abi.fi_epp_config] = None,
 ) -> abi.fi_epp_config:
-    """Build a config in code.  profiles: [{"name", "role_mask", "scorers": [(kind, weight), ...]}].
+    """Build a config in code.  profiles: [{"name", "role_mask", "more_filters": [...], "scorers": [(kind, weight), ...]}].
     base: a pre-filled struct to start from instead of fi_epp_config_default() (then libfi_epp.so is not touched:
     bench.py's CPU reference arm builds its configuration without mapping the product library)."""
     cfg = base if base is not None else default_config()
@@ -84,6 +84,10 @@ def make_config(
             prof = cfg.profiles[i]
             prof.name = p.get("name", f"p{i}").encode()
             prof.role_mask = p.get("role_mask", 0)
+            more = list(p.get("more_filters", []))  # further by-label filters, ANDed with role_mask
+            prof.n_more_filters = len(more)
+            for j, f in enumerate(more):
+                prof.more_filters[j] = f
             sc = p["scorers"]
             prof.n_scorers = len(sc)
             for j, (kind, weight) in enumerate(sc):

@@ -62,6 +62,8 @@ extern "C" {
 #define FI_EPP_ABI_VERSION 2u
 #define FI_EPP_MAX_PROFILES 4u
 #define FI_EPP_MAX_SCORERS 4u
+#define FI_EPP_MAX_FILTERS 4u /* by-label filters per profile */
+#define FI_EPP_MAX_LABELS 24u /* (label, value) pairs a configuration can filter on */
 #define FI_EPP_MAX_BLOCKS 1023u /* counts are kept in 10 bit-planes on the GPU */
 #define FI_NO_ENDPOINT 0xFFFFFFFFu
 #define FI_EPP_UNIQUE_ID_BYTES 128u
@@ -90,12 +92,15 @@ typedef enum fi_scorer_kind {
   FI_SCORER_LORA = 4     /* lora-affinity-scorer         */
 } fi_scorer_kind;
 
-/* role bits: `fusioninfer.io/component-type` values (api/core/v1alpha1/
- * inferenceservice_types.go:26-33) that the by-label filters of
- * strategy.go:135-144 key on. */
+/* Label bits of an endpoint (fi_endpoint_state.role_mask) — what the by-label filters of strategy.go:135-144
+ * test.  The three `fusioninfer.io/component-type` values (api/core/v1alpha1/inferenceservice_types.go:26-33)
+ * have fixed bits; any other (label, value) pair a configuration filters on is given one of the bits from
+ * FI_ROLE_FIRST_FREE up by fi_epp_config_from_yaml, which records the assignment in fi_epp_config.labels —
+ * the host sets that bit on every pod carrying the label value when it calls fi_epp_endpoints_update. */
 #define FI_ROLE_WORKER 1u
 #define FI_ROLE_PREFILLER 2u
 #define FI_ROLE_DECODER 4u
+#define FI_ROLE_FIRST_FREE 8u
 
 #define FI_ENDPOINT_ALIVE 1u
 
@@ -106,10 +111,22 @@ typedef struct fi_scorer {
 
 typedef struct fi_profile {
   char name[32];      /* schedulingProfiles[].name */
-  uint32_t role_mask; /* by-label filter: endpoint eligible iff role_mask==0 or (ep.role_mask & role_mask) */
+  uint32_t role_mask; /* first by-label filter (0: none): the endpoint must carry one of these label bits */
   uint32_t n_scorers;
   fi_scorer scorers[FI_EPP_MAX_SCORERS]; /* in profile order: fp64 accumulation order */
+  /* further by-label filters of the profile.  Filters chain like upstream's filter plugins: an endpoint is
+   * eligible iff it is alive and passes EVERY filter f, i.e. (ep.role_mask & f) != 0. */
+  uint32_t n_more_filters;
+  uint32_t more_filters[FI_EPP_MAX_FILTERS - 1];
 } fi_profile;
+
+/* One (label, value) pair of a by-label filter and the endpoint bit that stands for it. */
+typedef struct fi_label_bit {
+  char label[64]; /* e.g. "fusioninfer.io/component-type" */
+  char value[56]; /* one of the filter's validValues */
+  uint32_t bit;   /* single bit of fi_endpoint_state.role_mask */
+  uint32_t reserved;
+} fi_label_bit;
 
 typedef struct fi_epp_config {
   uint32_t struct_size; /* sizeof(fi_epp_config), checked */
@@ -133,6 +150,10 @@ typedef struct fi_epp_config {
   uint32_t pd_prefill_profile;
   double pd_threshold;        /* `threshold:` — prefill runs iff (1-hit)*len(prompt) >= threshold */
   fi_profile profiles[FI_EPP_MAX_PROFILES];
+  /* written by fi_epp_config_from_yaml, read by the host: which role_mask bit each filtered (label, value) has */
+  uint32_t n_labels;
+  uint32_t reserved1;
+  fi_label_bit labels[FI_EPP_MAX_LABELS];
 } fi_epp_config;
 
 /* One row of the pod datastore the scorers read (upstream metrics refresh). */

@@ -288,9 +288,14 @@ struct Oracle {
   std::string err;
 };
 
-inline bool eligible(const EpState& e, uint32_t role_mask) {
+// upstream by-label filter plugins chain: a pod stays a candidate iff it is alive and every filter of the
+// profile finds one of its validValues among the pod's labels (/root/reference/pkg/router/strategy.go:135-144)
+inline bool eligible(const EpState& e, const fi_profile& p) {
   if (!(e.flags & FI_ENDPOINT_ALIVE)) return false;
-  return role_mask == 0 || (e.role_mask & role_mask) != 0;
+  if (p.role_mask != 0 && (e.role_mask & p.role_mask) == 0) return false;
+  for (uint32_t f = 0; f < p.n_more_filters; ++f)
+    if ((e.role_mask & p.more_filters[f]) == 0) return false;
+  return true;
 }
 
 inline double clamp01(double s) { return s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s); }
@@ -305,7 +310,7 @@ struct ProfileCtx {
 ProfileCtx make_ctx(const Oracle& o, const fi_profile& p) {
   ProfileCtx c;
   for (const EpState& e : o.eps) {
-    if (!eligible(e, p.role_mask)) continue;
+    if (!eligible(e, p)) continue;
     if (!c.any) {
       c.min_q = c.max_q = e.queue_depth;
       c.any = true;
@@ -430,7 +435,7 @@ void pick_one(const Oracle& o, const std::vector<ProfileCtx>& ctx, const uint8_t
     uint32_t best_e = FI_NO_ENDPOINT;
     for (uint32_t e = 0; e < E; ++e) {  // max total; equal totals: the request's tie rotation decides
       const EpState& es = o.eps[e];
-      if (!eligible(es, prof.role_mask)) continue;
+      if (!eligible(es, prof)) continue;
       double t = total_score(prof, ctx[p], es, sc.match[e], n, adapter);
       if (best_e == FI_NO_ENDPOINT || t > best ||
           (t == best && tie_distance(e, start, E) < tie_distance(best_e, start, E))) {

@@ -52,7 +52,7 @@ def tie_start(n_blocks: int, first_hash: int, h0: int, r: int, E: int) -> int:
 
 class Restatement:
     def __init__(self, num_endpoints, block_bytes, max_blocks, profiles, pd=None, lpm=False, lru_capacity=0):
-        """profiles: [{"role_mask": int, "scorers": [(kind, weight), ...]}]; pd: {"decode", "prefill", "threshold"}"""
+        """profiles: [{"filters": [label-bit masks, ANDed], "scorers": [(kind, weight), ...]}]; pd: {"decode", "prefill", "threshold"}"""
         self.E, self.B, self.M = num_endpoints, block_bytes, max_blocks
         self.profiles, self.pd, self.lpm = profiles, pd, lpm
         self.index = {}  # hash -> set of endpoints
@@ -118,11 +118,11 @@ class Restatement:
         return counts
 
     # ---- A.4
-    def _eligible(self, e, role_mask):
+    def _eligible(self, e, prof):
         st = self.state.get(e)
         if st is None or not (st["flags"] & ALIVE):
             return False
-        return role_mask == 0 or (st["role_mask"] & role_mask) != 0
+        return all(st["role_mask"] & f for f in prof.get("filters", []))
 
     def _lora_score(self, e, adapter):
         mx, act, wai = self.lora.get(e, (0, [], []))
@@ -140,7 +140,7 @@ class Restatement:
         h0 = np.broadcast_to(np.asarray(h0, dtype=np.uint64), (R,))
         qctx = []
         for prof in self.profiles:
-            qs = [self.state[e]["queue"] for e in range(self.E) if self._eligible(e, prof.get("role_mask", 0))]
+            qs = [self.state[e]["queue"] for e in range(self.E) if self._eligible(e, prof)]
             qctx.append((min(qs), max(qs)) if qs else (0, 0))
         for r in range(R):
             p = raw[int(offsets[r]):int(offsets[r + 1])]
@@ -153,7 +153,7 @@ class Restatement:
                 best = None
                 mn, mx = qctx[pi]
                 for e in range(self.E):
-                    if not self._eligible(e, prof.get("role_mask", 0)):
+                    if not self._eligible(e, prof):
                         continue
                     st = self.state[e]
                     m = counts.get(e, 0)
@@ -189,7 +189,8 @@ def from_config(cfg, lpm=None):
     profiles = []
     for i in range(cfg.n_profiles):
         p = cfg.profiles[i]
-        profiles.append({"role_mask": int(p.role_mask),
+        filters = ([int(p.role_mask)] if p.role_mask else []) + [int(p.more_filters[f]) for f in range(p.n_more_filters)]
+        profiles.append({"filters": filters,
                          "scorers": [(int(p.scorers[j].kind), int(p.scorers[j].weight)) for j in range(p.n_scorers)]})
     pd = None
     if cfg.pd_enabled:

@@ -35,7 +35,8 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(abi.fi_index_op) == 16
     assert C.sizeof(abi.fi_endpoint_state) == 24
     assert C.sizeof(abi.fi_scorer) == 8
-    assert C.sizeof(abi.fi_profile) == 32 + 8 + 8 * abi.FI_EPP_MAX_SCORERS
+    assert C.sizeof(abi.fi_profile) == 32 + 8 + 8 * abi.FI_EPP_MAX_SCORERS + 4 * abi.FI_EPP_MAX_FILTERS
+    assert C.sizeof(abi.fi_label_bit) == 128
     cfg = default_config()
     assert cfg.struct_size == C.sizeof(abi.fi_epp_config)  # the library's own sizeof
 

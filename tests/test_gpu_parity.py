@@ -642,3 +642,26 @@ def test_add_chains_batch_equals_sequential_oracle(threads, monkeypatch):
     stt = gpu.index_stats()
     assert stt.lru_entries <= wl.E * 70 and stt.tombstones > 0
     gpu.close()
+
+
+def test_chained_label_filters_third_label():
+    """by-label generalised: profiles with several ANDed filters over component-type AND two
+    other labels' bits; disjoint filters admit nothing.  GPU == oracle."""
+    wl = H.small_workload(E=200, R=128)
+    prof = [{"name": "a", "role_mask": 1 | 4, "more_filters": [8 | 16, 32], "scorers": [(P, 60), (Q, 40)]},
+            {"name": "b", "role_mask": 2, "more_filters": [4], "scorers": [(K, 1)]},
+            {"name": "c", "role_mask": 0, "more_filters": [16], "scorers": [(P, 100), (K, 3)]}]
+    cfg = H.config_for(wl, profiles=prof)
+    gpu, cpu = _pair(cfg)
+    st = wl.endpoint_states()
+    rng = np.random.default_rng(9)
+    st["role_mask"] = (1 << rng.integers(0, 3, size=wl.E)) | (8 << rng.integers(0, 2, size=wl.E)) | np.where(rng.random(wl.E) < 0.7, 32, 0)
+    _load(wl, gpu, cpu, states=st)
+    tok, offs = wl.prompts()
+    got = gpu.pick_batch(tok, offs, wl.h0)
+    want = cpu.pick_batch(tok, offs, wl.h0)
+    assert H.picks_equal(got, want), H.describe_diff(got, want)
+    ok = ((st["role_mask"] & 5) != 0) & ((st["role_mask"] & 24) != 0) & ((st["role_mask"] & 32) != 0)
+    assert ok[got[:, 0]["endpoint"]].all() and (got[:, 1]["endpoint"] == abi.FI_NO_ENDPOINT).all()
+    assert ((st["role_mask"][got[:, 2]["endpoint"]] & 16) != 0).all()
+    gpu.close()

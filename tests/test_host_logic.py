@@ -342,3 +342,61 @@ def test_tie_rotation_arithmetic_of_the_kernels(hc):
         got = hc.fihc_tie_first_local(words.ctypes.data, W, start, ep_begin, ep_count)
         want = min(members, key=lambda e: (e + ep_begin - start) % E) if members else 0xFFFFFFFF
         assert got == want, (W, ep_begin, ep_count, start, members[:8], got, want)
+
+
+LABELS_YAML = """apiVersion: inference.networking.x-k8s.io/v1alpha1
+kind: EndpointPickerConfig
+plugins:
+- type: prefix-cache-scorer
+  parameters:
+    hashBlockSize: 64
+- type: queue-scorer
+- type: max-score-picker
+- type: by-label
+  name: decode-role
+  parameters:
+    label: "fusioninfer.io/component-type"
+    validValues: ["decoder", "worker"]
+- type: by-label
+  name: zone-filter
+  parameters:
+    label: "topology.kubernetes.io/zone"
+    validValues: ["us-east-1a", "us-east-1b"]
+- type: by-label
+  name: gpu-filter
+  parameters:
+    label: "nvidia.com/gpu.product"
+    validValues: ["B200"]
+schedulingProfiles:
+- name: default
+  plugins:
+  - pluginRef: decode-role
+  - pluginRef: zone-filter
+  - pluginRef: gpu-filter
+  - pluginRef: max-score-picker
+  - pluginRef: prefix-cache-scorer
+    weight: 70
+  - pluginRef: queue-scorer
+    weight: 30
+"""
+
+
+def test_config_by_label_with_arbitrary_labels_and_chained_filters():
+    """strategy.go:135-144 gives the by-label schema (label + validValues); SURVEY §8(f)3 asks for arbitrary
+    label sets.  Component-type values keep their fixed bits, other (label, value) pairs get the next free bit,
+    the assignment is reported in cfg.labels, and several filters in one profile are ANDed."""
+    cfg = config_from_yaml(LABELS_YAML)
+    p = cfg.profiles[0]
+    assert p.role_mask == abi.FI_ROLE_DECODER | abi.FI_ROLE_WORKER
+    assert p.n_more_filters == 2
+    table = {(cfg.labels[i].label.decode(), cfg.labels[i].value.decode()): cfg.labels[i].bit for i in range(cfg.n_labels)}
+    assert table[("fusioninfer.io/component-type", "decoder")] == abi.FI_ROLE_DECODER
+    assert table[("fusioninfer.io/component-type", "worker")] == abi.FI_ROLE_WORKER
+    za, zb = table[("topology.kubernetes.io/zone", "us-east-1a")], table[("topology.kubernetes.io/zone", "us-east-1b")]
+    gb = table[("nvidia.com/gpu.product", "B200")]
+    assert {za, zb, gb} == {8, 16, 32} and p.more_filters[0] == za | zb and p.more_filters[1] == gb
+    # two filters on the same label with disjoint values: ANDed -> nothing passes (round 1 read that as "no filter")
+    doc = PD_YAML.replace("  - pluginRef: prefill-pods\n", "  - pluginRef: prefill-pods\n  - pluginRef: decode-pods\n", 1)
+    cfg2 = config_from_yaml(doc)
+    pf = cfg2.profiles[cfg2.pd_prefill_profile]
+    assert pf.role_mask == abi.FI_ROLE_PREFILLER and pf.n_more_filters == 1 and pf.more_filters[0] == abi.FI_ROLE_DECODER

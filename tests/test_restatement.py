@@ -212,3 +212,22 @@ def test_tie_rotation_spreads_cold_requests():
         if shared[q]:
             first.setdefault(int(groups[q]), set()).add(int(got[q, 0]["endpoint"]))
     assert all(len(v) == 1 for v in first.values())
+
+
+def test_chained_label_filters():
+    """Several by-label filters in one profile are ANDed (upstream filter plugins chain): oracle == restatement,
+    and a disjoint pair admits nothing."""
+    wl = H.small_workload(E=30, R=40)
+    prof = [{"name": "a", "role_mask": 1 | 4, "more_filters": [8 | 16, 32], "scorers": [(P, 60), (Q, 40)]},
+            {"name": "b", "role_mask": 2, "more_filters": [4], "scorers": [(K, 1)]}]
+    cfg = H.config_for(wl, profiles=prof)
+    st = wl.endpoint_states()
+    rng = np.random.default_rng(9)
+    st["role_mask"] = (1 << rng.integers(0, 3, size=30)) | (8 << rng.integers(0, 2, size=30)) | np.where(rng.random(30) < 0.7, 32, 0)
+    o, r = _both(cfg, wl, states=st)
+    tok, offs = wl.prompts()
+    got = o.pick_batch(tok, offs, wl.h0)
+    _same(got, r.pick(tok, offs, wl.h0))
+    ok = ((st["role_mask"] & 5) != 0) & ((st["role_mask"] & 24) != 0) & ((st["role_mask"] & 32) != 0)
+    assert ok.any() and ok[got[:, 0]["endpoint"]].all()
+    assert (got[:, 1]["endpoint"] == abi.FI_NO_ENDPOINT).all()  # bits 2 and 4 are never set together here
