@@ -212,6 +212,8 @@ struct fi_epp {
   cudaEvent_t ev_pick = nullptr;   // completion of the most recent pick of any kind on s_main
   cudaEvent_t ev_plain = nullptr;  // completion of the most recent stream-ordered (not pipelined) pick
   uint64_t pipe_seq = 0;          // batches submitted
+  uint32_t pipe_hash_ctas = 0;    // per-SM caps of the pipelined path's two co-running kernels (0 = uncapped);
+  uint32_t pipe_match_ctas = 0;   // FI_EPP_PIPE_HASH_CTAS / FI_EPP_PIPE_MATCH_CTAS, option "pipe_hash_ctas" / "pipe_match_ctas"
   cudaEvent_t ev_index = nullptr, ev_user = nullptr, ev_done = nullptr, ev_ctr = nullptr;
 
   // request buffers (device)
@@ -641,7 +643,7 @@ int run_hash(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
   if (h->fast_hash) {
     {
       LaunchScope ls(h, s, K_HASH);
-      FI_CUDA(launch_hash_blocks(d_prompts, d_offsets + r0, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, pre, nb, s));
+      FI_CUDA(launch_hash_blocks(d_prompts, d_offsets + r0, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, pre, nb, 0, s));
     }
     LaunchScope ls(h, s, K_CHAIN);
     FI_CUDA(launch_chain_finalize(pre, nb, d_h0 + r0, R, h->MP, chain, s));
@@ -1017,7 +1019,11 @@ int submit_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, 
   FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_plain, 0));
   {
     LaunchScope ls(h, h->s_a, K_HASH);
-    FI_CUDA(launch_hash_blocks(d_prompts, d_offsets, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, h->d_pre, nb, h->s_a));
+    // The SM split of the pipeline: this batch's block hashing runs BESIDE the previous batch's match_pick —
+    // hash_blocks as at most pipe_hash_ctas CTAs per SM, match_pick as at most pipe_match_ctas (its three CTAs of
+    // 79 registers would leave no room) — instead of one after the other.
+    FI_CUDA(launch_hash_blocks(d_prompts, d_offsets, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, h->d_pre, nb,
+                               h->pipe_hash_ctas * (uint32_t)h->sm_count, h->s_a));
   }
   // The chain walk is serial latency — a warp per scheduler that wants an issue slot every few cycles — and
   // runs 3x slower next to a busy kernel (measured: 30 -> 100 us under match_pick), so it waits for the
@@ -1038,6 +1044,7 @@ int submit_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, 
   MatchParams mp{};
   fill_match_params(h, mp, chain, nb, d_offsets, d_h0, nullptr, R, d_out, true);
   mp.work_counter = h->d_work + 8 + slot;
+  mp.max_ctas_per_sm = h->pipe_match_ctas;
   {
     LaunchScope ls(h, h->s_main, K_MATCH);
     FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
@@ -1268,6 +1275,8 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   h->W = pow2_ceil32((cfg->endpoint_count + 31) / 32);
   h->fast_hash = (cfg->block_bytes % 32) == 0;
   if (const char* e = std::getenv("FI_EPP_TRACE")) h->trace_call = std::strtol(e, nullptr, 10);
+  if (const char* e = std::getenv("FI_EPP_PIPE_HASH_CTAS")) h->pipe_hash_ctas = (uint32_t)std::strtol(e, nullptr, 10);
+  if (const char* e = std::getenv("FI_EPP_PIPE_MATCH_CTAS")) h->pipe_match_ctas = (uint32_t)std::strtol(e, nullptr, 10);
   if (h->cfg.max_prompt_bytes == 0)
     h->cfg.max_prompt_bytes = (uint64_t)cfg->max_batch * cfg->block_bytes * cfg->max_blocks;
   if (h->cfg.index_slots == 0) {
@@ -2060,6 +2069,11 @@ int fi_epp_set_option(fi_epp* h, const char* name, int64_t value) {
   if (n == "feed_slices") {
     if (value < 1 || value > fi_epp::kMaxFeedSlices) return fail(h, FI_ERR_INVALID, "feed_slices: 1..16");
     h->feed_slices = (uint32_t)value;
+    return FI_OK;
+  }
+  if (n == "pipe_hash_ctas" || n == "pipe_match_ctas") {
+    if (value < 0 || value > 32) return fail(h, FI_ERR_INVALID, n + ": 0..32");
+    (n == "pipe_hash_ctas" ? h->pipe_hash_ctas : h->pipe_match_ctas) = (uint32_t)value;
     return FI_OK;
   }
   if (n == "lru_threads") {

@@ -46,50 +46,53 @@ __device__ __forceinline__ uint64_t pre_index(uint32_t r, uint32_t i, uint32_t M
 
 template <int STRIPES>
 __global__ void __launch_bounds__(256) hash_blocks_kernel(const uint8_t* __restrict__ prompts,
-                                                          const uint64_t* __restrict__ offsets, uint32_t M,
+                                                          const uint64_t* __restrict__ offsets, uint32_t R, uint32_t M,
                                                           uint32_t MP, uint64_t* __restrict__ pre,
                                                           uint32_t* __restrict__ nblocks) {
   constexpr uint32_t B = STRIPES * 32;
-  const uint32_t r = blockIdx.x;
-  const uint64_t off = offsets[r];
-  const uint64_t len = offsets[r + 1] - off;
-  const uint64_t nb64 = len / B;
-  const uint32_t n = nb64 > M ? M : (uint32_t)nb64;
-  if (threadIdx.x == 0) nblocks[r] = n;
-  const uint8_t* base = prompts + off;
   const uint32_t MP2 = MP / 2;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
-    const uint64_t pol = make_evict_first_policy();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint4* p = reinterpret_cast<const uint4*>(base + (uint64_t)i * B);
-      uint4 q[2 * STRIPES];
+  const uint64_t pol = make_evict_first_policy();
+  // one request per CTA pass; the grid is R CTAs, or capped when the kernel has to share the SMs with the
+  // previous batch's match_pick (pipelined API)
+  for (uint32_t r = blockIdx.x; r < R; r += gridDim.x) {
+    const uint64_t off = offsets[r];
+    const uint64_t len = offsets[r + 1] - off;
+    const uint64_t nb64 = len / B;
+    const uint32_t n = nb64 > M ? M : (uint32_t)nb64;
+    if (threadIdx.x == 0) nblocks[r] = n;
+    const uint8_t* base = prompts + off;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint4* p = reinterpret_cast<const uint4*>(base + (uint64_t)i * B);
+        uint4 q[2 * STRIPES];
 #pragma unroll
-      for (int s = 0; s < 2 * STRIPES; ++s) q[s] = ld_stream_v4(p + s, pol);
-      XAcc a = xacc_init();
+        for (int s = 0; s < 2 * STRIPES; ++s) q[s] = ld_stream_v4(p + s, pol);
+        XAcc a = xacc_init();
 #pragma unroll
-      for (int s = 0; s < STRIPES; ++s)
-        xacc_stripe(a, pack64(q[2 * s].x, q[2 * s].y), pack64(q[2 * s].z, q[2 * s].w),
-                    pack64(q[2 * s + 1].x, q[2 * s + 1].y), pack64(q[2 * s + 1].z, q[2 * s + 1].w));
-      pre[pre_index(r, i, MP2)] = xacc_finish(a, (uint64_t)B + 8);
-    }
-  } else {
-    // arbitrary byte alignment: aligned 64-bit windows + funnel shift
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const uintptr_t addr = reinterpret_cast<uintptr_t>(base + (uint64_t)i * B);
-      const uint64_t* wp = reinterpret_cast<const uint64_t*>(addr & ~(uintptr_t)7);
-      const uint32_t sh = (uint32_t)(addr & 7) * 8;
-      uint64_t w[4 * STRIPES + 1];
-#pragma unroll
-      for (int k = 0; k < 4 * STRIPES; ++k) w[k] = __ldg(wp + k);
-      w[4 * STRIPES] = sh ? __ldg(wp + 4 * STRIPES) : 0;
-      if (sh) {
-#pragma unroll
-        for (int k = 0; k < 4 * STRIPES; ++k) w[k] = (w[k] >> sh) | (w[k + 1] << (64 - sh));
+        for (int s = 0; s < STRIPES; ++s)
+          xacc_stripe(a, pack64(q[2 * s].x, q[2 * s].y), pack64(q[2 * s].z, q[2 * s].w),
+                      pack64(q[2 * s + 1].x, q[2 * s + 1].y), pack64(q[2 * s + 1].z, q[2 * s + 1].w));
+        pre[pre_index(r, i, MP2)] = xacc_finish(a, (uint64_t)B + 8);
       }
-      XAcc a = xacc_init();
+    } else {
+      // arbitrary byte alignment: aligned 64-bit windows + funnel shift
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(base + (uint64_t)i * B);
+        const uint64_t* wp = reinterpret_cast<const uint64_t*>(addr & ~(uintptr_t)7);
+        const uint32_t sh = (uint32_t)(addr & 7) * 8;
+        uint64_t w[4 * STRIPES + 1];
 #pragma unroll
-      for (int s = 0; s < STRIPES; ++s) xacc_stripe(a, w[4 * s], w[4 * s + 1], w[4 * s + 2], w[4 * s + 3]);
-      pre[pre_index(r, i, MP2)] = xacc_finish(a, (uint64_t)B + 8);
+        for (int k = 0; k < 4 * STRIPES; ++k) w[k] = __ldg(wp + k);
+        w[4 * STRIPES] = sh ? __ldg(wp + 4 * STRIPES) : 0;
+        if (sh) {
+#pragma unroll
+          for (int k = 0; k < 4 * STRIPES; ++k) w[k] = (w[k] >> sh) | (w[k + 1] << (64 - sh));
+        }
+        XAcc a = xacc_init();
+#pragma unroll
+        for (int s = 0; s < STRIPES; ++s) xacc_stripe(a, w[4 * s], w[4 * s + 1], w[4 * s + 2], w[4 * s + 3]);
+        pre[pre_index(r, i, MP2)] = xacc_finish(a, (uint64_t)B + 8);
+      }
     }
   }
 }
@@ -134,20 +137,21 @@ __global__ void __launch_bounds__(256) hash_blocks_any_kernel(const uint8_t* __r
 
 // One lane per request, one warp per group of 32 requests: h_i = chain_step(pre_i, h_{i-1}), in
 // groups of 8 links.  The walk is a pure dependency chain — 40 integer instructions per link, 5 dependent
-// 64-bit multiplies, ~110 cycles by ptxas' own stall counts — run by ONE warp per scheduler, so every
-// other instruction in the loop and every exposed memory latency adds straight to the batch's critical
-// path (ncu, round 1: 59 instructions and 222 cycles per link).  Hence:
+// 64-bit multiplies, ~110 cycles by ptxas' own stall counts — run by ONE warp per scheduler, in order: every
+// other instruction in the loop and every scoreboard wait adds straight to the batch's critical path (ncu,
+// round 1: 59 instructions and 222 cycles per link).  What the loop is built around:
 //   * pre-states are prefetched kAhead groups ahead with cp.async into a shared-memory ring (register
 //     prefetching does not work: ptxas puts every ring load on one counting scoreboard, so waiting for the
 //     oldest also waits for the newest; cp.async commit/wait groups have the needed "all but the N newest"
-//     semantics), and the ring is read into registers one group EARLY, so neither the wait nor the
-//     shared-memory latency sits between two links;
-//   * each lane stores its 8 hashes straight to its chain row as four 16-byte stores (row-major [r][i]:
-//     what the match kernel stages and chains_out returns).  The 32 rows of a warp are 32 separate 64-byte
-//     segments; the stores are posted and L2 merges the half-sector pairs, which costs nothing on the chain —
-//     the round-1 version transposed through shared memory (2 barriers, 8 shared accesses and 4 predicated
-//     stores per group: a third of the kernel's instructions);
-//   * the buffers are padded to whole groups (MP % 8 == 0), so the loop has no per-unit predicates.
+//     semantics), and the ring is read into registers one group EARLY (volatile ld.shared at the top of the
+//     iteration), so neither the wait nor the shared-memory latency sits between two links;
+//   * each lane stores its 8 hashes straight to its chain row as four 16-byte stores (row-major [r][i]: what
+//     the match kernel stages and chains_out returns) — but one group LATE, at the top of the next iteration,
+//     from registers nothing else writes for a whole group.  Stored right after the links (first version of
+//     this kernel: 197 cycles per link) the four scattered STG.128 shared one set of data registers, and each
+//     had to wait for the previous one's operand read behind 32 L1 wavefronts;
+//   * the loop is unrolled by two groups with the register roles swapped, so no buffer is ever copied;
+//   * the buffers are padded to whole groups (MP % 8 == 0): no per-unit predicates.
 // Entries [n, MP) of every row are zeroed.
 constexpr int kRing = 4;   // ring slots
 constexpr int kAhead = 3;  // prefetch distance in groups (= kRing - 1)
@@ -163,6 +167,12 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 __device__ __forceinline__ void st_row16(ulonglong2* p, const ulonglong2& v) {
   asm volatile("st.global.v2.u64 [%0], {%1, %2};\n" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+__device__ __forceinline__ ulonglong2 lds16(const ulonglong2* p) {
+  ulonglong2 v;
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];\n" : "=l"(v.x), "=l"(v.y) : "r"(sa) : "memory");
+  return v;
 }
 
 // Four warps (128 requests) per CTA, one per SM sub-partition.
@@ -184,9 +194,8 @@ __global__ void __launch_bounds__(kChainWarps * 32) chain_finalize_kernel(const 
   const uint32_t MP2 = MP / 2;  // 16-byte units per row; MP % 8 == 0: whole groups of 4 units
   const ulonglong2* p = reinterpret_cast<const ulonglong2*>(pre) + ((uint64_t)grp * MP2) * 32 + lane;  // unit u at p[u*32]
   ulonglong2* out = reinterpret_cast<ulonglong2*>(chain) + (uint64_t)(valid ? r : 0) * MP2;
-  const uint32_t ng_tot = MP2 / 4;
-  uint32_t ng_warp = (n + 7) / 8;           // groups that need arithmetic: warp-uniform maximum ...
-  uint32_t ng_full = valid ? n / 8 : 0;     // ... and the groups in which every lane has 8 blocks: minimum
+  uint32_t ng_warp = (n + 7) / 8;        // groups that need arithmetic: warp-uniform maximum ...
+  uint32_t ng_full = valid ? n / 8 : 0;  // ... and the groups in which every lane has 8 blocks: minimum
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     ng_warp = max(ng_warp, __shfl_xor_sync(0xFFFFFFFFu, ng_warp, d));
@@ -205,56 +214,85 @@ __global__ void __launch_bounds__(kChainWarps * 32) chain_finalize_kernel(const 
 #pragma unroll
   for (int s = 0; s < kAhead; ++s) issue((uint32_t)s);
 
-  ulonglong2 cur[4], nxt[4];
+  ulonglong2 inA[4], inB[4], outA[4], outB[4];
   cp_async_wait<kAhead - 1>();  // group 0 has landed (a lane reads only its own copies: no barrier)
 #pragma unroll
-  for (int k = 0; k < 4; ++k) cur[k] = ring[0][k][lane];
+  for (int k = 0; k < 4; ++k) inA[k] = lds16(&ring[0][k][lane]);
 
-  uint32_t g = 0;
-  // ---- groups in which every lane of the warp has all 8 blocks: nothing but the links on the chain
-#pragma unroll 1
-  for (; g < ng_full; ++g) {
-    issue(g + kAhead);            // refills the slot whose registers were taken one iteration ago
-    cp_async_wait<kAhead - 1>();  // group g + 1 has landed; its registers are needed only next iteration
+  // one group: refill the ring, store the PREVIOUS group's hashes (if any), fetch the NEXT group's pre-states
+  // into `nxt`, then the 8 links of `cur` into `res`
+  auto group = [&](uint32_t g, const ulonglong2 (&cur)[4], ulonglong2 (&nxt)[4], const ulonglong2 (&prev)[4],
+                   ulonglong2 (&res)[4], bool store_prev) {
+    issue(g + kAhead);  // refills the slot whose registers were taken one group ago
+    if (store_prev && valid) {
+      ulonglong2* o = out + (g - 1) * 4;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) nxt[k] = ring[(g + 1) % kRing][k][lane];
-    ulonglong2* o = out + g * 4;
+      for (int k = 0; k < 4; ++k) st_row16(o + k, prev[k]);
+    }
+    cp_async_wait<kAhead - 1>();  // group g + 1 has landed; its registers are needed only by the next group
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nxt[k] = lds16(&ring[(g + 1) % kRing][k][lane]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      ulonglong2 v;
       h = chain_step(cur[k].x, h);
-      v.x = h;
+      res[k].x = h;
       h = chain_step(cur[k].y, h);
-      v.y = h;
-      if (valid) st_row16(o + k, v);
+      res[k].y = h;
     }
+  };
+
+  uint32_t g = 0;
+  bool pending = false;  // outA / outB of group g - 1 not stored yet (which one: parity of g)
+  // ---- groups in which every lane of the warp has all 8 blocks, two per iteration (A/B roles swap)
+  if (ng_full >= 1) {
+    group(0, inA, inB, outB, outA, false);
+    g = 1;
+    pending = true;
+#pragma unroll 1
+    for (; g + 1 < ng_full; g += 2) {
+      group(g, inB, inA, outA, outB, true);
+      group(g + 1, inA, inB, outB, outA, true);
+    }
+    if (g < ng_full) {  // one more (odd position): B in, A out
+      group(g, inB, inA, outA, outB, true);
+      ++g;
+      // bring the roles back to "next input in inA, last output in outA"
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+      for (int k = 0; k < 4; ++k) outA[k] = outB[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) inA[k] = inB[k];
+    }
   }
-  // ---- ragged groups: some lane's chain ends inside
+  if (pending && valid) {
+    ulonglong2* o = out + (g - 1) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st_row16(o + k, outA[k]);
+  }
+  // ---- ragged groups: some lane's chain ends inside (next input is in inA)
 #pragma unroll 1
   for (; g < ng_warp; ++g) {
     issue(g + kAhead);
     cp_async_wait<kAhead - 1>();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) nxt[k] = ring[(g + 1) % kRing][k][lane];
+    for (int k = 0; k < 4; ++k) inB[k] = lds16(&ring[(g + 1) % kRing][k][lane]);
     ulonglong2* o = out + g * 4;
     const uint32_t i0 = g * 8;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       ulonglong2 v;
-      uint64_t t = chain_step(cur[k].x, h);
+      uint64_t t = chain_step(inA[k].x, h);
       const bool v0 = i0 + 2 * k < n;
       h = v0 ? t : h;
       v.x = v0 ? t : 0;
-      t = chain_step(cur[k].y, h);
+      t = chain_step(inA[k].y, h);
       const bool v1 = i0 + 2 * k + 1 < n;
       h = v1 ? t : h;
       v.y = v1 ? t : 0;
       if (valid) st_row16(o + k, v);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+    for (int k = 0; k < 4; ++k) inA[k] = inB[k];
   }
   cp_async_wait<0>();
   // ---- the rest of every row is zero
@@ -262,7 +300,6 @@ __global__ void __launch_bounds__(kChainWarps * 32) chain_finalize_kernel(const 
     const ulonglong2 z = make_ulonglong2(0, 0);
     for (uint32_t u = g * 4; u < MP2; ++u) st_row16(out + u, z);
   }
-  (void)ng_tot;
 }
 
 // Fully serial path for block sizes that are not a multiple of 32.
@@ -292,16 +329,17 @@ __global__ void __launch_bounds__(128) hash_generic_kernel(const uint8_t* __rest
 }  // namespace
 
 cudaError_t launch_hash_blocks(const uint8_t* prompts, const uint64_t* offsets, uint32_t R, uint32_t B, uint32_t M,
-                               uint32_t MP, uint64_t* pre, uint32_t* nblocks, cudaStream_t s) {
+                               uint32_t MP, uint64_t* pre, uint32_t* nblocks, uint32_t grid_cap, cudaStream_t s) {
   if (R == 0) return cudaSuccess;
   uint32_t threads = (M + 31) / 32 * 32;
   if (threads > 256) threads = 256;
+  const uint32_t grid = (grid_cap && grid_cap < R) ? grid_cap : R;
   if (B == 64)
-    hash_blocks_kernel<2><<<R, threads, 0, s>>>(prompts, offsets, M, MP, pre, nblocks);
+    hash_blocks_kernel<2><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks);
   else if (B == 32)
-    hash_blocks_kernel<1><<<R, threads, 0, s>>>(prompts, offsets, M, MP, pre, nblocks);
+    hash_blocks_kernel<1><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks);
   else if (B == 128)
-    hash_blocks_kernel<4><<<R, threads, 0, s>>>(prompts, offsets, M, MP, pre, nblocks);
+    hash_blocks_kernel<4><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks);
   else
     hash_blocks_any_kernel<<<R, threads, 0, s>>>(prompts, offsets, B, M, MP, pre, nblocks);
   return cudaGetLastError();

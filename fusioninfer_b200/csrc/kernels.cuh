@@ -154,6 +154,7 @@ struct MatchParams {
   unsigned long long* probed_blocks;  // optional Σ N_probe
   uint32_t* work_counter;             // dynamic request queue of the launch
   uint32_t zero_work_counter;         // launcher zeroes it first (0: the caller already did)
+  uint32_t max_ctas_per_sm;           // 0: as many as fit; else a cap (pipelined API: leave room for hash_blocks)
   uint32_t lane_zero;                 // always 0: makes the ticket address formally lane-dependent (match_kernels.cu take_ticket)
   PeerXchg px;                        // sharded mode, peer-memory exchange (px.enabled)
 };
@@ -173,8 +174,10 @@ struct MergeParams {
 };
 
 // ---- launchers (each returns the cudaGetLastError() of its launch) -----------
+// grid_cap: 0 = one CTA per request; else at most that many CTAs (the pipelined API shares the SMs with match_pick)
 cudaError_t launch_hash_blocks(const uint8_t* prompts, const uint64_t* offsets, uint32_t R, uint32_t B,
-                               uint32_t M, uint32_t MP, uint64_t* pre, uint32_t* nblocks, cudaStream_t s);
+                               uint32_t M, uint32_t MP, uint64_t* pre, uint32_t* nblocks, uint32_t grid_cap,
+                               cudaStream_t s);
 cudaError_t launch_chain_finalize(const uint64_t* pre, const uint32_t* nblocks, const uint64_t* h0,
                                   uint32_t R, uint32_t MP, uint64_t* chain, cudaStream_t s);
 cudaError_t launch_hash_generic(const uint8_t* prompts, const uint64_t* offsets, const uint64_t* h0,

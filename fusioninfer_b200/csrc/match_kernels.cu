@@ -712,7 +712,9 @@ cudaError_t launch_match_t(const MatchParams& p, int sm_count, cudaStream_t s) {
       cached_smem = smem + 1;
     }
     uint32_t grid = (p.R + kWarps - 1) / kWarps;
-    const uint32_t cap = (uint32_t)sm_count * (uint32_t)cached_per_sm;
+    uint32_t per_sm_now = (uint32_t)cached_per_sm;
+    if (p.max_ctas_per_sm && p.max_ctas_per_sm < per_sm_now) per_sm_now = p.max_ctas_per_sm;
+    const uint32_t cap = (uint32_t)sm_count * per_sm_now;
     if (grid > cap) grid = cap;
     if (grid == 0) grid = 1;
     if (p.zero_work_counter) {

@@ -342,6 +342,8 @@ int fi_epp_comm_exchange(fi_epp* h);
  *   "shard_hash"   sharded hashing: 1 = split over the ranks + all-gather of the chains (default), 0 = replicated
  *   "feed_slices"  slices of a host-buffer pick's prompt copy, 1..16 (default 8)
  *   "lru_threads"  host worker threads of fi_epp_index_add_chains (takes effect at the next call)
+ *   "pipe_hash_ctas", "pipe_match_ctas"  CTAs per SM of the two kernels the pipelined path runs side by side
+ *                  (fi_epp_pick_submit: batch k+1's block hashing next to batch k's match; 0 = uncapped)
  * FI_ERR_INVALID for an unknown name or a value out of range. */
 int fi_epp_set_option(fi_epp* h, const char* name, int64_t value);
 
