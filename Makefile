@@ -27,9 +27,9 @@ $(LIB): $(CU_OBJS) $(OBJDIR)/epp_config.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -ldl
 
 # host-only build of the shared host/device arithmetic, for CPU unit tests
-$(HOSTCHECK): $(CSRC)/hostcheck.cpp $(CSRC)/xxh64.cuh $(CSRC)/bitslice.cuh $(CSRC)/lru.h $(CSRC)/tiebreak.cuh
+$(HOSTCHECK): $(CSRC)/hostcheck.cpp $(CSRC)/xxh64.cuh $(CSRC)/bitslice.cuh $(CSRC)/lru.h $(CSRC)/lru_batch.h $(CSRC)/tiebreak.cuh
 	@mkdir -p $(dir $(HOSTCHECK))
-	$(CXX) -O2 -std=c++17 -ffp-contract=off -fPIC -Wall -Wextra -shared -x c++ $(CSRC)/hostcheck.cpp -o $@
+	$(CXX) -O2 -std=c++17 -ffp-contract=off -fPIC -Wall -Wextra -shared -pthread -x c++ $(CSRC)/hostcheck.cpp -o $@
 
 oracle:
 	$(MAKE) -C oracle

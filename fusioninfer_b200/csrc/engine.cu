@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -29,6 +30,7 @@
 #include "../../include/fi_epp.h"
 #include "kernels.cuh"
 #include "lru.h"
+#include "lru_batch.h"
 #include "xxh64.cuh"
 
 using namespace fi;
@@ -114,74 +116,6 @@ unsigned usable_cores() {
   const unsigned hc = std::thread::hardware_concurrency();
   return hc ? hc : 1u;
 }
-
-// Persistent worker threads for the host LRU (fi_epp_index_add_chains): run(n, fn) calls fn(task, worker)
-// for task = 0..n-1, tasks handed out dynamically; the caller is worker 0.
-class WorkerPool {
- public:
-  explicit WorkerPool(unsigned workers) : n_(workers < 1 ? 1 : workers) {
-    for (unsigned w = 1; w < n_; ++w) th_.emplace_back([this, w] { loop(w); });
-  }
-  ~WorkerPool() {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-      ++gen_;
-    }
-    cv_.notify_all();
-    for (auto& t : th_) t.join();
-  }
-  unsigned size() const { return n_; }
-  void run(uint32_t ntasks, const std::function<void(uint32_t, unsigned)>& fn) {
-    if (ntasks == 0) return;
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      fn_ = &fn;
-      ntasks_ = ntasks;
-      next_.store(0, std::memory_order_relaxed);
-      busy_ = n_ - 1;
-      ++gen_;
-    }
-    cv_.notify_all();
-    work(0);
-    std::unique_lock<std::mutex> lk(mu_);
-    done_.wait(lk, [this] { return busy_ == 0; });
-    fn_ = nullptr;
-  }
-
- private:
-  void work(unsigned w) {
-    for (;;) {
-      const uint32_t t = next_.fetch_add(1, std::memory_order_relaxed);
-      if (t >= ntasks_) break;
-      (*fn_)(t, w);
-    }
-  }
-  void loop(unsigned w) {
-    uint64_t seen = 0;
-    for (;;) {
-      {
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (stop_) return;
-      }
-      work(w);
-      std::lock_guard<std::mutex> lk(mu_);
-      if (--busy_ == 0) done_.notify_one();
-    }
-  }
-  unsigned n_;
-  std::vector<std::thread> th_;
-  std::mutex mu_;
-  std::condition_variable cv_, done_;
-  const std::function<void(uint32_t, unsigned)>* fn_ = nullptr;
-  uint32_t ntasks_ = 0;
-  std::atomic<uint32_t> next_{0};
-  unsigned busy_ = 0;
-  uint64_t gen_ = 0;
-  bool stop_ = false;
-};
 
 }  // namespace
 
@@ -269,6 +203,8 @@ struct fi_epp {
   std::unordered_set<PairKey, PairHash> cleared;
   std::vector<LruSet> lrus;
   std::unique_ptr<WorkerPool> pool;  // host LRU workers (fi_epp_index_add_chains), created on first use
+  std::vector<WorkerOps> lru_outs;   // their op lists (capacity kept from batch to batch)
+  bool verbose = false;              // FI_EPP_VERBOSE
   unsigned lru_threads = 0;          // 0: FI_EPP_LRU_THREADS, else min(usable cores, 64)
 
   // endpoints / score tables
@@ -1275,6 +1211,7 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   h->W = pow2_ceil32((cfg->endpoint_count + 31) / 32);
   h->fast_hash = (cfg->block_bytes % 32) == 0;
   if (const char* e = std::getenv("FI_EPP_TRACE")) h->trace_call = std::strtol(e, nullptr, 10);
+  h->verbose = std::getenv("FI_EPP_VERBOSE") != nullptr;
   if (const char* e = std::getenv("FI_EPP_PIPE_HASH_CTAS")) h->pipe_hash_ctas = (uint32_t)std::strtol(e, nullptr, 10);
   if (const char* e = std::getenv("FI_EPP_PIPE_MATCH_CTAS")) h->pipe_match_ctas = (uint32_t)std::strtol(e, nullptr, 10);
   if (h->cfg.max_prompt_bytes == 0)
@@ -1510,76 +1447,6 @@ int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes,
 
 namespace {
 
-// open-addressed set of 64-bit keys, emptied in O(1) (generation stamps): the hashes one endpoint evicted
-// during the current fi_epp_index_add_chains call
-struct StampSet {
-  std::vector<uint64_t> key;
-  std::vector<uint32_t> gen;
-  uint32_t cur = 0, mask = 0, used = 0;
-  void reset() {
-    if (key.empty()) {
-      key.assign(1u << 12, 0);
-      gen.assign(1u << 12, 0);
-      mask = (1u << 12) - 1;
-    }
-    ++cur;
-    used = 0;
-    if (cur == 0) {  // stamp wrapped
-      std::fill(gen.begin(), gen.end(), 0u);
-      cur = 1;
-    }
-  }
-  static uint32_t mix(uint64_t h) {
-    h ^= h >> 29;
-    h *= 0x9E3779B97F4A7C15ULL;
-    return (uint32_t)(h >> 32);
-  }
-  bool contains(uint64_t k) const {
-    for (uint32_t i = mix(k) & mask;; i = (i + 1) & mask) {
-      if (gen[i] != cur) return false;
-      if (key[i] == k) return true;
-    }
-  }
-  void insert(uint64_t k) {
-    if ((used + 1) * 2 > mask + 1) grow();
-    for (uint32_t i = mix(k) & mask;; i = (i + 1) & mask) {
-      if (gen[i] != cur) {
-        gen[i] = cur;
-        key[i] = k;
-        ++used;
-        return;
-      }
-      if (key[i] == k) return;
-    }
-  }
-  void grow() {
-    std::vector<uint64_t> ok;
-    ok.reserve(used);
-    for (uint32_t i = 0; i <= mask; ++i)
-      if (gen[i] == cur) ok.push_back(key[i]);
-    const uint32_t n = (mask + 1) * 2;
-    key.assign(n, 0);
-    gen.assign(n, 0);
-    mask = n - 1;
-    cur = 1;
-    used = 0;
-    for (uint64_t k : ok) insert(k);
-  }
-};
-
-// ops one worker produced, by segment: within a segment SETs run before CLEARs; a SET that follows a CLEAR of
-// the same (hash, endpoint) pair opens the endpoint's next segment ("last op wins", exactly)
-struct WorkerOps {
-  std::vector<std::vector<fi_index_op>> sets, clears;
-  StampSet evicted;
-  void need(size_t seg) {
-    if (sets.size() <= seg) {
-      sets.resize(seg + 1);
-      clears.resize(seg + 1);
-    }
-  }
-};
-
 struct CopyJob {
   fi_index_op* dst;
   const fi_index_op* src;
@@ -1604,68 +1471,20 @@ int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t
   }
   if (err == FI_OK) err = check_counters(h);
 
-  // ---- 1. requests of every local endpoint, in request order (counting sort)
+  // ---- 1./2. bucket the requests by endpoint and walk the LRUs on the worker pool (lru_batch.h)
   const uint32_t lo = h->cfg.endpoint_begin, EL = h->cfg.endpoint_count;
-  std::vector<uint32_t> first(EL + 1, 0), order, active;
-  std::vector<WorkerOps> outs;
+  std::vector<WorkerOps>& outs = h->lru_outs;  // persistent: capacity survives from batch to batch
   size_t nseg = 0;
-  if (err == FI_OK) {
-    for (uint32_t r = 0; r < R; ++r) {
-      const uint32_t e = endpoints[r] - lo;
-      if (endpoints[r] != FI_NO_ENDPOINT && e < EL && nblocks[r]) first[e + 1]++;
-    }
-    for (uint32_t e = 0; e < EL; ++e) {
-      if (first[e + 1]) active.push_back(e);
-      first[e + 1] += first[e];
-    }
-    order.resize(first[EL]);
-    std::vector<uint32_t> fill(first.begin(), first.end() - 1);
-    for (uint32_t r = 0; r < R; ++r) {
-      const uint32_t e = endpoints[r] - lo;
-      if (endpoints[r] != FI_NO_ENDPOINT && e < EL && nblocks[r]) order[fill[e]++] = r;
-    }
-    // ---- 2. walk the LRUs: one endpoint per task
-    if (!h->pool) {
-      unsigned t = std::min(usable_cores(), 64u);
-      if (const char* ev = std::getenv("FI_EPP_LRU_THREADS")) t = (unsigned)std::max(1L, std::strtol(ev, nullptr, 10));
-      if (h->lru_threads) t = h->lru_threads;
-      h->pool.reset(new WorkerPool(t));
-    }
-    outs.resize(h->pool->size());
-    h->pool->run((uint32_t)active.size(), [&](uint32_t task, unsigned w) {
-      const uint32_t e = active[task];
-      LruSet& l = h->lrus[e];
-      WorkerOps& o = outs[w];
-      o.evicted.reset();
-      size_t seg = 0;
-      o.need(0);
-      bool any_evicted = false;
-      for (uint32_t k = first[e]; k < first[e + 1]; ++k) {
-        const uint32_t r = order[k];
-        const uint64_t* c = chains + (size_t)r * pitch_blocks;
-        for (uint32_t i = 0; i < nblocks[r]; ++i) {
-          uint64_t ev = 0;
-          bool did = false;
-          const bool inserted = l.touch(c[i], &ev, &did);
-          if (did) {
-            o.clears[seg].push_back(fi_index_op{ev, e + lo, FI_OP_CLEAR});
-            o.evicted.insert(ev);
-            any_evicted = true;
-          }
-          if (inserted) {
-            if (any_evicted && o.evicted.contains(c[i])) {  // re-added after its eviction in this call
-              ++seg;
-              o.need(seg);
-              o.evicted.reset();
-              any_evicted = false;
-            }
-            o.sets[seg].push_back(fi_index_op{c[i], e + lo, FI_OP_SET});
-          }
-        }
-      }
-    });
-    for (auto& o : outs) nseg = std::max(nseg, o.sets.size());
+  const auto t_start = std::chrono::steady_clock::now();
+  if (!h->pool) {
+    unsigned t = std::min(usable_cores(), 128u);
+    if (const char* ev = std::getenv("FI_EPP_LRU_THREADS")) t = (unsigned)std::max(1L, std::strtol(ev, nullptr, 10));
+    if (h->lru_threads) t = h->lru_threads;
+    h->pool.reset(new WorkerPool(t));
   }
+  if (err == FI_OK) nseg = lru_walk_batch(h->lrus, lo, EL, endpoints, chains, pitch_blocks, nblocks, R, *h->pool, outs);
+  else for (auto& o : outs) o.begin_batch();
+  const auto t_walked = std::chrono::steady_clock::now();
 
   // ---- 3. stage segment by segment (SETs, then CLEARs), flushing whenever a staging buffer is full.
   // `flushes` is first counted (dry run) so that the ranks of a sharded pool can agree on the rounds.
@@ -1700,7 +1519,7 @@ int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t
     for (size_t seg = 0; seg < nseg; ++seg) {
       for (int kind = 0; kind < 2; ++kind) {
         for (auto& o : outs) {
-          if (o.sets.size() <= seg) continue;
+          if (o.nseg <= seg) continue;
           const std::vector<fi_index_op>& v = kind == 0 ? o.sets[seg] : o.clears[seg];
           size_t done = 0;
           while (done < v.size()) {
@@ -1737,7 +1556,17 @@ int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t
   if (h->world <= 1) {
     if (err != FI_OK) return err;
     // the tail stays staged: it is launched with the next flush — at the latest by the next pick / sync
-    return walk(false, [&]() { return flush_ops(h); }, nullptr);
+    int rc1 = walk(false, [&]() { return flush_ops(h); }, nullptr);
+    if (h->verbose) {
+      const auto t_end = std::chrono::steady_clock::now();
+      size_t nops = 0;
+      for (auto& o : outs)
+        for (size_t sg = 0; sg < o.nseg; ++sg) nops += o.sets[sg].size() + o.clears[sg].size();
+      std::fprintf(stderr, "[fi_epp] add_chains: %u requests, %zu ops, %zu segment(s), %u workers: LRU walk %.2f ms, staging %.2f ms\n",
+                   R, nops, nseg, h->pool->size(), std::chrono::duration<double, std::milli>(t_walked - t_start).count(),
+                   std::chrono::duration<double, std::milli>(t_end - t_walked).count());
+    }
+    return rc1;
   }
   // sharded: every flush is one gossip round, the tail included
   uint64_t mine = 0;

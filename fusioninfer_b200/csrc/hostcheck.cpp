@@ -7,6 +7,7 @@
 
 #include "bitslice.cuh"
 #include "lru.h"
+#include "lru_batch.h"
 #include "tiebreak.cuh"
 #include "xxh64.cuh"
 
@@ -109,6 +110,63 @@ void fihc_lru_touch(void* l, const uint64_t* keys, uint32_t n, uint8_t* inserted
     did_evict[i] = d ? 1 : 0;
     evicted[i] = ev;
   }
+}
+
+// fi_epp_index_add_chains' host phase (lru_batch.h) against the sequential definition: walk the batch on
+// `workers` threads, apply the resulting ops segment by segment (all SETs of a segment, then all its CLEARs — the
+// way the GPU applies a group) to a membership set, and compare that set and the LRU contents with one LRU per
+// endpoint touched request after request.  Returns 0 if identical, else a code; *segments = segments used.
+int fihc_lru_batch_check(uint32_t E, uint32_t cap, const uint32_t* endpoints, const uint64_t* chains, uint32_t pitch,
+                         const uint32_t* nblocks, uint32_t R, uint32_t batches, uint32_t workers, uint32_t* segments) {
+  std::vector<fi::LruSet> par(E, fi::LruSet(cap)), seq(E, fi::LruSet(cap));
+  fi::WorkerPool pool(workers);
+  std::vector<fi::WorkerOps> outs;
+  std::vector<std::vector<uint64_t>> member_par(E), member_seq(E);  // sorted membership per endpoint
+  auto has = [](std::vector<uint64_t>& v, uint64_t k) { return std::binary_search(v.begin(), v.end(), k); };
+  auto add = [&](std::vector<uint64_t>& v, uint64_t k) {
+    auto it = std::lower_bound(v.begin(), v.end(), k);
+    if (it == v.end() || *it != k) v.insert(it, k);
+  };
+  auto del = [&](std::vector<uint64_t>& v, uint64_t k) {
+    auto it = std::lower_bound(v.begin(), v.end(), k);
+    if (it != v.end() && *it == k) v.erase(it);
+  };
+  (void)has;
+  uint32_t max_seg = 0;
+  for (uint32_t b = 0; b < batches; ++b) {
+    const uint32_t* ep = endpoints + (size_t)b * R;
+    const uint64_t* ch = chains + (size_t)b * R * pitch;
+    const uint32_t* nb = nblocks + (size_t)b * R;
+    const size_t nseg = fi::lru_walk_batch(par, 0, E, ep, ch, pitch, nb, R, pool, outs);
+    if (nseg > max_seg) max_seg = (uint32_t)nseg;
+    for (size_t sgi = 0; sgi < nseg; ++sgi) {
+      for (auto& o : outs)
+        if (sgi < o.nseg)
+          for (auto& op : o.sets[sgi]) add(member_par[op.endpoint], op.hash);
+      for (auto& o : outs)
+        if (sgi < o.nseg)
+          for (auto& op : o.clears[sgi]) del(member_par[op.endpoint], op.hash);
+    }
+    for (uint32_t r = 0; r < R; ++r) {
+      if (ep[r] == FI_NO_ENDPOINT || ep[r] >= E) continue;
+      for (uint32_t i = 0; i < nb[r]; ++i) {
+        uint64_t ev = 0;
+        bool did = false;
+        const uint64_t k = ch[(size_t)r * pitch + i];
+        const bool ins = seq[ep[r]].touch(k, &ev, &did);
+        if (ins) add(member_seq[ep[r]], k);
+        if (did) del(member_seq[ep[r]], ev);
+      }
+    }
+    for (uint32_t e = 0; e < E; ++e) {
+      if (member_par[e] != member_seq[e]) return 1;
+      if (par[e].size() != seq[e].size() || par[e].size() != member_seq[e].size()) return 2;
+      for (uint64_t k : member_seq[e])
+        if (!par[e].contains(k)) return 3;
+    }
+  }
+  if (segments) *segments = max_seg;
+  return 0;
 }
 
 }  // extern "C"

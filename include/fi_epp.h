@@ -269,7 +269,7 @@ int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes,
  * indexer.Add(chains[r*pitch_blocks .. +nblocks[r]), endpoints[r]) for r = 0..R-1 (FI_NO_ENDPOINT and
  * endpoints of other shards are skipped).  Equal to R fi_epp_index_add_chain calls in request order; the
  * endpoints' LRUs are walked in parallel on host worker threads (FI_EPP_LRU_THREADS, default = usable
- * cores, at most 64).  `chains` / `nblocks` are what fi_epp_pick_batch returned (chains_out, picks'
+ * cores, at most 128).  `chains` / `nblocks` are what fi_epp_pick_batch returned (chains_out, picks'
  * n_blocks).  Collective on a sharded pool. */
 int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains, uint32_t pitch_blocks,
                             const uint32_t* nblocks, uint32_t R);

@@ -574,7 +574,7 @@ def test_tie_rotation_spreads_cold_requests_and_matches_the_rule():
     got, chains = gpu.pick_batch(tok, offs, wl.h0, want_chains=True)
     want = cpu.pick_batch(tok, offs, wl.h0)
     assert H.picks_equal(got, want), H.describe_diff(got, want)
-    assert len(np.unique(got[:, 0]["endpoint"])) > 100
+    assert len(np.unique(got[:, 0]["endpoint"])) > 60  # (requests of one Zipf group share their first block: same endpoint)
     for r in range(wl.R):
         assert got[r, 0]["endpoint"] == restate.tie_start(int(got[r, 0]["n_blocks"]), int(chains[r, 0]), wl.h0, r, wl.E)
     # short prompts (no block): rotation by (h0, request index); sliced and unsliced host feeds agree (r_base)

@@ -37,6 +37,9 @@ def hc():
     lib.fihc_lru_size.argtypes = [C.c_void_p]
     lib.fihc_lru_contains.argtypes = [C.c_void_p, C.c_uint64]
     lib.fihc_lru_touch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fihc_lru_batch_check.restype = C.c_int
+    lib.fihc_lru_batch_check.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                         C.c_uint32, C.c_uint32, C.c_void_p]
     lib.fihc_tie_start.restype = C.c_uint32
     lib.fihc_tie_start.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
     lib.fihc_tie_rot.restype = C.c_uint32
@@ -400,3 +403,26 @@ def test_config_by_label_with_arbitrary_labels_and_chained_filters():
     cfg2 = config_from_yaml(doc)
     pf = cfg2.profiles[cfg2.pd_prefill_profile]
     assert pf.role_mask == abi.FI_ROLE_PREFILLER and pf.n_more_filters == 1 and pf.more_filters[0] == abi.FI_ROLE_DECODER
+
+
+@pytest.mark.parametrize("workers", [1, 3, 8])
+def test_batch_lru_walk_equals_sequential_adds(hc, workers):
+    """fi_epp_index_add_chains' host phase (lru_batch.h: requests bucketed by endpoint, LRUs walked on a worker
+    pool, ops emitted in segments) against the definition — one indexer.Add after the other.  Small capacity and
+    recurring chains force evictions and re-adds of evicted hashes INSIDE one batch (the multi-segment path)."""
+    rng = np.random.default_rng(17 + workers)
+    E, cap, R, pitch, batches = 7, 40, 120, 24, 5
+    pool_chains = rng.integers(1, 2**63, size=(30, pitch), dtype=np.uint64)  # 30 recurring chains
+    eps = rng.integers(0, E + 2, size=(batches, R)).astype(np.uint32)
+    eps[eps == E] = 0xFFFFFFFF      # FI_NO_ENDPOINT: skipped
+    eps[eps == E + 1] = E + 100     # another shard: skipped
+    pick = rng.integers(0, 30, size=(batches, R))
+    chains = pool_chains[pick].copy()
+    fresh = rng.random((batches, R)) < 0.3     # some requests end in unique blocks
+    chains[fresh, pitch // 2:] = rng.integers(1, 2**63, size=(int(fresh.sum()), pitch - pitch // 2), dtype=np.uint64)
+    nb = rng.integers(0, pitch + 1, size=(batches, R)).astype(np.uint32)
+    seg = C.c_uint32(0)
+    rc = hc.fihc_lru_batch_check(E, cap, eps.ctypes.data, np.ascontiguousarray(chains).ctypes.data, pitch, nb.ctypes.data, R,
+                                 batches, workers, C.byref(seg))
+    assert rc == 0
+    assert seg.value >= 2  # the same-batch re-add path really ran

@@ -128,16 +128,26 @@ def main():
             tomb.append({"step": step, "used": int(s.used), "tombstones": int(s.tombstones), "rebuilds": int(s.rebuilds)})
     gpu.index_sync()
     st = gpu.index_stats()
+    # device time of the index kernels for one more step (profiled: CUDA events around every launch)
+    gpu.reset_stats()
+    gpu.set_profiling(True)
+    gpu.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr, pin_ch.ptr)
+    gpu.index_add_chains(np.ascontiguousarray(picks_v[:, main_p]["endpoint"]), chains_v,
+                         np.ascontiguousarray(picks_v[:, main_p]["n_blocks"]).astype(np.uint32))
+    gpu.index_sync()
+    pst = gpu.stats()
+    gpu.set_profiling(False)
     tp, ta = np.array(t_pick[1:]), np.array(t_add[1:])  # step 0 warms the worker pool / first-touch pages
     n = R * len(tp)
     out = {
         "mode": "churn: pick + indexer.Add(chain, picked endpoint) for every decision, LRUs at capacity",
         "workload": f"cfg{args.cfg}: {R} req/step x {wl.E} endpoints x {wl.T}-token prompts, lruCapacityPerServer {wl.lru_capacity}",
-        "steps_timed": len(tp), "lru_threads": args.threads or "default (usable cores, <= 64)",
+        "steps_timed": len(tp), "lru_threads": args.threads or "default (usable cores, <= 128)",
         "decisions_per_s": n / float(tp.sum() + ta.sum()),
         "pick_ms": {"p50": 1e3 * float(np.median(tp)), "p99": 1e3 * float(np.quantile(tp, 0.99)), "max": 1e3 * float(tp.max())},
         "add_ms": {"p50": 1e3 * float(np.median(ta)), "p99": 1e3 * float(np.quantile(ta, 0.99)), "max": 1e3 * float(ta.max())},
         "lru_touches_per_s": n * wl.n_blocks / float(ta.sum()),
+        "index_kernels_ms_per_step": pst.ms_index_apply, "index_kernel_launches_per_step": int(pst.n_index_apply),
         "index": {"slots": int(st.slots), "used": int(st.used), "tombstones": int(st.tombstones), "rebuilds": int(st.rebuilds),
                   "ops_applied": int(st.ops_applied), "lru_entries": int(st.lru_entries), "growth": tomb},
         "requests_with_prefix_hit": hits,
