@@ -39,3 +39,12 @@ clean:
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean
+
+# debug variant with per-phase clock64 sums inside match_pick (FI_EPP_LIB=fusioninfer_b200/lib/libfi_epp_timing.so FI_EPP_VERBOSE=1)
+TIMING_LIB := fusioninfer_b200/lib/libfi_epp_timing.so
+timing: $(TIMING_LIB)
+$(TIMING_LIB): $(CU_SRCS) $(HDRS) $(OBJDIR)/epp_config.o
+	@mkdir -p $(OBJDIR)/timing
+	for f in hash_kernels index_kernels match_kernels engine; do $(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -DFI_MATCH_TIMING -Xcompiler -fPIC -c $(CSRC)/$$f.cu -o $(OBJDIR)/timing/$$f.o || exit 1; done
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJDIR)/timing/*.o $(OBJDIR)/epp_config.o -ldl
+.PHONY: timing

@@ -341,21 +341,40 @@ def bind_to_gpu_numa(local):
         return f"numa: not bound ({type(e).__name__})", restore
 
 
-def measure_h2d_gbs(nbytes):
-    """The PCIe yardstick of the e2e leg: a pinned cudaMemcpyAsync of the same size in this process (best of 5)."""
+def measure_h2d_gbs(src_ptr, nbytes):
+    """The PCIe yardstick of the e2e leg: plain cudaMemcpyAsync calls from the SAME pinned buffer the e2e leg
+    feeds from, in this process — one copy of the whole buffer, and the buffer in 8 back-to-back slices (what the
+    library's host path does); best of 6 each, the better of the two."""
+    import ctypes
+
     import torch
 
-    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    rt = None
+    for name in ("libcudart.so.12", "libcudart.so"):
+        try:
+            rt = ctypes.CDLL(name)
+            break
+        except OSError:
+            continue
+    if rt is None:
+        return None
+    rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
     dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
     best = 0.0
-    for _ in range(6):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dst.copy_(src, non_blocking=True)
-        e1.record()
-        torch.cuda.synchronize()
-        best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
-    del src, dst
+    for slices in (1, 8):
+        per = (nbytes + slices - 1) // slices
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(slices):
+                n = min(per, nbytes - k * per)
+                if n > 0 and rt.cudaMemcpyAsync(dst.data_ptr() + k * per, src_ptr + k * per, n, 1, stream) != 0:
+                    return None
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del dst
     return best
 
 
@@ -620,9 +639,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cfg", type=int, default=3, choices=[2, 3, 4, 5])
     ap.add_argument("--mode", default=None, choices=["replicas", "sharded"])
-    ap.add_argument("--pipeline", action="store_true",
-                    help="time the pipelined device API (fi_epp_pick_submit / fi_epp_pick_wait, two batches in flight) "
-                         "instead of stream-ordered fi_epp_pick_batch_device calls")
+    ap.add_argument("--pipeline", dest="pipeline", action="store_true", default=True,
+                    help="(default) time the pipelined device API: fi_epp_pick_submit per batch, one fi_epp_pick_wait at the end "
+                         "of the K steps — two batches in flight, batch k+1 is hashed while batch k is matched")
+    ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
+                    help="time stream-ordered fi_epp_pick_batch_device calls instead (reported as roofline.stream_ordered anyway)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink R (debug only; the JSON line says so)")
     ap.add_argument("--batches", type=int, default=2, help="distinct request batches rotated through")
     ap.add_argument("--cpu-sample", type=int, default=4096)
@@ -697,6 +718,11 @@ def main():
     clk = clocks.stop()
     units = R * (world if mode == "replicas" else 1)
     value = units / (ms_step * 1e-3)
+    stream_ordered = None
+    if pipelined:  # the same K steps through the stream-ordered call, for reference
+        ms_so, _ = sc.time_steps(min(args.steps, 50), 3, False)
+        stream_ordered = {"decisions_per_s": units / (ms_so * 1e-3), "ms_per_step": ms_so,
+                          "how": "fi_epp_pick_batch_device, one call per step (each call orders the caller's stream behind its result)"}
 
     # ---- per-kernel durations + N_probe (profiled pass, not part of the number above) -----------
     avg_ms, nprobe_per_step = sc.kernel_split(args.steps)
@@ -716,7 +742,7 @@ def main():
         "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak,
         "other_kernels": {k: {"achieved": (alg[k] / (avg_ms[k] * 1e-3) / 1e9 if avg_ms[k] else 0.0),
                               "traffic": traffic.get(k)} for k in ("hash_blocks", "match_pick") if k != dom},
-        "index": sc.index_stats, "index_order_of_value": args.index_order,
+        "index": sc.index_stats, "index_order_of_value": args.index_order, "stream_ordered": stream_ordered,
     }
 
     # ---- e2e: public C-ABI call with host (pinned) buffers, H2D + D2H inside ---------------------
@@ -742,7 +768,7 @@ def main():
     dt = time.perf_counter() - t0
     dt = fdist.max_over_ranks(dt)
     h2d_bytes = int(tok0.nbytes + offs0.nbytes + 8 * R)
-    h2d_gbs = measure_h2d_gbs(int(tok0.nbytes)) if not args.no_e2e else None
+    h2d_gbs = measure_h2d_gbs(pin_tok.ptr, int(tok0.nbytes)) if not args.no_e2e else None
     h2d_gbs_min = -fdist.max_over_ranks(-h2d_gbs) if h2d_gbs else None
     e2e = {"value": units * e2e_steps / dt, "unit": "decisions/s",
            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(16 * R * P),
@@ -751,8 +777,9 @@ def main():
            "roofline": {"bound": "pcie", "h2d_gbs_measured": h2d_gbs_min, "unit": "GB/s",
                         "achieved": h2d_bytes / (dt / e2e_steps) / 1e9,
                         "frac": (h2d_bytes / (dt / e2e_steps) / 1e9 / h2d_gbs_min) if h2d_gbs_min else None,
-                        "how": "achieved = H2D bytes of a step / its wall time; yardstick = pinned cudaMemcpyAsync of the "
-                               "prompt bytes in this process (best of 6, slowest rank)"},
+                        "how": "achieved = H2D bytes of a step / its wall time (host clock, D2H of the picks and the last slice's "
+                               "kernels included); yardstick = bare cudaMemcpyAsync of the same pinned prompt buffer in this "
+                               "process (CUDA events; whole and in 8 slices, best of 6, slowest rank)"},
            "numa": numa_note}
     e2e_picks = pin_out.array(np.uint8).copy().view(np.dtype(
         [("endpoint", "<u4"), ("match_blocks", "<u2"), ("n_blocks", "<u2"), ("score", "<f8")])).reshape(R, P)

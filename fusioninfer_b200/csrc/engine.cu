@@ -105,16 +105,23 @@ uint64_t pow2_ceil64(uint64_t v) {
   return p;
 }
 
-// host cores this process may run on (affinity mask; the cgroup quota is the caller's business)
+// host cores this process may really use: the affinity mask capped by the cgroup CPU quota (more runnable
+// threads than quota only get the group throttled)
 unsigned usable_cores() {
+  unsigned n = std::thread::hardware_concurrency();
   cpu_set_t set;
   CPU_ZERO(&set);
-  if (sched_getaffinity(0, sizeof(set), &set) == 0) {
-    const int n = CPU_COUNT(&set);
-    if (n > 0) return (unsigned)n;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) n = (unsigned)CPU_COUNT(&set);
+  if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {  // cgroup v2: "<quota|max> <period>"
+    char q[64] = {0};
+    long long period = 0;
+    if (std::fscanf(f, "%63s %lld", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0) {
+      const long long quota = std::atoll(q);
+      if (quota > 0) n = std::min<unsigned>(n, (unsigned)std::max<long long>(1, (quota + period - 1) / period));
+    }
+    std::fclose(f);
   }
-  const unsigned hc = std::thread::hardware_concurrency();
-  return hc ? hc : 1u;
+  return n ? n : 1u;
 }
 
 }  // namespace
@@ -201,6 +208,7 @@ struct fi_epp {
   int cur_buf = 0;
   uint64_t n_sets = 0, n_clears = 0;
   std::unordered_set<PairKey, PairHash> cleared;
+  LruArena lru_arena;  // backing store of the LRUs (one huge-page mapping)
   std::vector<LruSet> lrus;
   std::unique_ptr<WorkerPool> pool;  // host LRU workers (fi_epp_index_add_chains), created on first use
   std::vector<WorkerOps> lru_outs;   // their op lists (capacity kept from batch to batch)
@@ -1139,6 +1147,8 @@ void fi_epp_destroy(fi_epp* h) {
   cudaFree(h->d_adapters);
   if (h->h_adapters) cudaFreeHost(h->h_adapters);
   h->pool.reset();
+  h->lrus.clear();
+  h->lru_arena.release();
   free_index(h->ix);
   free_index(h->ix_spare);
   for (int b = 0; b < 2; ++b) {
@@ -1251,8 +1261,8 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaMalloc(&h->d_chain, (size_t)h->chain_rows * h->MP * sizeof(uint64_t)));
   FI_TRY(cudaMalloc(&h->d_nblocks, (size_t)h->chain_rows * sizeof(uint32_t)));
   FI_TRY(cudaMalloc(&h->d_picks, R * h->P * sizeof(fi_pick)));
-  FI_TRY(cudaMalloc(&h->d_probed, sizeof(unsigned long long)));
-  FI_TRY(cudaMemset(h->d_probed, 0, sizeof(unsigned long long)));
+  FI_TRY(cudaMalloc(&h->d_probed, 8 * sizeof(unsigned long long)));
+  FI_TRY(cudaMemset(h->d_probed, 0, 8 * sizeof(unsigned long long)));
   FI_TRY(cudaMalloc(&h->d_work, 16 * sizeof(uint32_t)));
   FI_TRY(cudaMemset(h->d_work, 0, 16 * sizeof(uint32_t)));
   FI_TRY(cudaMallocHost(&h->h_picks, R * h->P * sizeof(fi_pick)));
@@ -1277,7 +1287,11 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
     FI_TRY(cudaEventCreateWithFlags(&h->ev_buf[b], cudaEventDisableTiming));
     FI_TRY(cudaEventRecord(h->ev_buf[b], h->s_index));
   }
-  if (cfg->lru_capacity) h->lrus.assign(cfg->endpoint_count, LruSet(cfg->lru_capacity));
+  if (cfg->lru_capacity) {
+    // virtual reservation only: an endpoint's tables become resident when it is first touched
+    LruArena* arena = h->lru_arena.reserve((size_t)cfg->endpoint_count * LruSet::bytes_needed(cfg->lru_capacity)) ? &h->lru_arena : nullptr;
+    h->lrus = std::vector<LruSet>(cfg->endpoint_count, LruSet(cfg->lru_capacity, arena));
+  }
 
   // endpoints + score tables
   h->eps.assign(cfg->num_endpoints, EndpointDev{0.0, 0, 0, 0, 0});
@@ -1930,9 +1944,13 @@ int fi_epp_get_stats(fi_epp* h, fi_epp_stats* out) {
   drain_profile(h);
   if (h->profiling) {
     FI_CUDA(cudaStreamSynchronize(h->s_main));
-    unsigned long long pb = 0;
-    FI_CUDA(cudaMemcpy(&pb, h->d_probed, sizeof(pb), cudaMemcpyDeviceToHost));
-    h->stats.probed_blocks = pb;
+    unsigned long long pb[8] = {0};
+    FI_CUDA(cudaMemcpy(pb, h->d_probed, sizeof(pb), cudaMemcpyDeviceToHost));
+    h->stats.probed_blocks = pb[0];
+    if (pb[5] && h->verbose)  // FI_MATCH_TIMING build: where a request's time goes inside match_pick
+      std::fprintf(stderr, "[fi_epp] match_pick phases, cycles per request over %llu requests: stage %.0f, first lookup %.0f, "
+                   "chunks %.0f, score+pick %.0f\n", pb[5], (double)pb[1] / pb[5], (double)pb[2] / pb[5], (double)pb[3] / pb[5],
+                   (double)pb[4] / pb[5]);
   }
   *out = h->stats;
   return FI_OK;
@@ -1944,7 +1962,7 @@ int fi_epp_reset_stats(fi_epp* h) {
   cudaSetDevice(h->cfg.device);
   drain_profile(h);
   cudaStreamSynchronize(h->s_main);
-  cudaMemset(h->d_probed, 0, sizeof(unsigned long long));
+  cudaMemset(h->d_probed, 0, 8 * sizeof(unsigned long long));
   h->stats = fi_epp_stats{};
   return FI_OK;
 }

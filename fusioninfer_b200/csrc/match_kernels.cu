@@ -235,6 +235,9 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
     if (r >= p.R) break;
     if (lane == 0) r_next = take_ticket(p.work_counter, threadIdx.x & p.lane_zero);
     const uint32_t n = p.nblocks[r];
+#ifdef FI_MATCH_TIMING
+    const long long tm0 = clock64();
+#endif
     // ---- 1. stage the chain
     {
       const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
@@ -243,6 +246,9 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
       __syncwarp();
     }
 
+#ifdef FI_MATCH_TIMING
+    const long long tm1 = clock64();
+#endif
     BitCounter cnt[VEC];
     uint32_t alive[VEC];
 #pragma unroll
@@ -260,6 +266,9 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
       const bool v0 = (uint32_t)lane < n;
       slot = resolve_chunk_nodes(ix, v0 ? s_chain[lane] : 0ull, v0, SLOT_MISS, false, lane);
     }
+#ifdef FI_MATCH_TIMING
+    const long long tm2 = clock64();
+#endif
     for (uint32_t c = 0; c < nchunks; ++c) {
       uint32_t rows_here;
       bool stop = false;
@@ -360,6 +369,9 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
       slot = slot_next;
     }
 
+#ifdef FI_MATCH_TIMING
+    const long long tm3 = clock64();
+#endif
     // ---- merge the lane groups' counters ---------------------------------------
     const bool nothing = matched_rows == 0;  // warp-uniform: no row was read, every counter is zero
     if (G > 1 && !nothing) {
@@ -511,6 +523,16 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
         }
       }
       if (p.probed_blocks) atomicAdd(p.probed_blocks, (unsigned long long)(matched_rows + (real_miss ? 1 : 0)));
+#ifdef FI_MATCH_TIMING
+      if (p.probed_blocks) {  // per-phase cycle sums behind the N_probe counter (debug build only)
+        const long long tm4 = clock64();
+        atomicAdd(p.probed_blocks + 1, (unsigned long long)(tm1 - tm0));
+        atomicAdd(p.probed_blocks + 2, (unsigned long long)(tm2 - tm1));
+        atomicAdd(p.probed_blocks + 3, (unsigned long long)(tm3 - tm2));
+        atomicAdd(p.probed_blocks + 4, (unsigned long long)(tm4 - tm3));
+        atomicAdd(p.probed_blocks + 5, 1ull);
+      }
+#endif
     }
     r_next = __shfl_sync(FULL, r_next, 0);  // also orders this request's s_chain reads before the next staging
   }
