@@ -12,6 +12,7 @@
 //                   blockSize: 5): fully serial per request, byte loads.
 #include "kernels.cuh"
 #include "xxh64.cuh"
+#include "xxh64_sm100.cuh"
 
 namespace fi {
 
@@ -44,8 +45,28 @@ __device__ __forceinline__ uint64_t pre_index(uint32_t r, uint32_t i, uint32_t M
   return ((((uint64_t)(r >> 5) * MP2 + (i >> 1)) * 32 + (r & 31)) << 1) + (i & 1);
 }
 
+// one 32-byte stripe per load: every lane fetches whole 32-byte sectors exactly once (with 16-byte loads the
+// two halves of a sector were requested by two instructions, and with L1::no_allocate both went to L2: ncu
+// counted 2x the prompt bytes between L2 and L1)
+struct Stripe {
+  uint32_t w[8];
+};
+__device__ __forceinline__ Stripe ld_stream_v8(const void* p, uint64_t pol) {
+  Stripe v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;\n"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void xacc2_stripe(XAcc2& a, const Stripe& q) {
+  a.v1 = xround2(a.v1, U2{q.w[0], q.w[1]});
+  a.v2 = xround2(a.v2, U2{q.w[2], q.w[3]});
+  a.v3 = xround2(a.v3, U2{q.w[4], q.w[5]});
+  a.v4 = xround2(a.v4, U2{q.w[6], q.w[7]});
+}
+
 template <int STRIPES>
-__global__ void __launch_bounds__(256) hash_blocks_kernel(const uint8_t* __restrict__ prompts,
+__global__ void __launch_bounds__(256, STRIPES <= 2 ? 8 : 5) hash_blocks_kernel(const uint8_t* __restrict__ prompts,
                                                           const uint64_t* __restrict__ offsets, uint32_t R, uint32_t M,
                                                           uint32_t MP, uint64_t* __restrict__ pre,
                                                           uint32_t* __restrict__ nblocks) {
@@ -61,18 +82,30 @@ __global__ void __launch_bounds__(256) hash_blocks_kernel(const uint8_t* __restr
     const uint32_t n = nb64 > M ? M : (uint32_t)nb64;
     if (threadIdx.x == 0) nblocks[r] = n;
     const uint8_t* base = prompts + off;
-    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(base) & 31);
+    if (mis == 0) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint8_t* p = base + (uint64_t)i * B;
+        Stripe q[STRIPES];
+#pragma unroll
+        for (int s = 0; s < STRIPES; ++s) q[s] = ld_stream_v8(p + 32 * s, pol);
+        XAcc2 a = xacc2_init();
+#pragma unroll
+        for (int s = 0; s < STRIPES; ++s) xacc2_stripe(a, q[s]);
+        pre[pre_index(r, i, MP2)] = xacc2_finish(a, (uint64_t)B + 8);
+      }
+    } else if ((mis & 15) == 0) {
       for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         const uint4* p = reinterpret_cast<const uint4*>(base + (uint64_t)i * B);
         uint4 q[2 * STRIPES];
 #pragma unroll
         for (int s = 0; s < 2 * STRIPES; ++s) q[s] = ld_stream_v4(p + s, pol);
-        XAcc a = xacc_init();
+        XAcc2 a = xacc2_init();
 #pragma unroll
         for (int s = 0; s < STRIPES; ++s)
-          xacc_stripe(a, pack64(q[2 * s].x, q[2 * s].y), pack64(q[2 * s].z, q[2 * s].w),
-                      pack64(q[2 * s + 1].x, q[2 * s + 1].y), pack64(q[2 * s + 1].z, q[2 * s + 1].w));
-        pre[pre_index(r, i, MP2)] = xacc_finish(a, (uint64_t)B + 8);
+          xacc2_stripe(a, Stripe{{q[2 * s].x, q[2 * s].y, q[2 * s].z, q[2 * s].w, q[2 * s + 1].x, q[2 * s + 1].y,
+                                  q[2 * s + 1].z, q[2 * s + 1].w}});
+        pre[pre_index(r, i, MP2)] = xacc2_finish(a, (uint64_t)B + 8);
       }
     } else {
       // arbitrary byte alignment: aligned 64-bit windows + funnel shift
@@ -88,10 +121,13 @@ __global__ void __launch_bounds__(256) hash_blocks_kernel(const uint8_t* __restr
 #pragma unroll
           for (int k = 0; k < 4 * STRIPES; ++k) w[k] = (w[k] >> sh) | (w[k + 1] << (64 - sh));
         }
-        XAcc a = xacc_init();
+        XAcc2 a = xacc2_init();
 #pragma unroll
-        for (int s = 0; s < STRIPES; ++s) xacc_stripe(a, w[4 * s], w[4 * s + 1], w[4 * s + 2], w[4 * s + 3]);
-        pre[pre_index(r, i, MP2)] = xacc_finish(a, (uint64_t)B + 8);
+        for (int s = 0; s < STRIPES; ++s)
+          xacc2_stripe(a, Stripe{{(uint32_t)w[4 * s], (uint32_t)(w[4 * s] >> 32), (uint32_t)w[4 * s + 1],
+                                  (uint32_t)(w[4 * s + 1] >> 32), (uint32_t)w[4 * s + 2], (uint32_t)(w[4 * s + 2] >> 32),
+                                  (uint32_t)w[4 * s + 3], (uint32_t)(w[4 * s + 3] >> 32)}});
+        pre[pre_index(r, i, MP2)] = xacc2_finish(a, (uint64_t)B + 8);
       }
     }
   }
