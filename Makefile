@@ -8,7 +8,7 @@ OBJDIR := build
 LIB := fusioninfer_b200/lib/libfi_epp.so
 HOSTCHECK := fusioninfer_b200/lib/libfi_hostcheck.so
 
-CU_SRCS := $(CSRC)/hash_kernels.cu $(CSRC)/index_kernels.cu $(CSRC)/match_kernels.cu $(CSRC)/engine.cu
+CU_SRCS := $(CSRC)/hash_kernels.cu $(CSRC)/index_kernels.cu $(CSRC)/lru_kernels.cu $(CSRC)/match_kernels.cu $(CSRC)/engine.cu
 CU_OBJS := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/fi_epp.h
 
@@ -27,7 +27,7 @@ $(LIB): $(CU_OBJS) $(OBJDIR)/epp_config.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -ldl
 
 # host-only build of the shared host/device arithmetic, for CPU unit tests
-$(HOSTCHECK): $(CSRC)/hostcheck.cpp $(CSRC)/xxh64.cuh $(CSRC)/bitslice.cuh $(CSRC)/lru.h $(CSRC)/lru_batch.h $(CSRC)/tiebreak.cuh
+$(HOSTCHECK): $(CSRC)/hostcheck.cpp $(CSRC)/xxh64.cuh $(CSRC)/bitslice.cuh $(CSRC)/lru.h $(CSRC)/lru_batch.h $(CSRC)/lru_plan.h $(CSRC)/tiebreak.cuh
 	@mkdir -p $(dir $(HOSTCHECK))
 	$(CXX) -O2 -std=c++17 -ffp-contract=off -fPIC -Wall -Wextra -shared -pthread -x c++ $(CSRC)/hostcheck.cpp -o $@
 
@@ -45,6 +45,6 @@ TIMING_LIB := fusioninfer_b200/lib/libfi_epp_timing.so
 timing: $(TIMING_LIB)
 $(TIMING_LIB): $(CU_SRCS) $(HDRS) $(OBJDIR)/epp_config.o
 	@mkdir -p $(OBJDIR)/timing
-	for f in hash_kernels index_kernels match_kernels engine; do $(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -DFI_MATCH_TIMING -Xcompiler -fPIC -c $(CSRC)/$$f.cu -o $(OBJDIR)/timing/$$f.o || exit 1; done
+	for f in hash_kernels index_kernels lru_kernels match_kernels engine; do $(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -DFI_MATCH_TIMING -Xcompiler -fPIC -c $(CSRC)/$$f.cu -o $(OBJDIR)/timing/$$f.o || exit 1; done
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJDIR)/timing/*.o $(OBJDIR)/epp_config.o -ldl
 .PHONY: timing

@@ -31,6 +31,8 @@
 #include "kernels.cuh"
 #include "lru.h"
 #include "lru_batch.h"
+#include "lru_device.cuh"
+#include "lru_plan.h"
 #include "xxh64.cuh"
 
 using namespace fi;
@@ -213,6 +215,30 @@ struct fi_epp {
   std::unique_ptr<WorkerPool> pool;  // host LRU workers (fi_epp_index_add_chains), created on first use
   std::vector<WorkerOps> lru_outs;   // their op lists (capacity kept from batch to batch)
   bool verbose = false;              // FI_EPP_VERBOSE
+  // device-resident LRU (lru_kernels.cu): the default for single-rank handles whose lru_capacity holds a whole
+  // chain; option "device_lru" / FI_EPP_DEVICE_LRU=0 selects the host LRU instead.  Allocated at the first Add;
+  // the two are never mixed on one handle.
+  int lru_mode = -1;  // -1: not chosen yet, 0: host LRU, 1: device LRU
+  int lru_want = -1;  // option / environment override (-1: automatic)
+  DevLru dlru{};
+  uint32_t* d_lru_state = nullptr;           // head | tail | count | used | error
+  unsigned long long* d_lru_ctr = nullptr;   // [0] SETs emitted, [1] endpoints maintained, [2] CLEARs of the running sub-batch, [3] CLEARs total
+  struct LruHostStat {
+    uint32_t error, pad;
+    unsigned long long n_sets, n_maintained, n_clears_cur, n_clears;
+  };
+  LruHostStat* h_lru_stat = nullptr;         // pinned copy, refreshed after every call
+  uint32_t* d_lru_plan = nullptr;            // the planner's arrays of the current call
+  uint32_t* h_lru_plan = nullptr;            // pinned staging of the same
+  size_t lru_plan_cap = 0;                   // in u32 words
+  uint32_t *d_lru_slot_of = nullptr, *d_lru_wcount = nullptr, *d_lru_base = nullptr;
+  fi_index_op *d_lru_sets = nullptr, *d_lru_clears = nullptr;
+  uint64_t lru_touch_cap = 0;                // touches per sub-batch the scratch arrays hold
+  uint64_t* d_lru_chains = nullptr;          // staging of host chains
+  size_t lru_chains_cap = 0;                 // in u64 words
+  cudaEvent_t ev_lru = nullptr;              // the previous call's staging has been consumed
+  uint32_t last_plain_R = 0;                 // rows of d_chain the most recent stream-ordered pick wrote
+  LruPlan lru_plan;
   unsigned lru_threads = 0;          // 0: FI_EPP_LRU_THREADS, else min(usable cores, 64)
 
   // endpoints / score tables
@@ -412,6 +438,8 @@ int check_counters(fi_epp* h) {
   if (!h->ctr_pending) return FI_OK;
   FI_CUDA(cudaEventSynchronize(h->ev_ctr));
   h->ctr_pending = false;
+  if (h->h_lru_stat && h->h_lru_stat->error)
+    return fail(h, FI_ERR_STATE, "device LRU: invariant " + std::to_string(h->h_lru_stat->error) + " broken");
   if (h->h_ctr->overflow) return fail(h, FI_ERR_CAPACITY, "index full: raise index_slots");
   const uint64_t used = h->h_ctr->used, tomb = h->h_ctr->tombstones;
   if (used * 10 > h->ix.C * 7) {
@@ -553,6 +581,212 @@ int submit_op(fi_epp* h, uint64_t hash, uint32_t endpoint, uint32_t op) {
     h->h_clears[h->cur_buf][h->n_clears++] = fi_index_op{hash, endpoint, FI_OP_CLEAR};
   }
   if (h->n_sets == kOpChunk || h->n_clears == kOpChunk) return flush_ops(h);
+  return FI_OK;
+}
+
+// ---- device-resident LRU (lru_kernels.cu) --------------------------------------------------------------
+// Which LRU serves this handle's indexer.Add calls: decided at the first one.
+int choose_lru_mode(fi_epp* h) {
+  if (h->lru_mode >= 0) return FI_OK;
+  int want = h->lru_want;
+  if (want < 0) {
+    if (const char* e = std::getenv("FI_EPP_DEVICE_LRU")) want = std::strtol(e, nullptr, 10) != 0;
+  }
+  const bool possible = h->world <= 1 && h->cfg.lru_capacity >= h->cfg.max_blocks && h->cfg.lru_capacity <= (1u << 28);
+  if (want == 1 && !possible)
+    return fail(h, FI_ERR_STATE, "device_lru needs a single-rank handle and lru_capacity >= max_blocks");
+  h->lru_mode = (want < 0 ? possible : want == 1) ? 1 : 0;
+  return FI_OK;
+}
+
+int ensure_dev_lru(fi_epp* h) {
+  if (h->dlru.slots) return FI_OK;
+  const uint32_t EL = h->cfg.endpoint_count, C = h->cfg.lru_capacity;
+  DevLru& d = h->dlru;
+  d.EL = EL;
+  d.capacity = C;
+  d.TS = std::max<uint32_t>(pow2_ceil32(4u * C), 64u);  // <= 70 % full even right before a maintenance (lru_kernels.cu)
+  d.L = d.TS;
+  const size_t slot_bytes = (size_t)EL * (d.TS + 2) * sizeof(LruSlot), log_bytes = (size_t)EL * d.L * sizeof(uint64_t);
+  size_t free_b = 0, total_b = 0;
+  FI_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  h->lru_touch_cap = std::max<uint64_t>((uint64_t)h->cfg.max_batch * h->MP, 1u << 16);
+  const size_t scratch = (size_t)h->lru_touch_cap * (sizeof(uint32_t) + 2 * sizeof(fi_index_op));
+  if (slot_bytes + log_bytes + scratch + (256u << 20) > free_b)
+    return fail(h, FI_ERR_NOMEM, "device LRU does not fit in free HBM (option device_lru = 0 selects the host LRU)");
+  FI_CUDA(cudaMalloc(&d.slots, slot_bytes));
+  FI_CUDA(cudaMalloc(&d.log, log_bytes));
+  FI_CUDA(cudaMalloc(&h->d_lru_state, ((size_t)4 * EL + 2) * sizeof(uint32_t)));
+  FI_CUDA(cudaMalloc(&h->d_lru_ctr, 4 * sizeof(unsigned long long)));
+  FI_CUDA(cudaMallocHost(&h->h_lru_stat, sizeof(fi_epp::LruHostStat)));
+  std::memset(h->h_lru_stat, 0, sizeof(fi_epp::LruHostStat));
+  FI_CUDA(cudaMalloc(&h->d_lru_slot_of, h->lru_touch_cap * sizeof(uint32_t)));
+  FI_CUDA(cudaMalloc(&h->d_lru_sets, h->lru_touch_cap * sizeof(fi_index_op)));
+  FI_CUDA(cudaMalloc(&h->d_lru_clears, h->lru_touch_cap * sizeof(fi_index_op)));
+  FI_CUDA(cudaMalloc(&h->d_lru_wcount, (size_t)h->cfg.max_batch * sizeof(uint32_t)));
+  FI_CUDA(cudaMalloc(&h->d_lru_base, (size_t)h->cfg.max_batch * sizeof(uint32_t)));
+  FI_CUDA(cudaEventCreateWithFlags(&h->ev_lru, cudaEventDisableTiming));
+  FI_CUDA(cudaMemsetAsync(d.slots, 0, slot_bytes, h->s_index));
+  FI_CUDA(cudaMemsetAsync(h->d_lru_state, 0, ((size_t)4 * EL + 2) * sizeof(uint32_t), h->s_index));
+  FI_CUDA(cudaMemsetAsync(h->d_lru_ctr, 0, 4 * sizeof(unsigned long long), h->s_index));
+  FI_CUDA(cudaEventRecord(h->ev_lru, h->s_index));
+  d.head = h->d_lru_state;
+  d.tail = d.head + EL;
+  d.count = d.tail + EL;
+  d.used = d.count + EL;
+  d.error = d.used + EL;
+  d.n_sets = h->d_lru_ctr;
+  d.n_maintained = h->d_lru_ctr + 1;
+  return FI_OK;
+}
+
+// queue the refresh of the pinned LRU status (error flag + totals) behind everything submitted so far
+int lru_refresh_stat(fi_epp* h) {
+  FI_CUDA(cudaMemcpyAsync(&h->h_lru_stat->error, h->dlru.error, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_index));
+  FI_CUDA(cudaMemcpyAsync(&h->h_lru_stat->n_sets, h->d_lru_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_index));
+  return FI_OK;
+}
+
+// indexer.Add(chains[r], endpoints[r]) for r = 0..R-1 through the device LRU.  `chains` is a host pointer
+// (copied to the device first) or, with on_device, memory the index stream can read.
+int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains, bool on_device, uint32_t pitch,
+                   const uint32_t* nblocks, uint32_t R) {
+  int rc = ensure_dev_lru(h);
+  if (rc != FI_OK) return rc;
+  for (uint32_t r = 0; r < R; ++r)
+    if (nblocks[r] > h->cfg.lru_capacity && endpoints[r] - h->cfg.endpoint_begin < h->cfg.endpoint_count)
+      return fail(h, FI_ERR_INVALID, "device LRU: a chain longer than lru_capacity");
+  rc = flush_ops(h);  // ops staged through fi_epp_index_apply come first
+  if (rc != FI_OK) return rc;
+  rc = check_counters(h);
+  if (rc != FI_OK) return rc;
+  const uint32_t EL = h->cfg.endpoint_count, lo = h->cfg.endpoint_begin;
+  const auto t0 = std::chrono::steady_clock::now();
+  LruPlan& pl = h->lru_plan;
+  lru_plan_batch(endpoints, nblocks, R, lo, EL, h->cfg.lru_capacity, h->lru_touch_cap, h->cfg.max_batch, &pl);
+  if (pl.subs.empty()) return FI_OK;
+  const size_t K = pl.req_id.size(), nsub = pl.subs.size();
+  // staging: req_id | req_ep | req_n | req_off | ep_list | ep_start[nsub][EL+1] | inc[nsub][EL]
+  const size_t words = 5 * K + nsub * ((size_t)2 * EL + 1);
+  FI_CUDA(cudaEventSynchronize(h->ev_lru));  // the previous call's staging (and chain copy) has been consumed
+  if (words > h->lru_plan_cap) {
+    cudaFree(h->d_lru_plan);
+    if (h->h_lru_plan) cudaFreeHost(h->h_lru_plan);
+    h->d_lru_plan = nullptr;
+    h->h_lru_plan = nullptr;
+    h->lru_plan_cap = 0;
+    const size_t cap = words + words / 2 + 1024;
+    FI_CUDA(cudaMalloc(&h->d_lru_plan, cap * sizeof(uint32_t)));
+    FI_CUDA(cudaMallocHost(&h->h_lru_plan, cap * sizeof(uint32_t)));
+    h->lru_plan_cap = cap;
+  }
+  uint32_t* hp = h->h_lru_plan;
+  std::memcpy(hp, pl.req_id.data(), K * 4);
+  std::memcpy(hp + K, pl.req_ep.data(), K * 4);
+  std::memcpy(hp + 2 * K, pl.req_n.data(), K * 4);
+  std::memcpy(hp + 3 * K, pl.req_off.data(), K * 4);
+  std::memcpy(hp + 4 * K, pl.ep_list.data(), K * 4);
+  std::memcpy(hp + 5 * K, pl.ep_start.data(), pl.ep_start.size() * 4);
+  std::memcpy(hp + 5 * K + nsub * ((size_t)EL + 1), pl.inc.data(), pl.inc.size() * 4);
+  // the LRU kernels run on the index stream; like every index update they are ordered behind the picks
+  // submitted so far (a pick sees the index as of its call)
+  FI_CUDA(cudaStreamWaitEvent(h->s_index, h->ev_pick, 0));
+  FI_CUDA(cudaMemcpyAsync(h->d_lru_plan, hp, words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_index));
+  h->stats.h2d_bytes += words * sizeof(uint32_t);
+  const uint64_t* d_chains = chains;
+  if (!on_device) {
+    const size_t cw = (size_t)R * pitch;
+    if (cw > h->lru_chains_cap) {
+      cudaFree(h->d_lru_chains);
+      h->d_lru_chains = nullptr;
+      h->lru_chains_cap = 0;
+      FI_CUDA(cudaMalloc(&h->d_lru_chains, cw * sizeof(uint64_t)));
+      h->lru_chains_cap = cw;
+    }
+    // only the rows the plan kept are needed; whole-range copy when most are (one DMA), row copies otherwise
+    if (K * 2 >= R) {
+      FI_CUDA(cudaMemcpyAsync(h->d_lru_chains, chains, cw * sizeof(uint64_t), cudaMemcpyHostToDevice, h->s_index));
+      h->stats.h2d_bytes += cw * sizeof(uint64_t);
+    } else {
+      for (size_t k = 0; k < K; ++k) {
+        const size_t r = pl.req_id[k];
+        FI_CUDA(cudaMemcpyAsync(h->d_lru_chains + r * pitch, chains + r * pitch, (size_t)pl.req_n[k] * sizeof(uint64_t),
+                                cudaMemcpyHostToDevice, h->s_index));
+        h->stats.h2d_bytes += (size_t)pl.req_n[k] * sizeof(uint64_t);
+      }
+    }
+    d_chains = h->d_lru_chains;
+  }
+  const uint32_t* dp = h->d_lru_plan;
+  for (size_t sb = 0; sb < nsub; ++sb) {
+    if (sb) {  // the index counters of the previous sub-batch decide about a rebuild before more keys arrive
+      rc = check_counters(h);
+      if (rc != FI_OK) return rc;
+    }
+    const LruSubBatch& sbt = pl.subs[sb];
+    LruBatch b{};
+    b.req_id = dp + sbt.k_begin;
+    b.req_ep = dp + K + sbt.k_begin;
+    b.req_n = dp + 2 * K + sbt.k_begin;
+    b.req_off = dp + 3 * K + sbt.k_begin;
+    b.ep_list = dp + 4 * K + sbt.k_begin;
+    b.ep_start = dp + 5 * K + sb * ((size_t)EL + 1);
+    const uint32_t* inc = dp + 5 * K + nsub * ((size_t)EL + 1) + sb * (size_t)EL;
+    b.chains = d_chains;
+    b.pitch = pitch;
+    b.K = sbt.k_end - sbt.k_begin;
+    b.slot_of = h->d_lru_slot_of;
+    b.wcount = h->d_lru_wcount;
+    b.base = h->d_lru_base;
+    b.sets = h->d_lru_sets;
+    {
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_lru_maintain(h->dlru, inc, false, h->s_index));
+    }
+    {
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_lru_touch(h->dlru, b, h->s_index));
+    }
+    {
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_lru_count(h->dlru, b, h->s_index));
+    }
+    {
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_lru_scan(h->dlru, b, h->s_index));
+    }
+    {
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_lru_append(h->dlru, b, lo, h->s_index));
+    }
+    {
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_index_set(h->ix, h->d_ctr, h->d_lru_sets, sbt.touches, lo, EL, h->rank, GossipLog{}, h->s_index));
+    }
+    FI_CUDA(cudaMemsetAsync(h->d_lru_ctr + 2, 0, sizeof(unsigned long long), h->s_index));
+    {
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_lru_evict(h->dlru, h->d_lru_clears, h->d_lru_ctr + 2, h->lru_touch_cap, lo, h->s_index));
+    }
+    {
+      LaunchScope ls(h, h->s_index, K_INDEX);
+      FI_CUDA(launch_index_clear_counted(h->ix, h->d_ctr, h->d_lru_clears, sbt.touches, h->d_lru_ctr + 2, lo, EL, h->rank,
+                                         GossipLog{}, h->s_index));
+    }
+    FI_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(IndexCounters), cudaMemcpyDeviceToHost, h->s_index));
+    FI_CUDA(cudaEventRecord(h->ev_ctr, h->s_index));
+    h->ctr_pending = true;
+  }
+  rc = lru_refresh_stat(h);
+  if (rc != FI_OK) return rc;
+  FI_CUDA(cudaEventRecord(h->ev_ctr, h->s_index));  // covers the status copy too
+  FI_CUDA(cudaEventRecord(h->ev_lru, h->s_index));
+  FI_CUDA(cudaEventRecord(h->ev_index, h->s_index));
+  if (h->verbose) {
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[fi_epp] device LRU: %u requests (%zu kept), %zu sub-batch(es), host side %.3f ms\n", R, K, nsub,
+                 std::chrono::duration<double, std::milli>(t1 - t0).count());
+  }
   return FI_OK;
 }
 
@@ -924,6 +1158,7 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
   if (rc != FI_OK) return rc;
   FI_CUDA(cudaEventRecord(h->ev_pick, h->s_main));  // index updates submitted later wait for this pick
   FI_CUDA(cudaEventRecord(h->ev_plain, h->s_main));
+  h->last_plain_R = R;
   return FI_OK;
 }
 
@@ -961,6 +1196,7 @@ int submit_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, 
   FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_in, 0));
   if (h->pipe_seq >= 2) FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_b[slot], 0));
   FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_plain, 0));
+  if (h->ev_lru) FI_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_lru, 0));  // a device-LRU Add may still be reading d_chain
   {
     LaunchScope ls(h, h->s_a, K_HASH);
     // The SM split of the pipeline: this batch's block hashing runs BESIDE the previous batch's match_pick —
@@ -1149,6 +1385,20 @@ void fi_epp_destroy(fi_epp* h) {
   h->pool.reset();
   h->lrus.clear();
   h->lru_arena.release();
+  cudaFree(h->dlru.slots);
+  cudaFree(h->dlru.log);
+  cudaFree(h->d_lru_state);
+  cudaFree(h->d_lru_ctr);
+  if (h->h_lru_stat) cudaFreeHost(h->h_lru_stat);
+  cudaFree(h->d_lru_plan);
+  if (h->h_lru_plan) cudaFreeHost(h->h_lru_plan);
+  cudaFree(h->d_lru_slot_of);
+  cudaFree(h->d_lru_wcount);
+  cudaFree(h->d_lru_base);
+  cudaFree(h->d_lru_sets);
+  cudaFree(h->d_lru_clears);
+  cudaFree(h->d_lru_chains);
+  if (h->ev_lru) cudaEventDestroy(h->ev_lru);
   free_index(h->ix);
   free_index(h->ix_spare);
   for (int b = 0; b < 2; ++b) {
@@ -1438,7 +1688,10 @@ int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes,
   if (endpoint >= h->cfg.num_endpoints) return fail(h, FI_ERR_INVALID, "endpoint out of range");
   const uint32_t e = endpoint - h->cfg.endpoint_begin;
   if (e >= h->cfg.endpoint_count) return FI_OK;  // another rank's shard
-  int rc = check_counters(h);
+  int rc = choose_lru_mode(h);
+  if (rc != FI_OK) return rc;
+  if (h->lru_mode == 1) return lru_device_add(h, &endpoint, hashes, false, n, &n, 1);
+  rc = check_counters(h);
   if (rc != FI_OK) return rc;
   LruSet& l = h->lrus[e];
   for (uint32_t i = 0; i < n; ++i) {
@@ -1483,6 +1736,8 @@ int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t
     if (endpoints[r] != FI_NO_ENDPOINT && endpoints[r] >= h->cfg.num_endpoints) err = fail(h, FI_ERR_INVALID, "endpoint out of range");
     else if (nblocks[r] > pitch_blocks) err = fail(h, FI_ERR_INVALID, "nblocks[r] larger than the chain pitch");
   }
+  if (err == FI_OK) err = choose_lru_mode(h);
+  if (err == FI_OK && h->lru_mode == 1) return lru_device_add(h, endpoints, chains, false, pitch_blocks, nblocks, R);
   if (err == FI_OK) err = check_counters(h);
 
   // ---- 1./2. bucket the requests by endpoint and walk the LRUs on the worker pool (lru_batch.h)
@@ -1610,6 +1865,60 @@ int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t
   return err;
 }
 
+// The same with the chains already in device memory (e.g. the chains_out of fi_epp_pick_batch_device): nothing
+// but the two small host arrays crosses PCIe.  Device LRU only.
+int fi_epp_index_add_chains_device(fi_epp* h, const uint32_t* endpoints, const void* d_chains, uint32_t pitch_blocks,
+                                   const uint32_t* nblocks, uint32_t R, void* stream) {
+  if (!h || ((!endpoints || !nblocks) && R)) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  if (!h->cfg.lru_capacity) return fail(h, FI_ERR_STATE, "lru_capacity is 0: no LRU");
+  if (!d_chains) {  // the chains of the handle's most recent stream-ordered pick, still in its own buffer
+    if (R > h->last_plain_R) return fail(h, FI_ERR_STATE, "no pick batch of that size to take the chains from");
+    d_chains = h->d_chain;
+    pitch_blocks = h->MP;
+  }
+  for (uint32_t r = 0; r < R; ++r) {
+    if (endpoints[r] != FI_NO_ENDPOINT && endpoints[r] >= h->cfg.num_endpoints) return fail(h, FI_ERR_INVALID, "endpoint out of range");
+    if (nblocks[r] > pitch_blocks) return fail(h, FI_ERR_INVALID, "nblocks[r] larger than the chain pitch");
+  }
+  int rc = choose_lru_mode(h);
+  if (rc != FI_OK) return rc;
+  if (h->lru_mode != 1) return fail(h, FI_ERR_STATE, "fi_epp_index_add_chains_device needs the device LRU");
+  // the chains were produced on the caller's stream
+  FI_CUDA(cudaEventRecord(h->ev_user, (cudaStream_t)stream));
+  FI_CUDA(cudaStreamWaitEvent(h->s_index, h->ev_user, 0));
+  return lru_device_add(h, endpoints, static_cast<const uint64_t*>(d_chains), true, pitch_blocks, nblocks, R);
+}
+
+// Diagnostics: the device LRU's content for one endpoint, least recently used first.
+int fi_epp_lru_dump(fi_epp* h, uint32_t endpoint, uint64_t* out, uint32_t cap, uint32_t* n_out) {
+  if (!h || !n_out || (!out && cap)) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  *n_out = 0;
+  const uint32_t e = endpoint - h->cfg.endpoint_begin;
+  if (e >= h->cfg.endpoint_count) return fail(h, FI_ERR_INVALID, "endpoint outside this handle's shard");
+  if (h->lru_mode != 1 || !h->dlru.slots) return h->lru_mode == 0 ? fail(h, FI_ERR_STATE, "the handle runs the host LRU") : FI_OK;
+  uint64_t* d_out = nullptr;
+  uint32_t* d_n = nullptr;
+  FI_CUDA(cudaMalloc(&d_out, ((size_t)h->dlru.capacity + 1) * sizeof(uint64_t)));
+  if (cudaMalloc(&d_n, sizeof(uint32_t)) != cudaSuccess) {
+    cudaFree(d_out);
+    return fail(h, FI_ERR_NOMEM, "cudaMalloc failed");
+  }
+  uint32_t n = 0;
+  cudaError_t er = launch_lru_dump(h->dlru, e, d_out, d_n, h->s_index);
+  if (er == cudaSuccess) er = cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, h->s_index);
+  if (er == cudaSuccess) er = cudaStreamSynchronize(h->s_index);
+  if (er == cudaSuccess && n) er = cudaMemcpy(out, d_out, (size_t)std::min(n, cap) * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_out);
+  cudaFree(d_n);
+  if (er != cudaSuccess) return fail(h, FI_ERR_CUDA, cudaGetErrorString(er));
+  *n_out = n;
+  return FI_OK;
+}
+
 int fi_epp_index_sync(fi_epp* h) {
   if (!h) return FI_ERR_INVALID;
   std::lock_guard<std::mutex> lk(h->mu);
@@ -1635,7 +1944,14 @@ int fi_epp_index_stats(fi_epp* h, fi_index_stats* out) {
   out->rebuilds = h->rebuilds;
   out->ops_applied = h->ops_applied;
   uint64_t l = 0;
-  for (auto& s : h->lrus) l += s.size();
+  if (h->lru_mode == 1 && h->dlru.slots) {
+    std::vector<uint32_t> cnt(h->dlru.EL);
+    FI_CUDA(cudaMemcpy(cnt.data(), h->dlru.count, cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint32_t c2 : cnt) l += c2;
+    out->ops_applied += h->h_lru_stat->n_sets + h->h_lru_stat->n_clears;
+  } else {
+    for (auto& s : h->lrus) l += s.size();
+  }
   out->lru_entries = l;
   return FI_OK;
 }
@@ -1917,6 +2233,12 @@ int fi_epp_set_option(fi_epp* h, const char* name, int64_t value) {
   if (n == "pipe_hash_ctas" || n == "pipe_match_ctas") {
     if (value < 0 || value > 32) return fail(h, FI_ERR_INVALID, n + ": 0..32");
     (n == "pipe_hash_ctas" ? h->pipe_hash_ctas : h->pipe_match_ctas) = (uint32_t)value;
+    return FI_OK;
+  }
+  if (n == "device_lru") {
+    if (value != 0 && value != 1) return fail(h, FI_ERR_INVALID, "device_lru: 0 or 1");
+    if (h->lru_mode >= 0 && h->lru_mode != (int)value) return fail(h, FI_ERR_STATE, "device_lru: the handle's LRU is already in use");
+    h->lru_want = (int)value;
     return FI_OK;
   }
   if (n == "lru_threads") {

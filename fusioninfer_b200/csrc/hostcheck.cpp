@@ -3,11 +3,15 @@
 // (tests/test_host_logic.py).  Not part of libfi_epp.so and never used to serve a pick.
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
+#include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "bitslice.cuh"
 #include "lru.h"
 #include "lru_batch.h"
+#include "lru_plan.h"
 #include "tiebreak.cuh"
 #include "xxh64.cuh"
 
@@ -166,6 +170,75 @@ int fihc_lru_batch_check(uint32_t E, uint32_t cap, const uint32_t* endpoints, co
     }
   }
   if (segments) *segments = max_seg;
+  return 0;
+}
+
+// The device LRU's batch rule (lru_kernels.cu) on the CPU: plan the batch with lru_plan_batch, apply every
+// sub-batch AT ONCE — per endpoint: the keys touched move behind everything else in the order of their LAST
+// touch, then the oldest entries beyond the capacity go — and compare recency order and content with one LRU
+// per endpoint touched request after request.  0 if identical; *subs = sub-batches of the last batch.
+int fihc_lru_plan_check(uint32_t E, uint32_t cap, const uint32_t* endpoints, const uint64_t* chains, uint32_t pitch,
+                        const uint32_t* nblocks, uint32_t R, uint32_t batches, uint64_t cap_touches, uint32_t cap_requests,
+                        uint32_t* subs) {
+  std::vector<std::vector<uint64_t>> order(E);  // oldest first
+  std::vector<fi::LruSet> seq(E, fi::LruSet(cap));
+  std::vector<std::vector<uint64_t>> seq_order(E);
+  fi::LruPlan pl;
+  for (uint32_t b = 0; b < batches; ++b) {
+    const uint32_t* ep = endpoints + (size_t)b * R;
+    const uint64_t* ch = chains + (size_t)b * R * pitch;
+    const uint32_t* nb = nblocks + (size_t)b * R;
+    fi::lru_plan_batch(ep, nb, R, 0, E, cap, cap_touches, cap_requests, &pl);
+    if (subs) *subs = (uint32_t)pl.subs.size();
+    size_t covered = 0;
+    for (size_t sb = 0; sb < pl.subs.size(); ++sb) {
+      const fi::LruSubBatch& s = pl.subs[sb];
+      if (s.k_end - s.k_begin > cap_requests || s.touches > cap_touches) return 10;
+      const uint32_t* st = pl.ep_start.data() + sb * ((size_t)E + 1);
+      const uint32_t* inc = pl.inc.data() + sb * (size_t)E;
+      for (uint32_t e = 0; e < E; ++e) {
+        // touches of endpoint e in this sub-batch, in request order
+        std::vector<uint64_t> t;
+        uint32_t last_k = 0;
+        for (uint32_t i = st[e]; i < st[e + 1]; ++i) {
+          const uint32_t k = s.k_begin + pl.ep_list[s.k_begin + i];
+          if (i > st[e] && k <= last_k) return 11;  // ascending
+          last_k = k;
+          if (pl.req_ep[k] != e) return 12;
+          const uint64_t* c = ch + (size_t)pl.req_id[k] * pitch;
+          t.insert(t.end(), c, c + pl.req_n[k]);
+        }
+        if (t.size() != inc[e] || t.size() > cap) return 13;
+        covered += t.size();
+        std::unordered_set<uint64_t> seen;
+        std::vector<uint64_t> winners;  // keys by last touch, newest first
+        for (size_t i = t.size(); i-- > 0;)
+          if (seen.insert(t[i]).second) winners.push_back(t[i]);
+        std::vector<uint64_t>& o = order[e];
+        o.erase(std::remove_if(o.begin(), o.end(), [&](uint64_t k) { return seen.count(k) != 0; }), o.end());
+        o.insert(o.end(), winners.rbegin(), winners.rend());
+        if (o.size() > cap) o.erase(o.begin(), o.begin() + (o.size() - cap));
+      }
+    }
+    size_t want_cov = 0;
+    for (uint32_t r = 0; r < R; ++r) {
+      if (ep[r] >= E) continue;
+      want_cov += nb[r];
+      for (uint32_t i = 0; i < nb[r]; ++i) {
+        const uint64_t k = ch[(size_t)r * pitch + i];
+        uint64_t ev = 0;
+        bool did = false;
+        const bool ins = seq[ep[r]].touch(k, &ev, &did);
+        std::vector<uint64_t>& so = seq_order[ep[r]];
+        if (!ins) so.erase(std::find(so.begin(), so.end(), k));
+        so.push_back(k);
+        if (did) so.erase(std::find(so.begin(), so.end(), ev));
+      }
+    }
+    if (covered != want_cov) return 14;
+    for (uint32_t e = 0; e < E; ++e)
+      if (order[e] != seq_order[e]) return 1;
+  }
   return 0;
 }
 

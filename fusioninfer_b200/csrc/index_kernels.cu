@@ -188,8 +188,13 @@ __device__ __forceinline__ void rank_vanished(const IndexView& ix, IndexCounters
 template <bool REMOTE>
 __global__ void __launch_bounds__(256) index_clear_kernel(IndexView ix, IndexCounters* ctr, const fi_index_op* __restrict__ ops,
                                                           const uint64_t* __restrict__ hashes, uint64_t n, uint32_t ep_begin,
-                                                          uint32_t ep_count, uint32_t rank, GossipLog log) {
+                                                          uint32_t ep_count, uint32_t rank, GossipLog log,
+                                                          const unsigned long long* __restrict__ n_dev) {
   const uint32_t rbit = 1u << rank;
+  if (n_dev) {  // op count produced on the device (lru_evict_kernel): n is only the buffer's capacity
+    const unsigned long long nd = *n_dev;
+    n = nd < n ? nd : n;
+  }
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t hsh;
     uint32_t e = 0;
@@ -292,7 +297,15 @@ cudaError_t launch_index_set(IndexView ix, IndexCounters* ctr, const fi_index_op
 cudaError_t launch_index_clear(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n,
                                uint32_t ep_begin, uint32_t ep_count, uint32_t rank, GossipLog log, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  index_clear_kernel<false><<<grid_for(n), 256, 0, s>>>(ix, ctr, ops, nullptr, n, ep_begin, ep_count, rank, log);
+  index_clear_kernel<false><<<grid_for(n), 256, 0, s>>>(ix, ctr, ops, nullptr, n, ep_begin, ep_count, rank, log, nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_index_clear_counted(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t cap,
+                                       const unsigned long long* n_dev, uint32_t ep_begin, uint32_t ep_count, uint32_t rank,
+                                       GossipLog log, cudaStream_t s) {
+  if (cap == 0) return cudaSuccess;
+  index_clear_kernel<false><<<grid_for(cap), 256, 0, s>>>(ix, ctr, ops, nullptr, cap, ep_begin, ep_count, rank, log, n_dev);
   return cudaGetLastError();
 }
 
@@ -306,7 +319,7 @@ cudaError_t launch_index_remote_appear(IndexView ix, IndexCounters* ctr, const u
 cudaError_t launch_index_remote_vanish(IndexView ix, IndexCounters* ctr, const uint64_t* hashes, uint64_t n, uint32_t rank,
                                        cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  index_clear_kernel<true><<<grid_for(n), 256, 0, s>>>(ix, ctr, nullptr, hashes, n, 0, 0, rank, GossipLog{});
+  index_clear_kernel<true><<<grid_for(n), 256, 0, s>>>(ix, ctr, nullptr, hashes, n, 0, 0, rank, GossipLog{}, nullptr);
   return cudaGetLastError();
 }
 

@@ -188,6 +188,10 @@ cudaError_t launch_index_set(IndexView ix, IndexCounters* ctr, const fi_index_op
                              uint32_t ep_begin, uint32_t ep_count, uint32_t rank, GossipLog log, cudaStream_t s);
 cudaError_t launch_index_clear(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t n,
                                uint32_t ep_begin, uint32_t ep_count, uint32_t rank, GossipLog log, cudaStream_t s);
+// the same with the op count read from device memory (ops produced by a kernel; cap = buffer capacity)
+cudaError_t launch_index_clear_counted(IndexView ix, IndexCounters* ctr, const fi_index_op* ops, uint64_t cap,
+                                       const unsigned long long* n_dev, uint32_t ep_begin, uint32_t ep_count, uint32_t rank,
+                                       GossipLog log, cudaStream_t s);
 // replay another rank's transitions into this rank's directory (n hashes; bit = that rank)
 cudaError_t launch_index_remote_appear(IndexView ix, IndexCounters* ctr, const uint64_t* hashes, uint64_t n,
                                        uint32_t rank, cudaStream_t s);

@@ -182,6 +182,23 @@ class EndpointPicker:
         self._check(self._lib.fi_epp_index_add_chains(self._h, _ptr(endpoints), _ptr(chains), pitch, _ptr(nblocks), R),
                     "fi_epp_index_add_chains")
 
+    def index_add_chains_device(self, endpoints: np.ndarray, d_chains: int, pitch: int, nblocks: np.ndarray, stream: int = 0):
+        """The same with the chains in device memory (pointer; e.g. the chains_out of pick_batch_device, written on
+        `stream`): only the two small host arrays cross PCIe.  Needs the device-resident LRU (the default)."""
+        endpoints = np.ascontiguousarray(endpoints, dtype=np.uint32)
+        nblocks = np.ascontiguousarray(nblocks, dtype=np.uint32)
+        self._check(self._lib.fi_epp_index_add_chains_device(self._h, _ptr(endpoints), C.c_void_p(d_chains), pitch, _ptr(nblocks),
+                                                             len(endpoints), C.c_void_p(stream)),
+                    "fi_epp_index_add_chains_device")
+
+    def lru_dump(self, endpoint: int) -> np.ndarray:
+        """Keys of `endpoint` in the device-resident LRU, least recently used first (diagnostics)."""
+        cap = max(int(self.cfg.lru_capacity), 1) + 1
+        out = np.zeros(cap, dtype=np.uint64)
+        n = C.c_uint32(0)
+        self._check(self._lib.fi_epp_lru_dump(self._h, endpoint, _ptr(out), cap, C.byref(n)), "fi_epp_lru_dump")
+        return out[: n.value].copy()
+
     def index_sync(self):
         self._check(self._lib.fi_epp_index_sync(self._h), "fi_epp_index_sync")
 

@@ -274,6 +274,21 @@ int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes,
 int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains, uint32_t pitch_blocks,
                             const uint32_t* nblocks, uint32_t R);
 
+/* The same with the chains already in device memory — the chains_out of fi_epp_pick_batch_device, written on
+ * `stream` — so that only the two small host arrays cross PCIe.  Served by the device-resident LRU
+ * (fusioninfer_b200/csrc/lru_kernels.cu), which is also what fi_epp_index_add_chain(s) use on a single-rank
+ * handle with lru_capacity >= max_blocks unless fi_epp_set_option(h, "device_lru", 0) / FI_EPP_DEVICE_LRU=0
+ * selected the host LRU before the first Add; FI_ERR_STATE when the handle runs the host LRU.
+ * d_chains == NULL: the chains of this handle's most recent fi_epp_pick_batch / fi_epp_pick_batch_device call,
+ * read from the handle's own buffer (pitch_blocks ignored; R <= that call's R) — the PreRequest step right after
+ * a pick, with nothing but the decisions crossing PCIe. */
+int fi_epp_index_add_chains_device(fi_epp* h, const uint32_t* endpoints, const void* d_chains, uint32_t pitch_blocks,
+                                   const uint32_t* nblocks, uint32_t R, void* stream);
+
+/* Diagnostics: the keys of `endpoint` in the device-resident LRU, least recently used first (at most `cap`
+ * written, *n_out = how many it holds).  FI_ERR_STATE when the handle runs the host LRU. */
+int fi_epp_lru_dump(fi_epp* h, uint32_t endpoint, uint64_t* out, uint32_t cap, uint32_t* n_out);
+
 int fi_epp_index_sync(fi_epp* h); /* block until submitted ops are applied */
 
 /* Diagnostics: out[i] = 1 iff (q[i].endpoint, q[i].hash) is in this handle's GPU index. */

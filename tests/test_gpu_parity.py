@@ -278,11 +278,14 @@ def test_pick_reference_block_size_5_ascii():
     gpu.close()
 
 
-def test_lru_add_chain_path_matches_oracle():
-    """Post-pick index maintenance (upstream PreRequest → indexer.Add) through the host LRU."""
+@pytest.mark.parametrize("device_lru", [0, 1])
+def test_lru_add_chain_path_matches_oracle(device_lru):
+    """Post-pick index maintenance (upstream PreRequest → indexer.Add), one chain per call, through the host LRU
+    and through the device-resident LRU."""
     wl = H.small_workload(E=24, R=96, lru_capacity=0)
     cfg = H.config_for(wl, profiles=WEIGHTED, lru_capacity=400, index_slots=1 << 16)  # ~12 chains/endpoint: steady eviction
     gpu, cpu = _pair(cfg)
+    gpu.set_option("device_lru", device_lru)
     st = wl.endpoint_states()
     gpu.update_endpoints(st)
     cpu.update_endpoints(st)
@@ -612,17 +615,19 @@ def test_gpu_equals_the_second_restatement(lpm):
         gpu.close()
 
 
-@pytest.mark.parametrize("threads", ["1", "5"])
+@pytest.mark.parametrize("threads", ["1", "5", "device"])
 def test_add_chains_batch_equals_sequential_oracle(threads, monkeypatch):
-    """fi_epp_index_add_chains (host LRU walked on a worker pool, segments where a hash is re-added after its
-    eviction inside the same batch) equals the oracle adding the chains one request at a time — over several
-    steps with LRU churn (capacity far below one batch's inserts per endpoint, so the same-batch re-add path
-    runs), and the picks stay bit-exact."""
-    monkeypatch.setenv("FI_EPP_LRU_THREADS", threads)
+    """fi_epp_index_add_chains equals the oracle adding the chains one request at a time — over several steps
+    with LRU churn (capacity far below one batch's inserts per endpoint), and the picks stay bit-exact.  Host LRU
+    walked on a worker pool (segments where a hash is re-added after its eviction inside the same batch), and the
+    device-resident LRU (the batch is cut into sub-batches of at most `capacity` touches per endpoint)."""
+    if threads != "device":
+        monkeypatch.setenv("FI_EPP_LRU_THREADS", threads)
     wl = H.small_workload(E=12, R=160, T=768, max_blocks=48, lru_capacity=70)
     prof = [{"name": "d", "scorers": [(P, 100), (K, 9), (Q, 5)]}]
     cfg = H.config_for(wl, profiles=prof, lru_capacity=70, index_slots=1 << 16)
     gpu, cpu = _pair(cfg)
+    gpu.set_option("device_lru", 1 if threads == "device" else 0)
     st = wl.endpoint_states()
     gpu.update_endpoints(st)
     cpu.update_endpoints(st)
@@ -664,4 +669,158 @@ def test_chained_label_filters_third_label():
     ok = ((st["role_mask"] & 5) != 0) & ((st["role_mask"] & 24) != 0) & ((st["role_mask"] & 32) != 0)
     assert ok[got[:, 0]["endpoint"]].all() and (got[:, 1]["endpoint"] == abi.FI_NO_ENDPOINT).all()
     assert ((st["role_mask"][got[:, 2]["endpoint"]] & 16) != 0).all()
+    gpu.close()
+
+
+class _PyLru:
+    """hashicorp/golang-lru semantics, the plainest way: an ordered dict per endpoint (oldest first)."""
+
+    def __init__(self, cap):
+        from collections import OrderedDict
+
+        self.cap, self.d = cap, OrderedDict()
+
+    def add_chain(self, keys):
+        for k in keys:
+            k = int(k)
+            if k in self.d:
+                self.d.move_to_end(k)
+            else:
+                self.d[k] = True
+                if len(self.d) > self.cap:
+                    self.d.popitem(last=False)
+
+
+def _device_lru_handle(E, cap, max_blocks, max_batch=256):
+    wl = H.small_workload(E=E, R=8, T=max_blocks * 16, max_blocks=max_blocks, lru_capacity=0)
+    cfg = H.config_for(wl, lru_capacity=cap, index_slots=1 << 17, max_batch=max_batch)
+    gpu = EndpointPicker(cfg)
+    gpu.set_option("device_lru", 1)
+    return gpu
+
+
+def _check_lru_state(gpu, ref, E):
+    """recency order AND index membership equal the sequential reference"""
+    for e in range(E):
+        got = gpu.lru_dump(e)
+        want = np.array(list(ref[e].d.keys()), dtype=np.uint64)
+        assert np.array_equal(got, want), f"endpoint {e}: {len(got)} vs {len(want)} entries"
+    # membership: every key ever seen, at every endpoint
+    seen = sorted({k for l in ref for k in l.d} | getattr(_check_lru_state, "extra", set()))
+    q = [(k, e, 0) for k in seen for e in range(E)]
+    have = gpu.index_contains(H.ops_array(q))
+    want = np.array([k in ref[e].d for k in seen for e in range(E)], dtype=bool)
+    assert np.array_equal(have.astype(bool), want)
+
+
+def test_device_lru_order_and_membership_random_batches():
+    """The device-resident LRU against a sequential ordered-dict LRU: random batches with shared prefixes, keys
+    re-touched within and across batches, hot endpoints that force several sub-batches, enough churn for the
+    log compaction / table rebuild to run many times; recency order (fi_epp_lru_dump) and index membership
+    are compared after every batch."""
+    E, cap, M = 6, 90, 24
+    gpu = _device_lru_handle(E, cap, M)
+    ref = [_PyLru(cap) for _ in range(E)]
+    rng = np.random.default_rng(2024)
+    ever = set()
+    # a pool of prefix chains; requests take a prefix of a pool chain plus a private tail
+    pool = rng.integers(1, 1 << 62, size=(40, M), dtype=np.uint64)
+    for step in range(40):
+        R = int(rng.integers(1, 60))
+        chains = np.zeros((R, M), dtype=np.uint64)
+        nb = rng.integers(0, M + 1, size=R).astype(np.uint32)
+        eps = rng.integers(0, E, size=R).astype(np.uint32)
+        if step % 5 == 0:
+            eps[:] = eps[0]  # hot spot: one endpoint takes the whole batch
+        eps[rng.random(R) < 0.05] = abi.FI_NO_ENDPOINT
+        for r in range(R):
+            c = pool[rng.integers(0, len(pool))]
+            cut = int(rng.integers(0, M + 1))
+            chains[r, :cut] = c[:cut]
+            chains[r, cut:] = rng.integers(1, 1 << 62, size=M - cut, dtype=np.uint64)
+            if rng.random() < 0.1 and nb[r] >= 2:
+                chains[r, nb[r] - 1] = chains[r, 0]  # the same key twice in one chain
+        gpu.index_add_chains(eps, chains, nb)
+        for r in range(R):
+            if eps[r] != abi.FI_NO_ENDPOINT:
+                ref[eps[r]].add_chain(chains[r, : nb[r]])
+                ever.update(int(k) for k in chains[r, : nb[r]])
+        if step % 4 == 3 or step < 3:
+            _check_lru_state.extra = set(list(ever)[:: max(1, len(ever) // 400)])
+            _check_lru_state(gpu, ref, E)
+    _check_lru_state.extra = ever
+    _check_lru_state(gpu, ref, E)
+    st = gpu.index_stats()
+    assert st.lru_entries == sum(len(l.d) for l in ref) and st.tombstones > 0
+    gpu.close()
+
+
+def test_device_lru_edge_cases():
+    """capacity hit exactly; a chain as long as the capacity; the hashes 0 and ~0 (the tables' own markers);
+    single-chain calls interleaved with batches; empty calls."""
+    E, cap, M = 3, 16, 16
+    gpu = _device_lru_handle(E, cap, M)
+    ref = [_PyLru(cap) for _ in range(E)]
+    ever = set()
+
+    def add(eps, chains, nb):
+        eps = np.asarray(eps, dtype=np.uint32)
+        chains = np.asarray(chains, dtype=np.uint64).reshape(len(eps), -1)
+        nb = np.asarray(nb, dtype=np.uint32)
+        gpu.index_add_chains(eps, chains, nb)
+        for r in range(len(eps)):
+            ref[eps[r]].add_chain(chains[r, : nb[r]])
+            ever.update(int(k) for k in chains[r, : nb[r]])
+        _check_lru_state.extra = ever
+        _check_lru_state(gpu, ref, E)
+
+    a = np.arange(1, 17, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    add([0], [a], [16])                      # fills endpoint 0 exactly
+    add([0], [a[::-1].copy()], [16])         # same keys, reversed recency: no eviction
+    b = a + np.uint64(7)
+    add([0, 0], [b, a], [16, 16])            # a chain of `capacity` new keys evicts everything, then back again
+    special = np.array([0, 0xFFFFFFFFFFFFFFFF, 5, 0, 9, 0xFFFFFFFFFFFFFFFF] + [11] * 10, dtype=np.uint64)
+    add([1, 2], [special, special], [6, 4])  # the hashes 0 and ~0 are ordinary members
+    for i in range(20):                      # push them out again, one new key per call (single-chain entry point)
+        k = np.array([1000 + i], dtype=np.uint64)
+        gpu.index_add_chain(1, k)
+        ref[1].add_chain(k)
+        ever.add(1000 + i)
+    _check_lru_state.extra = ever
+    _check_lru_state(gpu, ref, E)
+    add([1], [special], [6])                 # and in again
+    gpu.index_add_chains(np.zeros(0, np.uint32), np.zeros((0, M), np.uint64), np.zeros(0, np.uint32))
+    add([2, 2, 2], [a, b, a], [0, 3, 0])     # zero-length chains are skipped
+    gpu.close()
+
+
+def test_device_lru_from_device_chains():
+    """fi_epp_index_add_chains_device: the chains stay in device memory (chains_out of the device pick); same
+    picks as the oracle over several churn steps."""
+    import torch
+
+    wl = H.small_workload(E=40, R=256, T=512, max_blocks=32, lru_capacity=0)
+    prof = [{"name": "d", "scorers": [(P, 100), (K, 9), (Q, 5)]}]
+    cfg = H.config_for(wl, profiles=prof, lru_capacity=300, index_slots=1 << 17)
+    gpu, cpu = _pair(cfg)
+    st = wl.endpoint_states()
+    gpu.update_endpoints(st)
+    cpu.update_endpoints(st)
+    d_out = torch.zeros(wl.R * 16, dtype=torch.uint8, device="cuda")
+    d_ch = torch.zeros(wl.R * wl.max_blocks, dtype=torch.int64, device="cuda")
+    for step in range(5):
+        tok, offs = wl.prompts(batch=step % 2)
+        d_tok = torch.from_numpy(tok.view(np.int32)).cuda()
+        d_off = torch.from_numpy(offs.view(np.int64)).cuda()
+        d_h0 = torch.full((wl.R,), np.uint64(wl.h0).astype(np.int64), dtype=torch.int64, device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+        gpu.pick_batch_device(d_tok.data_ptr(), d_off.data_ptr(), d_h0.data_ptr(), wl.R, tok.nbytes, d_out.data_ptr(),
+                              d_chains=d_ch.data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(H.PICK_DTYPE).reshape(wl.R, 1)
+        want, wch = cpu.pick_batch(tok, offs, wl.h0, want_chains=True)
+        assert H.picks_equal(got, want), f"step {step}\n" + H.describe_diff(got, want)
+        gpu.index_add_chains_device(got[:, 0]["endpoint"], d_ch.data_ptr(), wl.max_blocks, got[:, 0]["n_blocks"], stream=stream)
+        cpu.index_add_chains(want[:, 0]["endpoint"], wch, want[:, 0]["n_blocks"])
+    assert gpu.index_stats().tombstones > 0
     gpu.close()

@@ -1,11 +1,15 @@
 #!/usr/bin/env python
 """Index-maintenance path under churn: every pick batch is followed by upstream's
-PreRequest step for the whole batch — indexer.Add(chain_r, picked endpoint_r) — through
-fi_epp_index_add_chains (host LRUs walked on a worker pool; SET/CLEAR deltas streamed to the GPU index on the
-side stream, ordered before the next pick).  Picks are checked bit-exactly against the oracle doing the same
-work (sequentially, one chain at a time), whose time is reported beside ours.
+PreRequest step for the whole batch — indexer.Add(chain_r, picked endpoint_r).  Two implementations:
+  --lru device (default)  the GPU-resident LRU (lru_kernels.cu): the chains never leave the device
+                          (fi_epp_index_add_chains_device with the handle's own chain buffer), only the picked
+                          endpoints come back from the host;
+  --lru host              fi_epp_index_add_chains on the host LRU (worker pool; SET/CLEAR deltas streamed to the
+                          GPU index on the side stream, ordered before the next pick).
+Picks are checked bit-exactly against the oracle doing the same work (sequentially, one chain at a time), whose
+time is reported beside ours.
 
-    python tools/bench_churn.py [--cfg 3] [--requests N] [--steps 12] [--threads T] [--no-oracle]
+    python tools/bench_churn.py [--cfg 3] [--requests N] [--steps 12] [--lru host --threads T] [--no-oracle]
 
 Defaults = BASELINE.json's headline pool: 1 024 endpoints, lruCapacityPerServer 31 250
 (/root/reference/pkg/router/strategy.go:59), 16 384 requests of 4 096 tokens per step.  The index starts
@@ -32,9 +36,10 @@ def main():
     ap.add_argument("--cfg", type=int, default=3)
     ap.add_argument("--requests", type=int, default=0)
     ap.add_argument("--endpoints", type=int, default=0)
-    ap.add_argument("--lru", type=int, default=0)
+    ap.add_argument("--lru-capacity", dest="lru", type=int, default=0)
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--lru", dest="lru_impl", choices=["device", "host"], default="device")
     ap.add_argument("--oracle-steps", type=int, default=2, help="steps the oracle mirrors (it is ~100x slower)")
     ap.add_argument("--no-oracle", action="store_true")
     ap.add_argument("--slot-mult", type=int, default=2)
@@ -58,6 +63,8 @@ def main():
                       max_batch=max(wl.R, 8192), max_prompt_bytes=max(wl.R, 8192) * wl.T * 4, index_slots=slots,
                       profiles=profiles, pd=pd)
     gpu = EndpointPicker(cfg)
+    device_lru = args.lru_impl == "device"
+    gpu.set_option("device_lru", 1 if device_lru else 0)
     if args.threads:
         gpu.set_option("lru_threads", args.threads)
     gpu.update_endpoints(wl.endpoint_states())
@@ -101,16 +108,27 @@ def main():
     t_pick, t_add, exact, hits = [], [], True, 0
     t_cpu_pick = t_cpu_add = 0.0
     tomb = []
+
+    def add_step():
+        ends = np.ascontiguousarray(picks_v[:, main_p]["endpoint"])
+        nbl = np.ascontiguousarray(picks_v[:, main_p]["n_blocks"]).astype(np.uint32)
+        if device_lru:
+            gpu.index_add_chains_device(ends, 0, 0, nbl)  # the chains of the pick just made, from the handle's buffer
+        else:
+            gpu.index_add_chains(ends, chains_v, nbl)
+
     for step in range(args.steps):
         tok, offs = wl.prompts(batch=step)
         pin_tok.array(np.uint32)[:] = tok.reshape(-1)
         pin_off.array(np.uint64)[:] = offs
         t0 = time.perf_counter()
-        gpu.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr, pin_ch.ptr)
+        # (the device LRU's kernels are asynchronous: the NEXT pick waits for them on the GPU, so their time
+        # shows up in pick_ms; decisions/s is over the wall clock of both calls, with a final sync)
+        gpu.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr, 0 if device_lru else pin_ch.ptr)
         t1 = time.perf_counter()
-        ends = np.ascontiguousarray(picks_v[:, main_p]["endpoint"])
-        nbl = np.ascontiguousarray(picks_v[:, main_p]["n_blocks"]).astype(np.uint32)
-        gpu.index_add_chains(ends, chains_v, nbl)
+        add_step()
+        if step == args.steps - 1:
+            gpu.index_sync()
         t2 = time.perf_counter()
         t_pick.append(t1 - t0)
         t_add.append(t2 - t1)
@@ -131,9 +149,8 @@ def main():
     # device time of the index kernels for one more step (profiled: CUDA events around every launch)
     gpu.reset_stats()
     gpu.set_profiling(True)
-    gpu.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr, pin_ch.ptr)
-    gpu.index_add_chains(np.ascontiguousarray(picks_v[:, main_p]["endpoint"]), chains_v,
-                         np.ascontiguousarray(picks_v[:, main_p]["n_blocks"]).astype(np.uint32))
+    gpu.pick_batch_raw(pin_tok.ptr, pin_off.ptr, pin_h0.ptr, R, pin_out.ptr, 0 if device_lru else pin_ch.ptr)
+    add_step()
     gpu.index_sync()
     pst = gpu.stats()
     gpu.set_profiling(False)
@@ -142,7 +159,8 @@ def main():
     out = {
         "mode": "churn: pick + indexer.Add(chain, picked endpoint) for every decision, LRUs at capacity",
         "workload": f"cfg{args.cfg}: {R} req/step x {wl.E} endpoints x {wl.T}-token prompts, lruCapacityPerServer {wl.lru_capacity}",
-        "steps_timed": len(tp), "lru_threads": args.threads or "default (usable cores, <= 128)",
+        "steps_timed": len(tp), "lru": args.lru_impl,
+        "lru_threads": None if device_lru else (args.threads or "default (usable cores, <= 128)"),
         "decisions_per_s": n / float(tp.sum() + ta.sum()),
         "pick_ms": {"p50": 1e3 * float(np.median(tp)), "p99": 1e3 * float(np.quantile(tp, 0.99)), "max": 1e3 * float(tp.max())},
         "add_ms": {"p50": 1e3 * float(np.median(ta)), "p99": 1e3 * float(np.quantile(ta, 0.99)), "max": 1e3 * float(ta.max())},
