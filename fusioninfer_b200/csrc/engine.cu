@@ -222,11 +222,13 @@ struct fi_epp {
   int lru_want = -1;  // option / environment override (-1: automatic)
   DevLru dlru{};
   uint32_t* d_lru_state = nullptr;           // head | tail | count | used | error
-  unsigned long long* d_lru_ctr = nullptr;   // [0] SETs emitted, [1] endpoints maintained, [2] CLEARs of the running sub-batch, [3] CLEARs total
+  unsigned long long* d_lru_ctr = nullptr;   // [0] SETs emitted, [1] endpoints maintained, [2] CLEARs of the running sub-batch,
+                                             // [3] CLEARs total, [4] doomed winners
   struct LruHostStat {
     uint32_t error, pad;
-    unsigned long long n_sets, n_maintained, n_clears_cur, n_clears;
+    unsigned long long n_sets, n_maintained, n_clears_cur, n_clears, n_doomed;
   };
+  uint64_t lru_deferred = 0, lru_sub_batches = 0;  // host-side totals
   LruHostStat* h_lru_stat = nullptr;         // pinned copy, refreshed after every call
   uint32_t* d_lru_plan = nullptr;            // the planner's arrays of the current call
   uint32_t* h_lru_plan = nullptr;            // pinned staging of the same
@@ -237,6 +239,7 @@ struct fi_epp {
   uint64_t* d_lru_chains = nullptr;          // staging of host chains
   size_t lru_chains_cap = 0;                 // in u64 words
   cudaEvent_t ev_lru = nullptr;              // the previous call's staging has been consumed
+  cudaEvent_t ev_lru_ovf = nullptr;          // the touch kernel's overflow flag has reached the host
   uint32_t last_plain_R = 0;                 // rows of d_chain the most recent stream-ordered pick wrote
   LruPlan lru_plan;
   unsigned lru_threads = 0;          // 0: FI_EPP_LRU_THREADS, else min(usable cores, 64)
@@ -605,8 +608,9 @@ int ensure_dev_lru(fi_epp* h) {
   DevLru& d = h->dlru;
   d.EL = EL;
   d.capacity = C;
-  d.TS = std::max<uint32_t>(pow2_ceil32(4u * C), 64u);  // <= 70 % full even right before a maintenance (lru_kernels.cu)
+  d.TS = std::max<uint32_t>(pow2_ceil32(4u * C), 64u);  // C entries + a batch's new keys + tombstones (lru_kernels.cu)
   d.L = d.TS;
+  d.insert_limit = (uint32_t)((uint64_t)d.TS * 85 / 100);
   const size_t slot_bytes = (size_t)EL * (d.TS + 2) * sizeof(LruSlot), log_bytes = (size_t)EL * d.L * sizeof(uint64_t);
   size_t free_b = 0, total_b = 0;
   FI_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -614,10 +618,11 @@ int ensure_dev_lru(fi_epp* h) {
   const size_t scratch = (size_t)h->lru_touch_cap * (sizeof(uint32_t) + 2 * sizeof(fi_index_op));
   if (slot_bytes + log_bytes + scratch + (256u << 20) > free_b)
     return fail(h, FI_ERR_NOMEM, "device LRU does not fit in free HBM (option device_lru = 0 selects the host LRU)");
+  const size_t state_words = (size_t)7 * EL + 2;
   FI_CUDA(cudaMalloc(&d.slots, slot_bytes));
   FI_CUDA(cudaMalloc(&d.log, log_bytes));
-  FI_CUDA(cudaMalloc(&h->d_lru_state, ((size_t)4 * EL + 2) * sizeof(uint32_t)));
-  FI_CUDA(cudaMalloc(&h->d_lru_ctr, 4 * sizeof(unsigned long long)));
+  FI_CUDA(cudaMalloc(&h->d_lru_state, state_words * sizeof(uint32_t)));
+  FI_CUDA(cudaMalloc(&h->d_lru_ctr, 8 * sizeof(unsigned long long)));
   FI_CUDA(cudaMallocHost(&h->h_lru_stat, sizeof(fi_epp::LruHostStat)));
   std::memset(h->h_lru_stat, 0, sizeof(fi_epp::LruHostStat));
   FI_CUDA(cudaMalloc(&h->d_lru_slot_of, h->lru_touch_cap * sizeof(uint32_t)));
@@ -626,44 +631,55 @@ int ensure_dev_lru(fi_epp* h) {
   FI_CUDA(cudaMalloc(&h->d_lru_wcount, (size_t)h->cfg.max_batch * sizeof(uint32_t)));
   FI_CUDA(cudaMalloc(&h->d_lru_base, (size_t)h->cfg.max_batch * sizeof(uint32_t)));
   FI_CUDA(cudaEventCreateWithFlags(&h->ev_lru, cudaEventDisableTiming));
+  FI_CUDA(cudaEventCreateWithFlags(&h->ev_lru_ovf, cudaEventDisableTiming));
   FI_CUDA(cudaMemsetAsync(d.slots, 0, slot_bytes, h->s_index));
-  FI_CUDA(cudaMemsetAsync(h->d_lru_state, 0, ((size_t)4 * EL + 2) * sizeof(uint32_t), h->s_index));
-  FI_CUDA(cudaMemsetAsync(h->d_lru_ctr, 0, 4 * sizeof(unsigned long long), h->s_index));
+  FI_CUDA(cudaMemsetAsync(h->d_lru_state, 0, state_words * sizeof(uint32_t), h->s_index));
+  FI_CUDA(cudaMemsetAsync(h->d_lru_ctr, 0, 8 * sizeof(unsigned long long), h->s_index));
   FI_CUDA(cudaEventRecord(h->ev_lru, h->s_index));
   d.head = h->d_lru_state;
   d.tail = d.head + EL;
   d.count = d.tail + EL;
   d.used = d.count + EL;
-  d.error = d.used + EL;
+  d.hold = d.used + EL;
+  d.dcount = d.hold + EL;
+  d.ovf = d.dcount + EL;
+  d.any_ovf = d.ovf + EL;
+  d.error = d.any_ovf + 1;
   d.n_sets = h->d_lru_ctr;
   d.n_maintained = h->d_lru_ctr + 1;
+  d.n_clears = h->d_lru_ctr + 3;
+  d.n_doomed = h->d_lru_ctr + 4;
   return FI_OK;
 }
 
 // queue the refresh of the pinned LRU status (error flag + totals) behind everything submitted so far
 int lru_refresh_stat(fi_epp* h) {
   FI_CUDA(cudaMemcpyAsync(&h->h_lru_stat->error, h->dlru.error, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_index));
-  FI_CUDA(cudaMemcpyAsync(&h->h_lru_stat->n_sets, h->d_lru_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_index));
+  FI_CUDA(cudaMemcpyAsync(&h->h_lru_stat->n_sets, h->d_lru_ctr, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_index));
   return FI_OK;
 }
 
 // indexer.Add(chains[r], endpoints[r]) for r = 0..R-1 through the device LRU.  `chains` is a host pointer
-// (copied to the device first) or, with on_device, memory the index stream can read.
+// (copied to the device first) or, with on_device, memory the index stream can read.  The first pass is
+// OPTIMISTIC: sub-batches are cut only by the scratch arrays' size, and an endpoint whose table cannot take the
+// batch's distinct keys is rolled back and deferred; the deferred requests then run in a second, conservative pass
+// (at most lru_capacity touches per endpoint and sub-batch: always fits).
 int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains, bool on_device, uint32_t pitch,
-                   const uint32_t* nblocks, uint32_t R) {
+                   const uint32_t* nblocks, uint32_t R, bool conservative = false) {
   int rc = ensure_dev_lru(h);
   if (rc != FI_OK) return rc;
+  const uint32_t EL = h->cfg.endpoint_count, lo = h->cfg.endpoint_begin;
   for (uint32_t r = 0; r < R; ++r)
-    if (nblocks[r] > h->cfg.lru_capacity && endpoints[r] - h->cfg.endpoint_begin < h->cfg.endpoint_count)
+    if (nblocks[r] > h->cfg.lru_capacity && endpoints[r] - lo < EL)
       return fail(h, FI_ERR_INVALID, "device LRU: a chain longer than lru_capacity");
   rc = flush_ops(h);  // ops staged through fi_epp_index_apply come first
   if (rc != FI_OK) return rc;
   rc = check_counters(h);
   if (rc != FI_OK) return rc;
-  const uint32_t EL = h->cfg.endpoint_count, lo = h->cfg.endpoint_begin;
   const auto t0 = std::chrono::steady_clock::now();
   LruPlan& pl = h->lru_plan;
-  lru_plan_batch(endpoints, nblocks, R, lo, EL, h->cfg.lru_capacity, h->lru_touch_cap, h->cfg.max_batch, &pl);
+  lru_plan_batch(endpoints, nblocks, R, lo, EL, conservative ? h->cfg.lru_capacity : 0xFFFFFFFFu, h->lru_touch_cap, h->cfg.max_batch,
+                 &pl);
   if (pl.subs.empty()) return FI_OK;
   const size_t K = pl.req_id.size(), nsub = pl.subs.size();
   // staging: req_id | req_ep | req_n | req_off | ep_list | ep_start[nsub][EL+1] | inc[nsub][EL]
@@ -718,6 +734,10 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
     d_chains = h->d_lru_chains;
   }
   const uint32_t* dp = h->d_lru_plan;
+  h->lru_sub_batches += nsub;
+  std::vector<uint8_t> deferred;  // per request of this call: its endpoint overflowed in the optimistic pass
+  std::vector<uint32_t> ovf_host;
+  size_t n_deferred = 0;
   for (size_t sb = 0; sb < nsub; ++sb) {
     if (sb) {  // the index counters of the previous sub-batch decide about a rebuild before more keys arrive
       rc = check_counters(h);
@@ -747,6 +767,29 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
       LaunchScope ls(h, h->s_index, K_INDEX);
       FI_CUDA(launch_lru_touch(h->dlru, b, h->s_index));
     }
+    // did some endpoint's table refuse keys?  (one host round trip per sub-batch; everything after it is queued
+    // without waiting)
+    FI_CUDA(cudaMemcpyAsync(&h->h_lru_stat->pad, h->dlru.any_ovf, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_index));
+    FI_CUDA(cudaEventRecord(h->ev_lru_ovf, h->s_index));
+    FI_CUDA(cudaEventSynchronize(h->ev_lru_ovf));
+    const bool any_ovf = h->h_lru_stat->pad != 0;
+    if (any_ovf) {
+      if (conservative) return fail(h, FI_ERR_STATE, "device LRU: overflow in a conservative sub-batch");
+      {
+        LaunchScope ls(h, h->s_index, K_INDEX);
+        FI_CUDA(launch_lru_untouch(h->dlru, b, h->s_index));
+      }
+      ovf_host.resize(EL);
+      FI_CUDA(cudaMemcpyAsync(ovf_host.data(), h->dlru.ovf, (size_t)EL * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_index));
+      FI_CUDA(cudaStreamSynchronize(h->s_index));
+      if (deferred.empty()) deferred.assign(R, 0);
+      for (uint32_t k = sbt.k_begin; k < sbt.k_end; ++k)
+        if (ovf_host[pl.req_ep[k]]) {
+          deferred[pl.req_id[k]] = 1;
+          ++n_deferred;
+        }
+    }
+    FI_CUDA(cudaMemsetAsync(h->d_lru_ctr + 2, 0, sizeof(unsigned long long), h->s_index));
     {
       LaunchScope ls(h, h->s_index, K_INDEX);
       FI_CUDA(launch_lru_count(h->dlru, b, h->s_index));
@@ -757,22 +800,24 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
     }
     {
       LaunchScope ls(h, h->s_index, K_INDEX);
-      FI_CUDA(launch_lru_append(h->dlru, b, lo, h->s_index));
+      FI_CUDA(launch_lru_append(h->dlru, b, h->d_lru_clears, h->d_lru_ctr + 2, h->lru_touch_cap, lo, h->s_index));
     }
     {
       LaunchScope ls(h, h->s_index, K_INDEX);
       FI_CUDA(launch_index_set(h->ix, h->d_ctr, h->d_lru_sets, sbt.touches, lo, EL, h->rank, GossipLog{}, h->s_index));
     }
-    FI_CUDA(cudaMemsetAsync(h->d_lru_ctr + 2, 0, sizeof(unsigned long long), h->s_index));
     {
       LaunchScope ls(h, h->s_index, K_INDEX);
       FI_CUDA(launch_lru_evict(h->dlru, h->d_lru_clears, h->d_lru_ctr + 2, h->lru_touch_cap, lo, h->s_index));
     }
     {
+      // CLEARs of a sub-batch: at most one per entry that was in the LRUs before it and per key it added
+      const uint64_t cap = std::min<uint64_t>(h->lru_touch_cap, sbt.touches + (uint64_t)EL * h->cfg.lru_capacity);
       LaunchScope ls(h, h->s_index, K_INDEX);
-      FI_CUDA(launch_index_clear_counted(h->ix, h->d_ctr, h->d_lru_clears, sbt.touches, h->d_lru_ctr + 2, lo, EL, h->rank,
-                                         GossipLog{}, h->s_index));
+      FI_CUDA(launch_index_clear_counted(h->ix, h->d_ctr, h->d_lru_clears, cap, h->d_lru_ctr + 2, lo, EL, h->rank, GossipLog{},
+                                         h->s_index));
     }
+    if (any_ovf) FI_CUDA(cudaMemsetAsync(h->dlru.ovf, 0, ((size_t)EL + 1) * sizeof(uint32_t), h->s_index));  // ovf[] and any_ovf
     FI_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(IndexCounters), cudaMemcpyDeviceToHost, h->s_index));
     FI_CUDA(cudaEventRecord(h->ev_ctr, h->s_index));
     h->ctr_pending = true;
@@ -784,8 +829,15 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
   FI_CUDA(cudaEventRecord(h->ev_index, h->s_index));
   if (h->verbose) {
     const auto t1 = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "[fi_epp] device LRU: %u requests (%zu kept), %zu sub-batch(es), host side %.3f ms\n", R, K, nsub,
+    std::fprintf(stderr, "[fi_epp] device LRU%s: %u requests (%zu kept), %zu sub-batch(es), %zu deferred, host side %.3f ms\n",
+                 conservative ? " (conservative pass)" : "", R, K, nsub, n_deferred,
                  std::chrono::duration<double, std::milli>(t1 - t0).count());
+  }
+  h->lru_deferred += n_deferred;
+  if (n_deferred) {
+    std::vector<uint32_t> ep2(R);
+    for (uint32_t r = 0; r < R; ++r) ep2[r] = deferred[r] ? endpoints[r] : FI_NO_ENDPOINT;
+    return lru_device_add(h, ep2.data(), d_chains, true, pitch, nblocks, R, true);
   }
   return FI_OK;
 }
@@ -1399,6 +1451,7 @@ void fi_epp_destroy(fi_epp* h) {
   cudaFree(h->d_lru_clears);
   cudaFree(h->d_lru_chains);
   if (h->ev_lru) cudaEventDestroy(h->ev_lru);
+  if (h->ev_lru_ovf) cudaEventDestroy(h->ev_lru_ovf);
   free_index(h->ix);
   free_index(h->ix_spare);
   for (int b = 0; b < 2; ++b) {
@@ -1916,6 +1969,24 @@ int fi_epp_lru_dump(fi_epp* h, uint32_t endpoint, uint64_t* out, uint32_t cap, u
   cudaFree(d_n);
   if (er != cudaSuccess) return fail(h, FI_ERR_CUDA, cudaGetErrorString(er));
   *n_out = n;
+  return FI_OK;
+}
+
+// Diagnostics: totals of the device-resident LRU since create — out[0] SETs emitted, [1] CLEARs emitted,
+// [2] doomed winners, [3] endpoint maintenance passes, [4] requests deferred to a conservative pass, [5] sub-batches.
+int fi_epp_lru_counters(fi_epp* h, uint64_t out[6]) {
+  if (!h || !out) return FI_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
+  for (int i = 0; i < 6; ++i) out[i] = 0;
+  if (h->lru_mode != 1 || !h->dlru.slots) return FI_OK;
+  FI_CUDA(cudaStreamSynchronize(h->s_index));
+  out[0] = h->h_lru_stat->n_sets;
+  out[1] = h->h_lru_stat->n_clears;
+  out[2] = h->h_lru_stat->n_doomed;
+  out[3] = h->h_lru_stat->n_maintained;
+  out[4] = h->lru_deferred;
+  out[5] = h->lru_sub_batches;
   return FI_OK;
 }
 

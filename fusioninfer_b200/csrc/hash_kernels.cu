@@ -10,9 +10,6 @@
 //   chain_finalize  one thread per request walks the serial tail+avalanche link.
 //   hash_generic    block sizes that are not a multiple of 32 (e.g. the reference's
 //                   blockSize: 5): fully serial per request, byte loads.
-#include <algorithm>
-#include <cstdlib>
-
 #include "kernels.cuh"
 #include "xxh64.cuh"
 #include "xxh64_sm100.cuh"
@@ -133,114 +130,6 @@ __global__ void __launch_bounds__(256, STRIPES <= 2 ? 8 : 5) hash_blocks_kernel(
         pre[pre_index(r, i, MP2)] = xacc2_finish(a, (uint64_t)B + 8);
       }
     }
-  }
-}
-
-// Persistent variant: a few CTAs per SM walk the requests with a stride of the grid, and every thread fetches
-// its block of the NEXT request (and the offsets of the one after) before it hashes the current one — the
-// prompt stream never waits for a CTA to be scheduled, read its offsets, and only then issue its loads
-// (hash_blocks_kernel: 82 % of the warp slots filled, 70 % of the DRAM peak).
-template <int STRIPES>
-__global__ void __launch_bounds__(256, 4) hash_blocks_stream_kernel(const uint8_t* __restrict__ prompts,
-                                                                    const uint64_t* __restrict__ offsets, uint32_t R, uint32_t M,
-                                                                    uint32_t MP, uint64_t* __restrict__ pre,
-                                                                    uint32_t* __restrict__ nblocks) {
-  constexpr uint32_t B = STRIPES * 32;
-  const uint32_t MP2 = MP / 2;
-  const uint64_t pol = make_evict_first_policy();
-  const uint32_t G = gridDim.x, tid = threadIdx.x;
-  uint32_t r = blockIdx.x;
-  if (r >= R) return;
-  // request state: (offset, end) two requests ahead, data one request ahead
-  uint64_t off_c = offsets[r], end_c = offsets[r + 1];
-  uint64_t off_n = 0, end_n = 0;
-  if (r + G < R) {
-    off_n = offsets[r + G];
-    end_n = offsets[r + G + 1];
-  }
-  Stripe q[STRIPES];
-  auto geometry = [&](uint64_t off, uint64_t end, uint32_t& n, bool& fast) {
-    const uint64_t nb64 = (end - off) / B;
-    n = nb64 > M ? M : (uint32_t)nb64;
-    fast = ((reinterpret_cast<uintptr_t>(prompts) + off) & 31) == 0;
-  };
-  uint32_t n_c;
-  bool fast_c;
-  geometry(off_c, end_c, n_c, fast_c);
-  if (fast_c && tid < n_c) {
-#pragma unroll
-    for (int s = 0; s < STRIPES; ++s) q[s] = ld_stream_v8(prompts + off_c + (uint64_t)tid * B + 32 * s, pol);
-  }
-  for (;;) {
-    const uint32_t rn = r + G;
-    const bool has_n = rn < R;
-    uint32_t n_n = 0;
-    bool fast_n = false;
-    Stripe qn[STRIPES];
-    if (has_n) {
-      geometry(off_n, end_n, n_n, fast_n);
-      if (fast_n && tid < n_n) {
-#pragma unroll
-        for (int s = 0; s < STRIPES; ++s) qn[s] = ld_stream_v8(prompts + off_n + (uint64_t)tid * B + 32 * s, pol);
-      }
-    }
-    uint64_t off_nn = 0, end_nn = 0;
-    if (rn + G < R) {
-      off_nn = offsets[rn + G];
-      end_nn = offsets[rn + G + 1];
-    }
-    // ---- the current request
-    if (tid == 0) nblocks[r] = n_c;
-    const uint8_t* base = prompts + off_c;
-    if (fast_c) {
-      if (tid < n_c) {
-        XAcc2 a = xacc2_init();
-#pragma unroll
-        for (int s = 0; s < STRIPES; ++s) xacc2_stripe(a, q[s]);
-        pre[pre_index(r, tid, MP2)] = xacc2_finish(a, (uint64_t)B + 8);
-      }
-      for (uint32_t i = tid + blockDim.x; i < n_c; i += blockDim.x) {  // more blocks than threads: not prefetched
-        Stripe t[STRIPES];
-#pragma unroll
-        for (int s = 0; s < STRIPES; ++s) t[s] = ld_stream_v8(base + (uint64_t)i * B + 32 * s, pol);
-        XAcc2 a = xacc2_init();
-#pragma unroll
-        for (int s = 0; s < STRIPES; ++s) xacc2_stripe(a, t[s]);
-        pre[pre_index(r, i, MP2)] = xacc2_finish(a, (uint64_t)B + 8);
-      }
-    } else {
-      // arbitrary byte alignment: aligned 64-bit windows + funnel shift
-      for (uint32_t i = tid; i < n_c; i += blockDim.x) {
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(base + (uint64_t)i * B);
-        const uint64_t* wp = reinterpret_cast<const uint64_t*>(addr & ~(uintptr_t)7);
-        const uint32_t sh = (uint32_t)(addr & 7) * 8;
-        uint64_t w[4 * STRIPES + 1];
-#pragma unroll
-        for (int k = 0; k < 4 * STRIPES; ++k) w[k] = __ldg(wp + k);
-        w[4 * STRIPES] = sh ? __ldg(wp + 4 * STRIPES) : 0;
-        if (sh) {
-#pragma unroll
-          for (int k = 0; k < 4 * STRIPES; ++k) w[k] = (w[k] >> sh) | (w[k + 1] << (64 - sh));
-        }
-        XAcc2 a = xacc2_init();
-#pragma unroll
-        for (int s = 0; s < STRIPES; ++s)
-          xacc2_stripe(a, Stripe{{(uint32_t)w[4 * s], (uint32_t)(w[4 * s] >> 32), (uint32_t)w[4 * s + 1],
-                                  (uint32_t)(w[4 * s + 1] >> 32), (uint32_t)w[4 * s + 2], (uint32_t)(w[4 * s + 2] >> 32),
-                                  (uint32_t)w[4 * s + 3], (uint32_t)(w[4 * s + 3] >> 32)}});
-        pre[pre_index(r, i, MP2)] = xacc2_finish(a, (uint64_t)B + 8);
-      }
-    }
-    if (!has_n) break;
-    r = rn;
-    off_c = off_n;
-    end_c = end_n;
-    n_c = n_n;
-    fast_c = fast_n;
-#pragma unroll
-    for (int s = 0; s < STRIPES; ++s) q[s] = qn[s];
-    off_n = off_nn;
-    end_n = end_nn;
   }
 }
 
@@ -481,20 +370,6 @@ cudaError_t launch_hash_blocks(const uint8_t* prompts, const uint64_t* offsets, 
   uint32_t threads = (M + 31) / 32 * 32;
   if (threads > 256) threads = 256;
   const uint32_t grid = (grid_cap && grid_cap < R) ? grid_cap : R;
-  // FI_EPP_HASH_STREAM=<CTAs per SM>: the persistent, prefetching variant (A/B switch while it is being measured)
-  static const int stream_ctas = [] {
-    const char* e = std::getenv("FI_EPP_HASH_STREAM");
-    return e ? std::atoi(e) : 0;
-  }();
-  if (stream_ctas > 0 && grid_cap == 0 && (B == 64 || B == 32) && M <= 256) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t g = std::min<uint32_t>(R, (uint32_t)(sms * stream_ctas));
-    if (B == 64) hash_blocks_stream_kernel<2><<<g, 256, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks);
-    else hash_blocks_stream_kernel<1><<<g, 256, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks);
-    return cudaGetLastError();
-  }
   if (B == 64)
     hash_blocks_kernel<2><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks);
   else if (B == 32)

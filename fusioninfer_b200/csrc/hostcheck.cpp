@@ -173,13 +173,14 @@ int fihc_lru_batch_check(uint32_t E, uint32_t cap, const uint32_t* endpoints, co
   return 0;
 }
 
-// The device LRU's batch rule (lru_kernels.cu) on the CPU: plan the batch with lru_plan_batch, apply every
-// sub-batch AT ONCE — per endpoint: the keys touched move behind everything else in the order of their LAST
-// touch, then the oldest entries beyond the capacity go — and compare recency order and content with one LRU
-// per endpoint touched request after request.  0 if identical; *subs = sub-batches of the last batch.
+// The device LRU's batch rule (lru_kernels.cu) on the CPU: plan the batch with lru_plan_batch (at most plan_cap
+// touches per endpoint and sub-batch: the LRU capacity in the conservative pass, unlimited in the optimistic one),
+// apply every sub-batch AT ONCE — per endpoint: the keys touched move behind everything else in the order of
+// their LAST touch, then the oldest entries beyond the capacity go — and compare recency order and content with
+// one LRU per endpoint touched request after request.  0 if identical; *subs = sub-batches of the last batch.
 int fihc_lru_plan_check(uint32_t E, uint32_t cap, const uint32_t* endpoints, const uint64_t* chains, uint32_t pitch,
-                        const uint32_t* nblocks, uint32_t R, uint32_t batches, uint64_t cap_touches, uint32_t cap_requests,
-                        uint32_t* subs) {
+                        const uint32_t* nblocks, uint32_t R, uint32_t batches, uint32_t plan_cap, uint64_t cap_touches,
+                        uint32_t cap_requests, uint32_t* subs) {
   std::vector<std::vector<uint64_t>> order(E);  // oldest first
   std::vector<fi::LruSet> seq(E, fi::LruSet(cap));
   std::vector<std::vector<uint64_t>> seq_order(E);
@@ -188,7 +189,7 @@ int fihc_lru_plan_check(uint32_t E, uint32_t cap, const uint32_t* endpoints, con
     const uint32_t* ep = endpoints + (size_t)b * R;
     const uint64_t* ch = chains + (size_t)b * R * pitch;
     const uint32_t* nb = nblocks + (size_t)b * R;
-    fi::lru_plan_batch(ep, nb, R, 0, E, cap, cap_touches, cap_requests, &pl);
+    fi::lru_plan_batch(ep, nb, R, 0, E, plan_cap, cap_touches, cap_requests, &pl);
     if (subs) *subs = (uint32_t)pl.subs.size();
     size_t covered = 0;
     for (size_t sb = 0; sb < pl.subs.size(); ++sb) {
@@ -208,7 +209,7 @@ int fihc_lru_plan_check(uint32_t E, uint32_t cap, const uint32_t* endpoints, con
           const uint64_t* c = ch + (size_t)pl.req_id[k] * pitch;
           t.insert(t.end(), c, c + pl.req_n[k]);
         }
-        if (t.size() != inc[e] || t.size() > cap) return 13;
+        if (t.size() != inc[e] || t.size() > plan_cap) return 13;
         covered += t.size();
         std::unordered_set<uint64_t> seen;
         std::vector<uint64_t> winners;  // keys by last touch, newest first

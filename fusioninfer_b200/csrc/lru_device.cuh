@@ -19,11 +19,18 @@ struct DevLru {
   uint32_t* head;   // [EL] next free log position
   uint32_t* tail;   // [EL] oldest position that may still be live
   uint32_t* count;  // [EL] live entries
-  uint32_t* used;   // [EL] regular table slots consumed (entries + tombstones)
+  uint32_t* used;   // [EL] regular table slots consumed (entries + tombstones); reserved BEFORE an insert
+  uint32_t* hold;   // [EL] scratch: head before the running sub-batch's appends
+  uint32_t* dcount; // [EL] scratch: winners (distinct keys touched) of the running sub-batch
+  uint32_t* ovf;    // [EL] the running sub-batch would overfill this endpoint's table: its requests are deferred
+  uint32_t* any_ovf; // some ovf[e] was set by the running touch kernel
   uint32_t* error;  // != 0: an invariant broke (reported by the next host call)
-  unsigned long long* n_sets;        // totals, for fi_epp_index_stats
-  unsigned long long* n_maintained;
+  unsigned long long* n_sets;        // totals (fi_epp_index_stats, fi_epp_lru_counters): SETs emitted,
+  unsigned long long* n_clears;      // CLEARs emitted,
+  unsigned long long* n_doomed;      // winners that were gone again by the end of their sub-batch,
+  unsigned long long* n_maintained;  // log compactions + table rebuilds
   uint32_t EL, TS, L, capacity;
+  uint32_t insert_limit;  // a table never holds more than this many keys + tombstones (0.85 TS)
 };
 
 // one sub-batch of indexer.Add calls (lru_plan.h); K requests, `touches` blocks in total
@@ -39,15 +46,17 @@ struct LruBatch {
   uint32_t K;
   uint32_t* slot_of;        // [touches] scratch: table slot of every touch
   uint32_t* wcount;         // [K] scratch: winners per request
-  uint32_t* base;           // [K] scratch: log position of the request's first winner
+  uint32_t* base;           // [K] scratch: rank of the request's first winner among its endpoint's winners
   fi_index_op* sets;        // [touches] out: SET for touches that added a key, op 0 elsewhere (chain order kept)
 };
 
 cudaError_t launch_lru_maintain(const DevLru& lru, const uint32_t* inc, bool force, cudaStream_t s);
 cudaError_t launch_lru_touch(const DevLru& lru, const LruBatch& b, cudaStream_t s);
+cudaError_t launch_lru_untouch(const DevLru& lru, const LruBatch& b, cudaStream_t s);
 cudaError_t launch_lru_count(const DevLru& lru, const LruBatch& b, cudaStream_t s);
 cudaError_t launch_lru_scan(const DevLru& lru, const LruBatch& b, cudaStream_t s);
-cudaError_t launch_lru_append(const DevLru& lru, const LruBatch& b, uint32_t ep_begin, cudaStream_t s);
+cudaError_t launch_lru_append(const DevLru& lru, const LruBatch& b, fi_index_op* clears, unsigned long long* n_clears,
+                              uint64_t clears_cap, uint32_t ep_begin, cudaStream_t s);
 cudaError_t launch_lru_evict(const DevLru& lru, fi_index_op* clears, unsigned long long* n_clears, uint64_t clears_cap,
                              uint32_t ep_begin, cudaStream_t s);
 // diagnostics: the live keys of local endpoint e, least recently used first

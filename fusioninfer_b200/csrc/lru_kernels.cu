@@ -8,12 +8,18 @@
 // of wide kernels; only the request → endpoint assignment (two small arrays) comes from the host.
 //
 // Exactness.  An LRU of capacity C always holds the C most recently touched distinct keys, whatever it evicted
-// on the way.  So the state after a batch of touches depends only on every key's LAST touch, and a batch can be
-// applied in parallel provided no key touched in the batch could have been evicted again before its end — the
-// planner (lru_plan.h) cuts the request stream into sub-batches in which every endpoint receives at most C
-// touches.  The index then gets SET for the keys that were new to the endpoint and CLEAR for the least recently
-// used entries beyond C — the same membership as R sequential Adds (SET-then-CLEAR pairs of keys that a
-// sequential run inserts and evicts inside one sub-batch cannot occur: at most C touches).
+// on the way.  So the state after a batch of touches depends only on every key's LAST touch: per endpoint, the
+// keys touched in the batch, ordered by their last touch (the WINNERS), go behind everything older, and the
+// content is cut to the newest C.  A winner followed by C or more other winners is gone again by the end of the
+// batch (DOOMED: it never reaches the index, or is CLEARed if it was there before); the index gets SET for the
+// surviving winners that were new to the endpoint and CLEAR for the entries that fell off — the same membership
+// as R sequential Adds, whatever those inserted and evicted in between.
+//
+// Capacity.  A table takes the batch's distinct keys on top of its C entries; it holds 0.85 TS = 3.4 C.  A hot
+// endpoint whose requests share their prefix (why they were routed there) fits easily; one that receives more
+// NEW distinct keys than that in a single batch is detected while inserting (slots are reserved before they are
+// claimed), its touches are rolled back and its requests are re-run in sub-batches of at most C touches, which
+// always fit (lru_plan.h; endpoints are independent of each other, so deferring one is exact).
 //
 // Per endpoint e (all in HBM):
 //   table  [TS + 2] LruSlot   open-addressed, linear probing, key → (log position + 1, order of its last touch
@@ -26,13 +32,15 @@
 //                             records between tail and head, oldest first, ARE the LRU list.
 //   head, tail, count (live entries), used (table slots consumed)
 //
-// One sub-batch = kernels  maintain → touch → count → scan → append → [index SET] → evict → [index CLEAR]:
+// One sub-batch = kernels  maintain → touch → (untouch) → count → scan → append → [index SET] → evict → [index CLEAR]:
 //   maintain  endpoints whose log or table could overflow: compact the log (live records only, renumbered from
 //             0) and rebuild the table from it                                      one CTA per endpoint
 //   touch     find-or-insert every (endpoint, key); atomicMax of the touch order    one CTA per request
+//   untouch   (only after an overflow) undo the touches of the overflowed endpoints
 //   count     a touch is a WINNER iff it is its key's last touch of the sub-batch; winners per request
 //   scan      per endpoint, requests in order: log position of each request's first winner; new head
-//   append    winners write their log record, point the table at it, emit SET if the key was new
+//   append    surviving winners write their log record, point the table at it, emit SET if the key was new;
+//             doomed winners leave the table (CLEAR if they were entries before)
 //   evict     endpoints above capacity: walk the log from the tail, evict the oldest live records, emit CLEAR
 #include "kernels.cuh"
 #include "lru_device.cuh"
@@ -52,9 +60,9 @@ __device__ __forceinline__ unsigned long long vload64(const uint64_t* p) {
   return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
 
-// slot of `key` in endpoint table `tab`, inserting it if absent (*inserted).  LRU_MISS: table full (the
-// maintenance thresholds make that impossible; reported through the error flag).
-__device__ uint32_t lru_find_or_insert(LruSlot* tab, uint32_t TS, uint64_t key, bool* inserted) {
+// slot of `key` in endpoint table `tab`, inserting it if absent (*inserted).  A new key first reserves one of
+// the table's insert_limit slots (`used`); LRU_MISS when there is none left (the caller flags the overflow).
+__device__ uint32_t lru_find_or_insert(LruSlot* tab, uint32_t TS, uint64_t key, uint32_t* used, uint32_t limit, bool* inserted) {
   *inserted = false;
   if (key == KEY_EMPTY || key == KEY_TOMB) {
     const uint32_t s = TS + (key == KEY_TOMB ? 1u : 0u);
@@ -64,19 +72,34 @@ __device__ uint32_t lru_find_or_insert(LruSlot* tab, uint32_t TS, uint64_t key, 
   }
   const uint32_t mask = TS - 1;
   uint32_t i = lru_home(key, mask);
+  bool reserved = false;
   for (uint32_t it = 0; it < TS; ++it) {
     const unsigned long long k = vload64(&tab[i].key);
-    if (k == key) return i;
+    if (k == key) {
+      if (reserved) atomicSub(used, 1u);  // someone else inserted it meanwhile
+      return i;
+    }
     if (k == KEY_EMPTY) {
+      if (!reserved) {
+        if (atomicAdd(used, 1u) >= limit) {
+          atomicSub(used, 1u);
+          return LRU_MISS;
+        }
+        reserved = true;
+      }
       const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&tab[i].key), 0ull, (unsigned long long)key);
       if (old == 0ull) {
         *inserted = true;
         return i;
       }
-      if (old == key) return i;
+      if (old == key) {
+        atomicSub(used, 1u);
+        return i;
+      }
     }
     i = (i + 1) & mask;
   }
+  if (reserved) atomicSub(used, 1u);
   return LRU_MISS;
 }
 
@@ -127,30 +150,35 @@ __global__ void __launch_bounds__(256) lru_touch_kernel(DevLru lru, LruBatch b) 
   const uint32_t e = b.req_ep[k], n = b.req_n[k], off = b.req_off[k];
   LruSlot* tab = lru.slots + (uint64_t)e * (lru.TS + 2);
   const uint64_t* chain = b.chains + (uint64_t)b.req_id[k] * b.pitch;
-  uint32_t mine = 0;
   for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
     const uint64_t key = chain[j];
     bool ins = false;
-    const uint32_t slot = lru_find_or_insert(tab, lru.TS, key, &ins);
+    const uint32_t slot = lru_find_or_insert(tab, lru.TS, key, lru.used + e, lru.insert_limit, &ins);
     b.slot_of[off + j] = slot;
-    if (slot == LRU_MISS) {
-      atomicExch(lru.error, 1u);
+    if (slot == LRU_MISS) {  // the table cannot take this batch's distinct keys: the endpoint is deferred
+      lru.ovf[e] = 1u;
+      *lru.any_ovf = 1u;
       continue;
     }
     atomicMax(&tab[slot].ord, off + j + 1);
-    if (ins && slot < lru.TS) ++mine;
   }
-  // one atomic per CTA for the slots it consumed
-  uint32_t tot = 0;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
-  __shared__ uint32_t s_tot;
-  if (threadIdx.x == 0) s_tot = 0;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_tot, mine);
-  __syncthreads();
-  tot = s_tot;
-  if (threadIdx.x == 0 && tot) atomicAdd(lru.used + e, tot);
+}
+
+// ---- untouch: roll back the touches of the endpoints that overflowed -----------------------------------
+__global__ void __launch_bounds__(256) lru_untouch_kernel(DevLru lru, LruBatch b) {
+  const uint32_t k = blockIdx.x;
+  const uint32_t e = b.req_ep[k], n = b.req_n[k], off = b.req_off[k];
+  if (!lru.ovf[e]) return;
+  LruSlot* tab = lru.slots + (uint64_t)e * (lru.TS + 2);
+  for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+    const uint32_t slot = b.slot_of[off + j];
+    if (slot == LRU_MISS) continue;
+    // keys this sub-batch inserted have no log record yet: they leave again (as tombstones: the re-run's
+    // maintenance pass rebuilds the table); entries that were there before just forget the touch.  Several
+    // touches of one key write the same values.
+    if (tab[slot].posp1 == 0) lru_retire(tab, lru.TS, slot);
+    else tab[slot].ord = 0;
+  }
 }
 
 // ---- count ----------------------------------------------------------------------------------------
@@ -159,7 +187,8 @@ __global__ void __launch_bounds__(256) lru_count_kernel(DevLru lru, LruBatch b) 
   const uint32_t e = b.req_ep[k], n = b.req_n[k], off = b.req_off[k];
   const LruSlot* tab = lru.slots + (uint64_t)e * (lru.TS + 2);
   uint32_t wins = 0;
-  for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+  const bool deferred = lru.ovf[e] != 0;
+  for (uint32_t j = threadIdx.x; j < n && !deferred; j += blockDim.x) {
     const uint32_t slot = b.slot_of[off + j];
     if (slot != LRU_MISS && tab[slot].ord == off + j + 1) ++wins;
   }
@@ -179,7 +208,7 @@ __global__ void __launch_bounds__(256) lru_scan_kernel(DevLru lru, LruBatch b) {
   if (e >= lru.EL) return;
   const uint32_t i0 = b.ep_start[e], i1 = b.ep_start[e + 1];
   if (i0 == i1) return;
-  uint32_t running = lru.head[e];
+  uint32_t running = 0;
   for (uint32_t i = i0; i < i1; i += 32) {
     const bool v = i + lane < i1;
     const uint32_t k = v ? b.ep_list[i + lane] : 0;
@@ -194,55 +223,91 @@ __global__ void __launch_bounds__(256) lru_scan_kernel(DevLru lru, LruBatch b) {
     running += __shfl_sync(0xFFFFFFFFu, inc, 31);
   }
   if (lane == 0) {
-    if (running > lru.L) atomicExch(lru.error, 2u);  // cannot happen: maintenance runs first
-    lru.head[e] = running;
+    const uint32_t head = lru.head[e];
+    const uint32_t kept = running < lru.capacity ? running : lru.capacity;  // the doomed winners get no record
+    lru.hold[e] = head;
+    lru.dcount[e] = running;
+    if ((uint64_t)head + kept > lru.L) atomicExch(lru.error, 2u);  // cannot happen: maintenance runs first
+    lru.head[e] = head + kept;
   }
 }
 
 // ---- append -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lru_append_kernel(DevLru lru, LruBatch b, uint32_t ep_begin) {
+__global__ void __launch_bounds__(256) lru_append_kernel(DevLru lru, LruBatch b, fi_index_op* clears, unsigned long long* n_clears,
+                                                         uint64_t clears_cap, uint32_t ep_begin) {
   const uint32_t k = blockIdx.x;
   const uint32_t e = b.req_ep[k], n = b.req_n[k], off = b.req_off[k];
   LruSlot* tab = lru.slots + (uint64_t)e * (lru.TS + 2);
   uint64_t* log = lru.log + (uint64_t)e * lru.L;
   const uint64_t* chain = b.chains + (uint64_t)b.req_id[k] * b.pitch;
-  uint32_t at = b.base[k];
-  uint32_t fresh = 0;
+  const bool deferred = lru.ovf[e] != 0;
+  const uint32_t D = lru.dcount[e], hold = lru.hold[e];
+  const uint32_t doomed_below = D > lru.capacity ? D - lru.capacity : 0;  // winners of rank < this are gone again
+  uint32_t at = b.base[k];  // rank of this request's next winner among the endpoint's winners
+  uint32_t fresh = 0, lost = 0, doomed = 0;
   for (uint32_t j0 = 0; j0 < n; j0 += blockDim.x) {  // uniform trip count: block-wide barriers inside
     const uint32_t j = j0 + threadIdx.x;
     uint32_t slot = LRU_MISS;
     bool win = false;
-    if (j < n) {
+    if (j < n && !deferred) {
       slot = b.slot_of[off + j];
       win = slot != LRU_MISS && tab[slot].ord == off + j + 1;
     }
     uint32_t tot = 0;
-    const uint32_t rank = cta_rank(win, &tot);
+    const uint32_t rank = at + cta_rank(win, &tot);
     fi_index_op op{0, 0, 0};
     if (win) {
       const uint64_t key = chain[j];
-      const uint32_t p = at + rank;
-      if (p < lru.L) log[p] = key;
-      if (tab[slot].posp1 == 0) {  // new to this endpoint
-        op = fi_index_op{key, ep_begin + e, FI_OP_SET};
-        ++fresh;
+      const bool was_entry = tab[slot].posp1 != 0;
+      if (rank < doomed_below) {
+        // touched, but C or more distinct keys were touched after it: not in the LRU at the end of the batch
+        lru_retire(tab, lru.TS, slot);
+        ++doomed;
+        if (was_entry) {
+          ++lost;
+          const unsigned long long c = atomicAdd(n_clears, 1ull);
+          if (c < clears_cap) clears[c] = fi_index_op{key, ep_begin + e, FI_OP_CLEAR};
+        }
+      } else {
+        const uint32_t p = hold + (rank - doomed_below);
+        if (p < lru.L) log[p] = key;
+        if (!was_entry) {  // new to this endpoint
+          op = fi_index_op{key, ep_begin + e, FI_OP_SET};
+          ++fresh;
+        }
+        tab[slot].posp1 = p + 1;
+        tab[slot].ord = 0;
       }
-      tab[slot].posp1 = p + 1;
-      tab[slot].ord = 0;
     }
     if (j < n) b.sets[off + j] = op;
     at += tot;
   }
+  // per-CTA totals: entries gained / lost
+  __shared__ uint32_t s_fresh, s_lost, s_doomed;
+  if (threadIdx.x == 0) s_fresh = s_lost = s_doomed = 0;
+  __syncthreads();
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, d);
-  __shared__ uint32_t s_tot;
-  if (threadIdx.x == 0) s_tot = 0;
+  for (int d = 16; d > 0; d >>= 1) {
+    fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, d);
+    lost += __shfl_xor_sync(0xFFFFFFFFu, lost, d);
+    doomed += __shfl_xor_sync(0xFFFFFFFFu, doomed, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (fresh) atomicAdd(&s_fresh, fresh);
+    if (lost) atomicAdd(&s_lost, lost);
+    if (doomed) atomicAdd(&s_doomed, doomed);
+  }
   __syncthreads();
-  if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(&s_tot, fresh);
-  __syncthreads();
-  if (threadIdx.x == 0 && s_tot) {
-    atomicAdd(lru.count + e, s_tot);
-    atomicAdd(lru.n_sets, (unsigned long long)s_tot);
+  if (threadIdx.x == 0) {
+    if (s_fresh) {
+      atomicAdd(lru.count + e, s_fresh);
+      atomicAdd(lru.n_sets, (unsigned long long)s_fresh);
+    }
+    if (s_lost) {
+      atomicSub(lru.count + e, s_lost);
+      atomicAdd(lru.n_clears, (unsigned long long)s_lost);
+    }
+    if (s_doomed) atomicAdd(lru.n_doomed, (unsigned long long)s_doomed);
   }
 }
 
@@ -292,6 +357,7 @@ __global__ void __launch_bounds__(256) lru_evict_kernel(DevLru lru, fi_index_op*
     if (need) atomicExch(lru.error, 3u);  // fewer live records than entries: cannot happen
     lru.tail[e] = t < head ? t : head;
     lru.count[e] = lru.capacity + need;
+    atomicAdd(lru.n_clears, (unsigned long long)(cnt - lru.capacity - need));
   }
 }
 
@@ -300,9 +366,11 @@ __global__ void __launch_bounds__(256) lru_maintain_kernel(DevLru lru, const uin
   const uint32_t e = blockIdx.x;
   const uint32_t add = inc ? inc[e] : 0;
   const uint32_t head = lru.head[e];
-  // the log must take `add` more records, the table `add` more keys (keeping it at most 70 % full)
-  const bool log_tight = (uint64_t)head + add > lru.L;
-  const bool tab_tight = ((uint64_t)lru.used[e] + add) * 10 > (uint64_t)lru.TS * 7;
+  // the log takes at most `capacity` more records per sub-batch (doomed winners get none); the table should
+  // stay at most 60 % full if the sub-batch brings the usual amount of new keys (more is caught by the insert limit)
+  const uint32_t addc = add < lru.capacity ? add : lru.capacity;
+  const bool log_tight = (uint64_t)head + addc > lru.L;
+  const bool tab_tight = ((uint64_t)lru.used[e] + addc) * 10 > (uint64_t)lru.TS * 6;
   if (!force && !log_tight && !tab_tight) return;
   LruSlot* tab = lru.slots + (uint64_t)e * (lru.TS + 2);
   uint64_t* log = lru.log + (uint64_t)e * lru.L;
@@ -331,13 +399,14 @@ __global__ void __launch_bounds__(256) lru_maintain_kernel(DevLru lru, const uin
   // 2. fresh table from the compacted log
   const uint4 z = make_uint4(0, 0, 0, 0);
   for (uint32_t i = threadIdx.x; i < lru.TS; i += blockDim.x) reinterpret_cast<uint4*>(tab)[i] = z;
+  if (threadIdx.x == 0) lru.used[e] = 0;
   __syncthreads();
   uint32_t regular = 0;
   for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) {
     const uint64_t key = log[i];
     if (key == KEY_EMPTY || key == KEY_TOMB) continue;
     bool ins = false;
-    const uint32_t slot = lru_find_or_insert(tab, lru.TS, key, &ins);
+    const uint32_t slot = lru_find_or_insert(tab, lru.TS, key, lru.used + e, lru.TS, &ins);
     if (slot == LRU_MISS) {
       atomicExch(lru.error, 4u);
       continue;
@@ -355,7 +424,7 @@ __global__ void __launch_bounds__(256) lru_maintain_kernel(DevLru lru, const uin
   if (threadIdx.x == 0) {
     lru.tail[e] = 0;
     lru.head[e] = d;
-    lru.used[e] = s_tot;
+    if (atomicAdd(lru.used + e, 0u) != s_tot) atomicExch(lru.error, 6u);
     if (d != lru.count[e]) atomicExch(lru.error, 5u);  // live records == entries, always
     atomicAdd(lru.n_maintained, 1ull);
   }
@@ -395,6 +464,11 @@ cudaError_t launch_lru_touch(const DevLru& lru, const LruBatch& b, cudaStream_t 
   lru_touch_kernel<<<b.K, 256, 0, s>>>(lru, b);
   return cudaGetLastError();
 }
+cudaError_t launch_lru_untouch(const DevLru& lru, const LruBatch& b, cudaStream_t s) {
+  if (b.K == 0) return cudaSuccess;
+  lru_untouch_kernel<<<b.K, 256, 0, s>>>(lru, b);
+  return cudaGetLastError();
+}
 cudaError_t launch_lru_count(const DevLru& lru, const LruBatch& b, cudaStream_t s) {
   if (b.K == 0) return cudaSuccess;
   lru_count_kernel<<<b.K, 256, 0, s>>>(lru, b);
@@ -404,9 +478,10 @@ cudaError_t launch_lru_scan(const DevLru& lru, const LruBatch& b, cudaStream_t s
   lru_scan_kernel<<<(lru.EL + 7) / 8, 256, 0, s>>>(lru, b);
   return cudaGetLastError();
 }
-cudaError_t launch_lru_append(const DevLru& lru, const LruBatch& b, uint32_t ep_begin, cudaStream_t s) {
+cudaError_t launch_lru_append(const DevLru& lru, const LruBatch& b, fi_index_op* clears, unsigned long long* n_clears,
+                              uint64_t clears_cap, uint32_t ep_begin, cudaStream_t s) {
   if (b.K == 0) return cudaSuccess;
-  lru_append_kernel<<<b.K, 256, 0, s>>>(lru, b, ep_begin);
+  lru_append_kernel<<<b.K, 256, 0, s>>>(lru, b, clears, n_clears, clears_cap, ep_begin);
   return cudaGetLastError();
 }
 cudaError_t launch_lru_evict(const DevLru& lru, fi_index_op* clears, unsigned long long* n_clears, uint64_t clears_cap,

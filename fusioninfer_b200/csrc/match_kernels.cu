@@ -156,43 +156,78 @@ __device__ __forceinline__ void load_row_words(const uint32_t* __restrict__ p, b
   }
 }
 
-// Nodes of the (up to) 32 blocks of a chunk, one block per lane.  A cached prefix was inserted in chain
-// order, so its nodes are consecutive (index_device.cuh): lanes already confirmed by the caller's
-// speculation come in with done = true; for the rest, the FIRST unresolved lane looks its key up in the
-// hash table, and the lanes after it check "my node = that node + my distance" with one coalesced klog
-// read.  A miss ends the walk (the lanes behind it are irrelevant: both match modes stop at the first
-// block the index does not hold).  After two table lookups that did not settle the chunk (a prefix whose
-// nodes are scattered) every remaining lane probes the table in parallel, as a plain hash index would.
-__device__ __forceinline__ uint32_t resolve_chunk_nodes(const IndexView& ix, uint64_t h, bool valid, uint32_t node, bool done,
-                                                        int lane) {
-  const bool plain = valid && !key_is_special(h);
-  done = done || !valid;
-  for (int tries = 0;; ++tries) {
-    const unsigned m = __ballot_sync(FULL, !done);
-    if (!m) break;
-    if (tries < 2) {
-      const int first = __ffs(m) - 1;
+// Nodes of ALL blocks of a request, before any row is read.  A cached prefix was inserted in chain order, so its
+// nodes are consecutive (index_device.cuh): after ONE table lookup for block `pos` every later block i checks
+// "my node = that node + (i - pos)" — coalesced reads of klog, all chunks of the request in flight at once.  The
+// table is probed again only where that fails: normally at the first block the index does not hold, which ends
+// the walk (both match modes stop at the first block no pod holds).  A prefix whose nodes are scattered (an index
+// built out of chain order) gets kSpecTries such rounds, then its remaining blocks probe the table in parallel,
+// 64 at a time, as a plain hash index would.
+// Returns m = number of leading blocks the index holds (the first miss, or n); s_node[0 .. m) = their nodes.
+//
+// (Round 1 resolved chunk c+1 while chunk c's rows were in flight: a request's serial chain was two dependent
+// memory round trips per 32 blocks, ~5 800 cycles per chunk and 23 us for a fully cached 256-block prompt — a
+// third of the whole kernel, which is how long the last such request kept the other warps waiting.  With the
+// nodes known up front the rows of a request are independent loads.)
+constexpr int kSpecTries = 4;
+constexpr int kSpecChunks = 8;  // chunks of 32 blocks verified per round (256 blocks; longer chains loop)
+
+__device__ __forceinline__ uint32_t resolve_request_nodes(const IndexView& ix, const uint64_t* __restrict__ s_chain,
+                                                          uint32_t* __restrict__ s_node, uint32_t n, int lane) {
+  uint32_t pos = 0;  // blocks [0, pos) are resolved and present
+  for (int tries = 0; pos < n; ++tries) {
+    if (tries < kSpecTries) {
       uint32_t nf = SLOT_MISS;
-      if (lane == first) nf = index_find(ix, h);
-      nf = __shfl_sync(FULL, nf, first);
-      if (lane == first) {
-        node = nf;
-        done = true;
-      }
-      if (nf == SLOT_MISS) break;  // first miss of the request
-      if (!done && plain && lane > first) {
-        const uint32_t cand = nf + (uint32_t)(lane - first);
-        if (nf < ix.C && node_holds(ix, cand, h)) {
-          node = cand;
-          done = true;
+      if (lane == 0) nf = index_find(ix, s_chain[pos]);
+      nf = __shfl_sync(FULL, nf, 0);
+      if (nf == SLOT_MISS) return pos;  // first miss of the request
+      if (lane == 0) s_node[pos] = nf;
+      uint32_t fail = n;  // first block after pos whose node is not nf + distance
+      if (nf >= ix.C) {
+        fail = pos + 1;  // the hashes 0 / ~0 own fixed nodes: nothing to speculate from
+      } else {
+        for (uint32_t i0 = pos + 1; i0 < n && fail == n; i0 += 32 * kSpecChunks) {
+          uint64_t hk[kSpecChunks], kk[kSpecChunks];
+#pragma unroll
+          for (int c = 0; c < kSpecChunks; ++c) {
+            const uint32_t idx = i0 + 32 * c + lane;
+            hk[c] = 0;
+            kk[c] = 1;  // (!= hk: a lane without a block never verifies)
+            if (idx < n) {
+              hk[c] = s_chain[idx];
+              const uint64_t cand = (uint64_t)nf + (idx - pos);
+              if (cand < ix.C) kk[c] = __ldg(ix.klog + cand);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < kSpecChunks; ++c) {
+            const uint32_t idx = i0 + 32 * c + lane;
+            if (fail != n || i0 + 32 * c >= n) break;  // warp-uniform
+            const bool ok = idx < n && kk[c] == hk[c] && !key_is_special(hk[c]);
+            const unsigned bad = __ballot_sync(FULL, idx < n && !ok);
+            const uint32_t upto = bad ? (uint32_t)(__ffs(bad) - 1) : 32u;
+            if ((uint32_t)lane < upto && idx < n) s_node[idx] = nf + (idx - pos);
+            if (bad) fail = i0 + 32 * c + upto;
+          }
         }
       }
-    } else if (!done) {
-      node = index_find_lazy(ix, h);
-      done = true;
+      pos = fail;
+    } else {
+      // scattered prefix: every remaining block of the next 64 probes the table
+      const uint32_t ia = pos + lane, ib = pos + 32 + lane;
+      uint32_t na = SLOT_MISS, nb = SLOT_MISS;
+      if (ia < n) na = index_find_lazy(ix, s_chain[ia]);
+      if (ib < n) nb = index_find_lazy(ix, s_chain[ib]);
+      const unsigned ma = __ballot_sync(FULL, ia < n && na == SLOT_MISS);
+      const unsigned mb = __ballot_sync(FULL, ib < n && nb == SLOT_MISS);
+      const uint32_t upto = ma ? (uint32_t)(__ffs(ma) - 1) : (mb ? 32u + (uint32_t)(__ffs(mb) - 1) : 64u);
+      if ((uint32_t)lane < upto && ia < n) s_node[ia] = na;
+      if ((uint32_t)lane + 32 < upto && ib < n) s_node[ib] = nb;
+      if (ma || mb) return pos + upto;
+      pos = pos + 64 < n ? pos + 64 : n;
     }
   }
-  return node;
+  return n;
 }
 
 // next request of the launch's dynamic queue.  Plain PTX on purpose: for `if (lane == 0) atomicAdd(..)` the
@@ -219,6 +254,7 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
   const int t = lane % LPR;  // position within the row
   const int g = lane / LPR;  // row group
   uint64_t* s_chain = s_mem + (size_t)warp * p.MP;
+  uint32_t* s_node = reinterpret_cast<uint32_t*>(s_mem + (size_t)kWarps * p.MP) + (size_t)warp * p.MP;  // node of every block
   const IndexView ix = p.ix;
   const uint32_t P = p.st.n_profiles;
   const char* row_base = reinterpret_cast<const char*>(ix.rows + t * VEC);
@@ -259,114 +295,64 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
     uint32_t matched_rows = 0;
     bool real_miss = false;
 
-    // ---- 2./3. probe + row reads, 32 blocks per chunk ---------------------------
-    const uint32_t nchunks = (n + 31) / 32;
-    uint32_t slot;  // node of this lane's block of the current chunk
-    {
-      const bool v0 = (uint32_t)lane < n;
-      slot = resolve_chunk_nodes(ix, v0 ? s_chain[lane] : 0ull, v0, SLOT_MISS, false, lane);
-    }
+    // ---- 2. the index node of every block up to the first one no endpoint holds ---------------
+    const uint32_t m_rows = resolve_request_nodes(ix, s_chain, s_node, n, lane);
+    real_miss = m_rows < n;
+    __syncwarp();  // s_node is written by some lanes and read by others
 #ifdef FI_MATCH_TIMING
     const long long tm2 = clock64();
 #endif
-    for (uint32_t c = 0; c < nchunks; ++c) {
-      uint32_t rows_here;
-      bool stop = false;
-      {
-        const unsigned mm = __ballot_sync(FULL, slot == SLOT_MISS);
-        rows_here = mm ? (uint32_t)(__ffs(mm) - 1) : 32u;
-        if (mm) {
-          stop = true;
-          real_miss = (c * 32 + rows_here) < n;
-        }
-      }
-      // Issue the next chunk's lookup before touching this chunk's rows: the speculative read of
-      // klog[node of this chunk's last block + 1 + lane] (all 32 lanes hit here, or we would stop).
-      uint64_t hn = 0, kspec = 0;
-      bool validn = false, spec = false;
-      uint32_t cand = SLOT_MISS;
-      uint32_t slot_next = SLOT_MISS;
-      bool resolved = false;
-      if (!stop && c + 1 < nchunks) {
-        const uint32_t idx = (c + 1) * 32 + lane;
-        validn = idx < n;
-        const uint32_t last = __shfl_sync(FULL, slot, 31);
-        if (validn) {
-          hn = s_chain[idx];
-          cand = last + 1u + (uint32_t)lane;
-          spec = last < ix.C && cand < ix.C && !key_is_special(hn);
-          if (spec) kspec = __ldg(ix.klog + cand);
-        }
-      } else {
-        resolved = true;
-      }
-      // rows of this chunk; rows past the first miss read the permanently-zero row instead of being
-      // predicated off (decided once per chunk, so a row load is shuffle + multiply-add + load)
-      const uint32_t slot_eff = ((uint32_t)lane < rows_here && slot != SLOT_MISS) ? slot : zero_slot;
+    // ---- 3. the rows of those blocks: independent loads, BATCH instructions (BATCH * G rows) in flight --
 #pragma unroll 1
-      for (int q0 = 0; q0 < LPR; q0 += BATCH) {
-        if ((uint32_t)(q0 * G) >= rows_here) break;
-        uint32_t w[VEC][BATCH];
+    for (uint32_t b0 = 0; b0 < m_rows; b0 += BATCH * G) {
+      uint32_t w[VEC][BATCH];
+#pragma unroll
+      for (int qi = 0; qi < BATCH; ++qi) {
+        const uint32_t j = b0 + qi * G + g;  // row this lane helps read; rows past the end read the permanently
+        const uint32_t sn = j < m_rows ? s_node[j] : zero_slot;  // zero row instead of being predicated off
+        uint32_t tmp[VEC];
+        load_row_words<VEC>(reinterpret_cast<const uint32_t*>(row_base + (uint64_t)sn * row_bytes), true, tmp);
+#pragma unroll
+        for (int x = 0; x < VEC; ++x) w[x][qi] = tmp[x];
+      }
+      if (LPM) {
 #pragma unroll
         for (int qi = 0; qi < BATCH; ++qi) {
-          const int j = (q0 + qi) * G + g;  // row of the chunk this lane helps read
-          const uint32_t s = __shfl_sync(FULL, slot_eff, j);
-          uint32_t tmp[VEC];
-          load_row_words<VEC>(reinterpret_cast<const uint32_t*>(row_base + (uint64_t)s * row_bytes), true, tmp);
 #pragma unroll
-          for (int x = 0; x < VEC; ++x) w[x][qi] = tmp[x];
-        }
-        if (!resolved) {
-          // settle the next chunk's nodes while this chunk's rows are in flight
-          const bool hit = spec && kspec == hn;
-          slot_next = resolve_chunk_nodes(ix, hn, validn, hit ? cand : SLOT_MISS, hit, lane);
-          resolved = true;
-        }
-        if (LPM) {
+          for (int x = 0; x < VEC; ++x) {
+            uint32_t v = w[x][qi];
+            if (G > 1) {  // prefix-AND over the G rows of this instruction
 #pragma unroll
-          for (int qi = 0; qi < BATCH; ++qi) {
-#pragma unroll
-            for (int x = 0; x < VEC; ++x) {
-              uint32_t v = w[x][qi];
-              if (G > 1) {  // prefix-AND over the G rows of this instruction
-#pragma unroll
-                for (int d = 1; d < G; d <<= 1) {
-                  const uint32_t o = __shfl_up_sync(FULL, v, d * LPR);
-                  if (g >= d) v &= o;
-                }
-                v &= alive[x];
-                alive[x] = __shfl_sync(FULL, v, (G - 1) * LPR + t);
-              } else {
-                v &= alive[x];
-                alive[x] = v;
+              for (int d = 1; d < G; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(FULL, v, d * LPR);
+                if (g >= d) v &= o;
               }
-              w[x][qi] = v;
+              v &= alive[x];
+              alive[x] = __shfl_sync(FULL, v, (G - 1) * LPR + t);
+            } else {
+              v &= alive[x];
+              alive[x] = v;
             }
+            w[x][qi] = v;
           }
         }
-#pragma unroll
-        for (int x = 0; x < VEC; ++x) {
-          // membership rows are sparse: most 32-endpoint words of a batch are zero for every lane,
-          // and adding zeros is a no-op — skip the carry-save tree then (warp-uniform branch)
-          uint32_t any = 0;
-#pragma unroll
-          for (int qi = 0; qi < BATCH; ++qi) any |= w[x][qi];
-          if (__any_sync(FULL, any != 0)) bc_add<BATCH>(cnt[x], w[x]);
-        }
       }
-      if (!resolved) {
-        const bool hit = spec && kspec == hn;
-        slot_next = resolve_chunk_nodes(ix, hn, validn, hit ? cand : SLOT_MISS, hit, lane);
+#pragma unroll
+      for (int x = 0; x < VEC; ++x) {
+        // membership rows are sparse: most 32-endpoint words of a batch are zero for every lane,
+        // and adding zeros is a no-op — skip the carry-save tree then (warp-uniform branch)
+        uint32_t any = 0;
+#pragma unroll
+        for (int qi = 0; qi < BATCH; ++qi) any |= w[x][qi];
+        if (__any_sync(FULL, any != 0)) bc_add<BATCH>(cnt[x], w[x]);
       }
-      matched_rows += rows_here;
-      if (stop) break;
+      matched_rows = min(m_rows, b0 + BATCH * G);
       if (LPM) {  // every local endpoint already dropped out: nothing more can match
         bool any = false;
 #pragma unroll
         for (int x = 0; x < VEC; ++x) any |= alive[x] != 0;
         if (!__ballot_sync(FULL, any)) break;
       }
-      slot = slot_next;
     }
 
 #ifdef FI_MATCH_TIMING
@@ -711,7 +697,7 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointD
 
 template <int LPR, int VEC>
 cudaError_t launch_match_t(const MatchParams& p, int sm_count, cudaStream_t s) {
-  const size_t smem = (size_t)kWarps * p.MP * sizeof(uint64_t);
+  const size_t smem = (size_t)kWarps * p.MP * (sizeof(uint64_t) + sizeof(uint32_t));  // chains + nodes
   auto go = [&](auto kern) -> cudaError_t {
     // occupancy is a property of (kernel, smem): query once per distinct smem size
     static size_t cached_smem_dev[64];

@@ -199,6 +199,12 @@ class EndpointPicker:
         self._check(self._lib.fi_epp_lru_dump(self._h, endpoint, _ptr(out), cap, C.byref(n)), "fi_epp_lru_dump")
         return out[: n.value].copy()
 
+    def lru_counters(self) -> dict:
+        """Totals of the device-resident LRU since create (diagnostics)."""
+        out = (C.c_uint64 * 6)()
+        self._check(self._lib.fi_epp_lru_counters(self._h, out), "fi_epp_lru_counters")
+        return dict(zip(("sets", "clears", "doomed", "maintained", "deferred_requests", "sub_batches"), [int(x) for x in out]))
+
     def index_sync(self):
         self._check(self._lib.fi_epp_index_sync(self._h), "fi_epp_index_sync")
 

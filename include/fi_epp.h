@@ -289,6 +289,12 @@ int fi_epp_index_add_chains_device(fi_epp* h, const uint32_t* endpoints, const v
  * written, *n_out = how many it holds).  FI_ERR_STATE when the handle runs the host LRU. */
 int fi_epp_lru_dump(fi_epp* h, uint32_t endpoint, uint64_t* out, uint32_t cap, uint32_t* n_out);
 
+/* Diagnostics: totals of the device-resident LRU since create — out[0] SETs emitted, [1] CLEARs emitted, [2] keys
+ * touched but gone again by the end of their batch, [3] per-endpoint maintenance passes (log compaction + table
+ * rebuild), [4] requests deferred to a conservative pass (their endpoint's table could not take the batch's new
+ * keys), [5] sub-batches run. */
+int fi_epp_lru_counters(fi_epp* h, uint64_t out[6]);
+
 int fi_epp_index_sync(fi_epp* h); /* block until submitted ops are applied */
 
 /* Diagnostics: out[i] = 1 iff (q[i].endpoint, q[i].hash) is in this handle's GPU index. */

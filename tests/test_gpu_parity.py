@@ -752,6 +752,11 @@ def test_device_lru_order_and_membership_random_batches():
     _check_lru_state(gpu, ref, E)
     st = gpu.index_stats()
     assert st.lru_entries == sum(len(l.d) for l in ref) and st.tombstones > 0
+    c = gpu.lru_counters()
+    # every path ran: keys gone again within their batch, an endpoint whose table refused a batch (rolled back and
+    # re-run in capacity-sized sub-batches), log compactions / table rebuilds
+    assert c["doomed"] > 0 and c["deferred_requests"] > 0 and c["maintained"] > 0 and c["sub_batches"] > 40, c
+    assert c["sets"] - c["clears"] == st.lru_entries
     gpu.close()
 
 

@@ -42,7 +42,7 @@ def hc():
                                          C.c_uint32, C.c_uint32, C.c_void_p]
     lib.fihc_lru_plan_check.restype = C.c_int
     lib.fihc_lru_plan_check.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
-                                        C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
+                                        C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
     lib.fihc_tie_start.restype = C.c_uint32
     lib.fihc_tie_start.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
     lib.fihc_tie_rot.restype = C.c_uint32
@@ -431,12 +431,16 @@ def test_batch_lru_walk_equals_sequential_adds(hc, workers):
     assert seg.value >= 2  # the same-batch re-add path really ran
 
 
-@pytest.mark.parametrize("cap_touches,cap_requests", [(1 << 30, 1 << 30), (300, 1 << 30), (1 << 30, 7)])
-def test_device_lru_batch_rule_equals_sequential_adds(hc, cap_touches, cap_requests):
-    """The rule the device-resident LRU applies (lru_kernels.cu): a sub-batch planned by lru_plan.h — at most
-    `capacity` touches per endpoint — is applied at once (touched keys move to the back in the order of their LAST
-    touch, then the oldest beyond the capacity go).  Against one indexer.Add after the other: same recency ORDER
-    and content after every batch, with hot endpoints (many sub-batches), recurring chains and scratch-size cuts."""
+@pytest.mark.parametrize("plan_cap,cap_touches,cap_requests,min_subs",
+                         [(40, 1 << 30, 1 << 30, 2), (0xFFFFFFFF, 1 << 30, 1 << 30, 1), (0xFFFFFFFF, 300, 1 << 30, 2),
+                          (40, 1 << 30, 7, 2), (0xFFFFFFFF, 1 << 30, 7, 2)])
+def test_device_lru_batch_rule_equals_sequential_adds(hc, plan_cap, cap_touches, cap_requests, min_subs):
+    """The rule the device-resident LRU applies (lru_kernels.cu): a sub-batch planned by lru_plan.h is applied at
+    once (touched keys move to the back in the order of their LAST touch, then the oldest beyond the capacity go —
+    which also removes keys touched early in a sub-batch that brings more than `capacity` distinct ones).  Against
+    one indexer.Add after the other: same recency ORDER and content after every batch, with hot endpoints,
+    recurring chains, the conservative per-endpoint cap (40 = the capacity) and the optimistic one (none), and
+    scratch-size cuts."""
     rng = np.random.default_rng(23)
     E, cap, R, pitch, batches = 5, 40, 150, 24, 6
     pool_chains = rng.integers(1, 2**63, size=(30, pitch), dtype=np.uint64)
@@ -451,6 +455,6 @@ def test_device_lru_batch_rule_equals_sequential_adds(hc, cap_touches, cap_reque
     nb = rng.integers(0, pitch + 1, size=(batches, R)).astype(np.uint32)
     subs = C.c_uint32(0)
     rc = hc.fihc_lru_plan_check(E, cap, eps.ctypes.data, np.ascontiguousarray(chains).ctypes.data, pitch, nb.ctypes.data, R,
-                                batches, cap_touches, cap_requests, C.byref(subs))
+                                batches, plan_cap, cap_touches, cap_requests, C.byref(subs))
     assert rc == 0
-    assert subs.value >= 2
+    assert subs.value >= min_subs
