@@ -50,6 +50,9 @@ namespace fi {
 namespace {
 
 constexpr uint32_t LRU_MISS = 0xFFFFFFFFu;
+// the per-endpoint kernels (evict, maintain) walk an endpoint's log with ONE CTA, a block of records per step with
+// a dependent table lookup each: the widest CTA keeps a hot endpoint's walk (up to `capacity` evictions) short
+constexpr int kWideCta = 1024;
 
 __device__ __forceinline__ uint32_t lru_home(uint64_t key, uint32_t mask) {
   // the index table buckets by the low bits of the hash: use high ones here
@@ -125,20 +128,24 @@ __device__ __forceinline__ void lru_retire(LruSlot* tab, uint32_t TS, uint32_t s
   tab[slot].key = slot >= TS ? 0ull : KEY_TOMB;  // the two special slots are simply freed
 }
 
-// CTA-wide exclusive scan of a flag (256 threads); returns this thread's rank, *total = number of flags set
+// CTA-wide exclusive scan of a flag (any whole number of warps up to 32); returns this thread's rank,
+// *total = number of flags set
 __device__ uint32_t cta_rank(bool flag, uint32_t* total) {
-  __shared__ uint32_t s_w[8];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ uint32_t s_w[32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const unsigned m = __ballot_sync(0xFFFFFFFFu, flag);
   if (lane == 0) s_w[warp] = __popc(m);
   __syncthreads();
-  uint32_t before = 0, tot = 0;
+  // every warp scans the (at most 32) warp totals with its own lanes
+  const uint32_t c = lane < nw ? s_w[lane] : 0u;
+  uint32_t inc = c;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    const uint32_t c = s_w[w];
-    before += (uint32_t)w < warp ? c : 0u;
-    tot += c;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if ((int)lane >= d) inc += t;
   }
+  const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+  const uint32_t before = __shfl_sync(0xFFFFFFFFu, inc - c, warp);
   __syncthreads();  // s_w is reused by the next call
   *total = tot;
   return before + __popc(m & ((1u << lane) - 1u));
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(256) lru_append_kernel(DevLru lru, LruBatch b,
 }
 
 // ---- evict: one CTA per endpoint above capacity ------------------------------------------------------
-__global__ void __launch_bounds__(256) lru_evict_kernel(DevLru lru, fi_index_op* clears, unsigned long long* n_clears,
+__global__ void __launch_bounds__(kWideCta) lru_evict_kernel(DevLru lru, fi_index_op* clears, unsigned long long* n_clears,
                                                         uint64_t clears_cap, uint32_t ep_begin) {
   const uint32_t e = blockIdx.x;
   const uint32_t cnt = lru.count[e];
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(256) lru_evict_kernel(DevLru lru, fi_index_op*
 }
 
 // ---- maintain: compact the log, rebuild the table -------------------------------------------------------
-__global__ void __launch_bounds__(256) lru_maintain_kernel(DevLru lru, const uint32_t* __restrict__ inc, uint32_t force) {
+__global__ void __launch_bounds__(kWideCta) lru_maintain_kernel(DevLru lru, const uint32_t* __restrict__ inc, uint32_t force) {
   const uint32_t e = blockIdx.x;
   const uint32_t add = inc ? inc[e] : 0;
   const uint32_t head = lru.head[e];
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(256) lru_dump_kernel(DevLru lru, uint32_t e, u
 }  // namespace
 
 cudaError_t launch_lru_maintain(const DevLru& lru, const uint32_t* inc, bool force, cudaStream_t s) {
-  lru_maintain_kernel<<<lru.EL, 256, 0, s>>>(lru, inc, force ? 1u : 0u);
+  lru_maintain_kernel<<<lru.EL, kWideCta, 0, s>>>(lru, inc, force ? 1u : 0u);
   return cudaGetLastError();
 }
 cudaError_t launch_lru_touch(const DevLru& lru, const LruBatch& b, cudaStream_t s) {
@@ -486,7 +493,7 @@ cudaError_t launch_lru_append(const DevLru& lru, const LruBatch& b, fi_index_op*
 }
 cudaError_t launch_lru_evict(const DevLru& lru, fi_index_op* clears, unsigned long long* n_clears, uint64_t clears_cap,
                              uint32_t ep_begin, cudaStream_t s) {
-  lru_evict_kernel<<<lru.EL, 256, 0, s>>>(lru, clears, n_clears, clears_cap, ep_begin);
+  lru_evict_kernel<<<lru.EL, kWideCta, 0, s>>>(lru, clears, n_clears, clears_cap, ep_begin);
   return cudaGetLastError();
 }
 cudaError_t launch_lru_dump(const DevLru& lru, uint32_t e, uint64_t* out, uint32_t* n_out, cudaStream_t s) {
