@@ -48,3 +48,11 @@ $(TIMING_LIB): $(CU_SRCS) $(HDRS) $(OBJDIR)/epp_config.o
 	for f in hash_kernels index_kernels lru_kernels match_kernels engine; do $(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -DFI_MATCH_TIMING -Xcompiler -fPIC -c $(CSRC)/$$f.cu -o $(OBJDIR)/timing/$$f.o || exit 1; done
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJDIR)/timing/*.o $(OBJDIR)/epp_config.o -ldl
 .PHONY: timing
+
+# A/B builds of the library with extra defines:  make variant NAME=b16 DEFS=-DFI_MATCH_BATCH=16
+# -> fusioninfer_b200/lib/libfi_epp_$(NAME).so (select it with FI_EPP_LIB=<path>)
+variant: $(CU_SRCS) $(HDRS) $(OBJDIR)/epp_config.o
+	@mkdir -p $(OBJDIR)/$(NAME)
+	for f in hash_kernels index_kernels lru_kernels match_kernels engine; do $(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo $(DEFS) -Xcompiler -fPIC -c $(CSRC)/$$f.cu -o $(OBJDIR)/$(NAME)/$$f.o || exit 1; done
+	$(NVCC) $(ARCH) -shared -o fusioninfer_b200/lib/libfi_epp_$(NAME).so $(OBJDIR)/$(NAME)/*.o $(OBJDIR)/epp_config.o -ldl
+.PHONY: variant

@@ -220,6 +220,7 @@ struct fi_epp {
   // the two are never mixed on one handle.
   int lru_mode = -1;  // -1: not chosen yet, 0: host LRU, 1: device LRU
   int lru_want = -1;  // option / environment override (-1: automatic)
+  uint32_t lru_table_slots = 0;  // option "lru_table_slots": slots per endpoint table of the device LRU (0: sized by free HBM)
   DevLru dlru{};
   uint32_t* d_lru_state = nullptr;           // head | tail | count | used | error
   unsigned long long* d_lru_ctr = nullptr;   // [0] SETs emitted, [1] endpoints maintained, [2] CLEARs of the running sub-batch,
@@ -608,12 +609,25 @@ int ensure_dev_lru(fi_epp* h) {
   DevLru& d = h->dlru;
   d.EL = EL;
   d.capacity = C;
-  d.TS = std::max<uint32_t>(pow2_ceil32(4u * C), 64u);  // C entries + a batch's new keys + tombstones (lru_kernels.cu)
-  d.L = d.TS;
-  d.insert_limit = (uint32_t)((uint64_t)d.TS * 85 / 100);
-  const size_t slot_bytes = (size_t)EL * (d.TS + 2) * sizeof(LruSlot), log_bytes = (size_t)EL * d.L * sizeof(uint64_t);
   size_t free_b = 0, total_b = 0;
   FI_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  // Log: at least 4 C records (a sub-batch appends at most C; more room = rarer compaction).  Table: at least 4 C slots (C entries + C new keys of a
+  // conservative sub-batch + tombstones); a table takes a batch's DISTINCT keys on top of its entries, and an
+  // endpoint that attracts a popular prefix can receive a large share of a batch — so the tables get as much as
+  // a quarter of the free HBM buys, up to 32 C slots (1 Mi slots = 16 MiB per endpoint at lruCapacityPerServer
+  // 31 250: 17 GB for 1 024 endpoints of a B200's 180).  Option "lru_table_slots" / FI_EPP_LRU_TABLE_SLOTS pins it.
+  d.L = std::max<uint32_t>(pow2_ceil32(4u * C), 64u);
+  const uint32_t ts_min = d.L;
+  uint32_t ts = pow2_ceil32(32u * C);
+  while (ts > ts_min && (size_t)EL * (ts + 2) * sizeof(LruSlot) > free_b / 4) ts >>= 1;
+  uint32_t want = h->lru_table_slots;
+  if (!want)
+    if (const char* ev = std::getenv("FI_EPP_LRU_TABLE_SLOTS")) want = (uint32_t)std::strtoul(ev, nullptr, 10);
+  if (want) ts = std::max(ts_min, pow2_ceil32(want));
+  d.TS = ts;
+  d.L = std::max(d.L, d.TS / 4);
+  d.insert_limit = (uint32_t)((uint64_t)d.TS * 85 / 100);
+  const size_t slot_bytes = (size_t)EL * (d.TS + 2) * sizeof(LruSlot), log_bytes = (size_t)EL * d.L * sizeof(uint64_t);
   h->lru_touch_cap = std::max<uint64_t>((uint64_t)h->cfg.max_batch * h->MP, 1u << 16);
   const size_t scratch = (size_t)h->lru_touch_cap * (sizeof(uint32_t) + 2 * sizeof(fi_index_op));
   if (slot_bytes + log_bytes + scratch + (256u << 20) > free_b)
@@ -2099,6 +2113,8 @@ int fi_epp_hash_batch(fi_epp* h, const uint8_t* prompts, const uint64_t* offsets
   if (rc != FI_OK) return rc;
   if (h->pipe_seq)  // a pipelined batch's stage A (on s_a) shares d_pre with us
     FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_a[(h->pipe_seq - 1) & 1], 0));
+  if (h->ev_lru) FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_lru, 0));  // a device-LRU Add may still be reading d_chain
+  h->last_plain_R = 0;  // d_chain no longer holds a pick batch's chains
   rc = run_hash(h, h->d_prompts, h->d_offsets, h->d_h0, 0, R, h->s_main);
   if (rc != FI_OK) return rc;
   if (chains_out) {
@@ -2310,6 +2326,12 @@ int fi_epp_set_option(fi_epp* h, const char* name, int64_t value) {
     if (value != 0 && value != 1) return fail(h, FI_ERR_INVALID, "device_lru: 0 or 1");
     if (h->lru_mode >= 0 && h->lru_mode != (int)value) return fail(h, FI_ERR_STATE, "device_lru: the handle's LRU is already in use");
     h->lru_want = (int)value;
+    return FI_OK;
+  }
+  if (n == "lru_table_slots") {
+    if (value < 0 || value > (1ll << 30)) return fail(h, FI_ERR_INVALID, "lru_table_slots: 0 .. 2^30");
+    if (h->dlru.slots) return fail(h, FI_ERR_STATE, "lru_table_slots: the device LRU is already allocated");
+    h->lru_table_slots = (uint32_t)value;
     return FI_OK;
   }
   if (n == "lru_threads") {

@@ -15,11 +15,12 @@
 // surviving winners that were new to the endpoint and CLEAR for the entries that fell off — the same membership
 // as R sequential Adds, whatever those inserted and evicted in between.
 //
-// Capacity.  A table takes the batch's distinct keys on top of its C entries; it holds 0.85 TS = 3.4 C.  A hot
-// endpoint whose requests share their prefix (why they were routed there) fits easily; one that receives more
-// NEW distinct keys than that in a single batch is detected while inserting (slots are reserved before they are
-// claimed), its touches are rolled back and its requests are re-run in sub-batches of at most C touches, which
-// always fit (lru_plan.h; endpoints are independent of each other, so deferring one is exact).
+// Capacity.  A table takes the batch's distinct keys on top of its C entries; it holds 0.85 TS, with TS between
+// 4 C and 32 C slots depending on how much HBM is free (engine.cu: a B200 gives 1 024 endpoints 1 Mi slots each).
+// An endpoint that receives more NEW distinct keys than that in a single batch is detected while inserting
+// (slots are reserved before they are claimed), its touches are rolled back and its requests are re-run in
+// sub-batches of at most C touches, which always fit (lru_plan.h; endpoints are independent of each other, so
+// deferring one is exact).
 //
 // Per endpoint e (all in HBM):
 //   table  [TS + 2] LruSlot   open-addressed, linear probing, key → (log position + 1, order of its last touch
@@ -33,8 +34,9 @@
 //   head, tail, count (live entries), used (table slots consumed)
 //
 // One sub-batch = kernels  maintain → touch → (untouch) → count → scan → append → [index SET] → evict → [index CLEAR]:
-//   maintain  endpoints whose log or table could overflow: compact the log (live records only, renumbered from
-//             0) and rebuild the table from it                                      one CTA per endpoint
+//   maintain  endpoints whose log could overflow: compact it (live records only, renumbered from 0; the table
+//             follows); endpoints whose table is crowded with tombstones: rebuild it from the compacted log
+//                                                                                    one CTA per endpoint
 //   touch     find-or-insert every (endpoint, key); atomicMax of the touch order    one CTA per request
 //   untouch   (only after an overflow) undo the touches of the overflowed endpoints
 //   count     a touch is a WINNER iff it is its key's last touch of the sub-batch; winners per request
@@ -381,8 +383,9 @@ __global__ void __launch_bounds__(kWideCta) lru_maintain_kernel(DevLru lru, cons
   if (!force && !log_tight && !tab_tight) return;
   LruSlot* tab = lru.slots + (uint64_t)e * (lru.TS + 2);
   uint64_t* log = lru.log + (uint64_t)e * lru.L;
-  // 1. live records move to the front, in order (a chunk is read completely before any of it is rewritten, and
-  //    the write cursor never passes the read cursor)
+  // 1. live records move to the front, in order, and the table follows them (a chunk is read completely before
+  //    any of it is rewritten, and the write cursor never passes the read cursor; a key's stale records all lie
+  //    before its live one, so a rewritten position is never mistaken for one of them)
   uint32_t d = 0;
   for (uint32_t t = lru.tail[e]; t < head; t += blockDim.x) {
     const uint32_t p = t + threadIdx.x;
@@ -398,12 +401,19 @@ __global__ void __launch_bounds__(kWideCta) lru_maintain_kernel(DevLru lru, cons
     const uint32_t rank = cta_rank(live, &tot);  // (barriers inside: reads above are done)
     if (live) {
       log[d + rank] = key;
-      if (slot >= lru.TS) tab[slot].posp1 = d + rank + 1;  // special slots survive the rebuild below
+      tab[slot].posp1 = d + rank + 1;
     }
     d += tot;
     __syncthreads();
   }
-  // 2. fresh table from the compacted log
+  if (threadIdx.x == 0) {
+    lru.tail[e] = 0;
+    lru.head[e] = d;
+    if (d != lru.count[e]) atomicExch(lru.error, 5u);  // live records == entries, always
+    atomicAdd(lru.n_maintained, 1ull);
+  }
+  if (!force && !tab_tight) return;
+  // 2. tombstones crowd the table: a fresh one from the compacted log (the two special slots keep their place)
   const uint4 z = make_uint4(0, 0, 0, 0);
   for (uint32_t i = threadIdx.x; i < lru.TS; i += blockDim.x) reinterpret_cast<uint4*>(tab)[i] = z;
   if (threadIdx.x == 0) lru.used[e] = 0;
@@ -428,13 +438,7 @@ __global__ void __launch_bounds__(kWideCta) lru_maintain_kernel(DevLru lru, cons
   __syncthreads();
   if ((threadIdx.x & 31) == 0 && regular) atomicAdd(&s_tot, regular);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    lru.tail[e] = 0;
-    lru.head[e] = d;
-    if (atomicAdd(lru.used + e, 0u) != s_tot) atomicExch(lru.error, 6u);
-    if (d != lru.count[e]) atomicExch(lru.error, 5u);  // live records == entries, always
-    atomicAdd(lru.n_maintained, 1ull);
-  }
+  if (threadIdx.x == 0 && atomicAdd(lru.used + e, 0u) != s_tot) atomicExch(lru.error, 6u);
 }
 
 // diagnostics (tests): the live keys of endpoint e, oldest first

@@ -173,13 +173,18 @@ constexpr int kSpecTries = 4;
 constexpr int kSpecChunks = 8;  // chunks of 32 blocks verified per round (256 blocks; longer chains loop)
 
 __device__ __forceinline__ uint32_t resolve_request_nodes(const IndexView& ix, const uint64_t* __restrict__ s_chain,
-                                                          uint32_t* __restrict__ s_node, uint32_t n, int lane) {
+                                                          uint32_t* __restrict__ s_node, uint32_t n, int lane, bool have_first,
+                                                          uint32_t first_node) {
   uint32_t pos = 0;  // blocks [0, pos) are resolved and present
   for (int tries = 0; pos < n; ++tries) {
     if (tries < kSpecTries) {
       uint32_t nf = SLOT_MISS;
-      if (lane == 0) nf = index_find(ix, s_chain[pos]);
-      nf = __shfl_sync(FULL, nf, 0);
+      if (tries == 0 && have_first) {
+        nf = first_node;  // block 0's table lookup was issued during the previous request (warp-uniform)
+      } else {
+        if (lane == 0) nf = index_find(ix, s_chain[pos]);
+        nf = __shfl_sync(FULL, nf, 0);
+      }
       if (nf == SLOT_MISS) return pos;  // first miss of the request
       if (lane == 0) s_node[pos] = nf;
       uint32_t fail = n;  // first block after pos whose node is not nf + distance
@@ -247,39 +252,67 @@ template <int LPR, int VEC, bool LPM, bool LORA>
 __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS : FI_MATCH_MIN_BLOCKS + 1))
     match_pick_kernel(const MatchParams p) {
   constexpr int G = 32 / LPR;                 // rows per load instruction
-  constexpr int BATCH = LPR < 8 ? LPR : 8;    // load instructions in flight
+#ifndef FI_MATCH_BATCH
+#define FI_MATCH_BATCH 8
+#endif
+  constexpr int BATCH = LPR < FI_MATCH_BATCH ? LPR : FI_MATCH_BATCH;  // load instructions in flight
   extern __shared__ __align__(16) uint64_t s_mem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int t = lane % LPR;  // position within the row
   const int g = lane / LPR;  // row group
-  uint64_t* s_chain = s_mem + (size_t)warp * p.MP;
-  uint32_t* s_node = reinterpret_cast<uint32_t*>(s_mem + (size_t)kWarps * p.MP) + (size_t)warp * p.MP;  // node of every block
+  // per warp: two chain buffers (the next request's chain is staged while this one is matched) and the nodes
+  uint64_t* const s_chain_base = s_mem + (size_t)(2 * warp) * p.MP;  // buffer b at s_chain_base + b * MP
+  uint32_t* s_node = reinterpret_cast<uint32_t*>(s_mem + (size_t)2 * kWarps * p.MP) + (size_t)warp * p.MP;  // node of every block
   const IndexView ix = p.ix;
   const uint32_t P = p.st.n_profiles;
   const char* row_base = reinterpret_cast<const char*>(ix.rows + t * VEC);
   const uint32_t row_bytes = 4u << ix.logW;
   const uint32_t zero_slot = (uint32_t)(ix.C + 2);  // never written: all-zero row
 
-  // dynamic work queue (requests differ a lot in how many rows they touch); the next item is
-  // fetched while the current one is processed so the atomic's round trip is off the critical path
+  // Dynamic work queue (requests differ a lot in how many rows they touch), software-pipelined across requests:
+  // while request r is matched, the ticket of the request after next is in flight, the chain of the next one is
+  // being staged into the other buffer, and the home bucket of its first block is being fetched (lanes 0-3:
+  // one key + node each) — a request starts with its chain and its first node already there instead of waiting
+  // out three dependent round trips (ticket -> chain -> table), a third of a request's time in round 1.
+  const uint32_t row_units = p.MP / 2;  // 16-byte units of a chain row (rows are zero-padded to MP by the walker)
+  auto stage = [&](uint32_t rr, uint64_t* dst) {
+    const uint64_t* crow = p.chain + (uint64_t)rr * p.MP;
+    for (uint32_t u = lane; u < row_units; u += 32) cp_async16(dst + 2 * u, crow + 2 * u);
+  };
   uint32_t r_next = 0;
   if (lane == 0) r_next = take_ticket(p.work_counter, threadIdx.x & p.lane_zero);
   r_next = __shfl_sync(FULL, r_next, 0);
+  int buf = 0;
+  if (r_next < p.R) stage(r_next, s_chain_base);
+  // prefetched home bucket of the current request's first block (valid when pf_ok)
+  bool pf_ok = false;
+  uint64_t pf_h = 0, pf_key = 0;
+  uint32_t pf_node = 0;
   for (;;) {
     const uint32_t r = r_next;
     if (r >= p.R) break;
     if (lane == 0) r_next = take_ticket(p.work_counter, threadIdx.x & p.lane_zero);
     const uint32_t n = p.nblocks[r];
+    uint64_t* s_chain = s_chain_base + (size_t)buf * p.MP;
 #ifdef FI_MATCH_TIMING
     const long long tm0 = clock64();
 #endif
-    // ---- 1. stage the chain
-    {
-      const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
-      for (uint32_t u = lane; 2 * u < n; u += 32) cp_async16(s_chain + 2 * u, crow + 2 * u);
-      cp_async_wait_all();
-      __syncwarp();
+    // ---- 1. the chain was staged during the previous request (or just above)
+    cp_async_wait_all();
+    __syncwarp();
+    // first block's node from the prefetched bucket
+    bool have_first = false;
+    uint32_t first_node = SLOT_MISS;
+    if (pf_ok && n) {
+      const unsigned hit = __ballot_sync(FULL, lane < BUCKET_KEYS && pf_key == pf_h);
+      const unsigned emp = __ballot_sync(FULL, lane < BUCKET_KEYS && pf_key == KEY_EMPTY);
+      if (hit) {
+        first_node = __shfl_sync(FULL, pf_node, __ffs(hit) - 1);
+        have_first = true;
+      } else if (emp) {
+        have_first = true;  // definite miss
+      }  // else: home bucket full without a match — resolve_request_nodes probes on
     }
 
 #ifdef FI_MATCH_TIMING
@@ -296,9 +329,16 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
     bool real_miss = false;
 
     // ---- 2. the index node of every block up to the first one no endpoint holds ---------------
-    const uint32_t m_rows = resolve_request_nodes(ix, s_chain, s_node, n, lane);
+    const uint32_t m_rows = resolve_request_nodes(ix, s_chain, s_node, n, lane, have_first, first_node);
     real_miss = m_rows < n;
     __syncwarp();  // s_node is written by some lanes and read by others
+    // ---- the next request: its ticket has long arrived; stage its chain and read its first hash
+    r_next = __shfl_sync(FULL, r_next, 0);
+    pf_ok = false;
+    if (r_next < p.R) {
+      stage(r_next, s_chain_base + (size_t)(buf ^ 1) * p.MP);
+      pf_h = __ldg(p.chain + (uint64_t)r_next * p.MP);
+    }
 #ifdef FI_MATCH_TIMING
     const long long tm2 = clock64();
 #endif
@@ -355,6 +395,14 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
       }
     }
 
+    if (r_next < p.R && !key_is_special(pf_h)) {  // pf_h has arrived by now: fetch its home bucket, used next iteration
+      pf_ok = true;
+      if (lane < BUCKET_KEYS) {
+        const uint64_t slot0 = (pf_h & ix.bmask) * BUCKET_KEYS + lane;
+        pf_key = __ldg(ix.keys + slot0);
+        pf_node = __ldg(ix.node_of + slot0);
+      }
+    }
 #ifdef FI_MATCH_TIMING
     const long long tm3 = clock64();
 #endif
@@ -520,7 +568,8 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
       }
 #endif
     }
-    r_next = __shfl_sync(FULL, r_next, 0);  // also orders this request's s_chain reads before the next staging
+    buf ^= 1;
+    __syncwarp();  // this request's s_chain / s_node reads are done before the buffers are written again
   }
 }
 
@@ -697,7 +746,7 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointD
 
 template <int LPR, int VEC>
 cudaError_t launch_match_t(const MatchParams& p, int sm_count, cudaStream_t s) {
-  const size_t smem = (size_t)kWarps * p.MP * (sizeof(uint64_t) + sizeof(uint32_t));  // chains + nodes
+  const size_t smem = (size_t)kWarps * p.MP * (2 * sizeof(uint64_t) + sizeof(uint32_t));  // 2 chain buffers + nodes
   auto go = [&](auto kern) -> cudaError_t {
     // occupancy is a property of (kernel, smem): query once per distinct smem size
     static size_t cached_smem_dev[64];

@@ -696,6 +696,7 @@ def _device_lru_handle(E, cap, max_blocks, max_batch=256):
     cfg = H.config_for(wl, lru_capacity=cap, index_slots=1 << 17, max_batch=max_batch)
     gpu = EndpointPicker(cfg)
     gpu.set_option("device_lru", 1)
+    gpu.set_option("lru_table_slots", 1)  # the minimum (4 x capacity): hot endpoints overflow their table
     return gpu
 
 
