@@ -187,10 +187,7 @@ struct fi_epp {
   unsigned long long* h_ghdr = nullptr;    // pinned copy
   uint64_t* d_ggather = nullptr;           // [world][kOpChunk]
   unsigned long long* d_probed = nullptr;
-  uint32_t* d_work = nullptr;  // [kWorkSlots] dynamic work-queue counters of in-flight match launches (slices 0..15, pipeline 16..17)
-  static constexpr int kWorkSlots = 18;
-  ProbeRec* d_probe = nullptr;     // [kWorkSlots][kProbeBins][max_batch] probe records of those launches
-  uint32_t* d_bins = nullptr;      // [kWorkSlots][32] their bin counters
+  uint32_t* d_work = nullptr;  // [16] dynamic work-queue counters of in-flight match launches
   // pinned host mirrors
   fi_pick* h_picks = nullptr;
   uint64_t* h_offsets = nullptr;
@@ -1040,14 +1037,6 @@ struct HostFeed {
   const uint64_t* offsets;  // host, [R+1]
 };
 
-// scratch of one in-flight match launch: its request queue counter, probe records and bin counters
-void set_work_slot(fi_epp* h, MatchParams& mp, int slot) {
-  mp.work_counter = h->d_work + slot;
-  mp.rec_pitch = h->cfg.max_batch;
-  mp.recs = h->d_probe + (size_t)slot * kProbeBins * h->cfg.max_batch;
-  mp.bin_count = h->d_bins + (size_t)slot * 32;
-}
-
 void fill_match_params(fi_epp* h, MatchParams& mp, const uint64_t* chain, const uint32_t* nb, const uint64_t* d_offsets,
                        const uint64_t* d_h0, const uint64_t* d_adapters, uint32_t R, fi_pick* out, bool local_pd) {
   mp.chain = chain;
@@ -1070,9 +1059,9 @@ void fill_match_params(fi_epp* h, MatchParams& mp, const uint64_t* chain, const 
   mp.pd_threshold = h->cfg.pd_threshold;
   mp.out = out;
   mp.probed_blocks = h->profiling ? h->d_probed : nullptr;
+  mp.work_counter = h->d_work;
   mp.zero_work_counter = 1;
   mp.lane_zero = 0;
-  set_work_slot(h, mp, 0);
 }
 
 // the whole pick on device buffers; result in d_out ([R][P])
@@ -1130,10 +1119,9 @@ int run_pick_impl(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets
       ms.r_base = r0;
       ms.R = Rk;
       ms.out = mp.out + (size_t)r0 * h->P;
-      set_work_slot(h, ms, (int)k);
+      ms.work_counter = h->d_work + k;
       LaunchScope ls(h, h->s_main, K_MATCH);
       FI_CUDA(launch_match_pick(ms, h->sm_count, h->s_main));
-      h->stats.kernel_launches++;  // (chain_probe + match_pick)
     }
     dump_trace(h, R);
     h->stats.pick_calls++;
@@ -1153,8 +1141,6 @@ int run_pick_impl(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets
     {
       LaunchScope ls(h, h->s_main, K_MATCH);
       FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
-    h->stats.kernel_launches++;  // (chain_probe + match_pick)
-      h->stats.kernel_launches++;  // (chain_probe + match_pick)
     }
     dump_trace(h, R);
     h->stats.pick_calls++;
@@ -1198,7 +1184,6 @@ int run_pick_impl(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets
   {
     LaunchScope ls(h, h->s_main, K_MATCH);
     FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
-    h->stats.kernel_launches++;  // (chain_probe + match_pick)
   }
   MergeParams mg{};
   if (p2p) {
@@ -1304,12 +1289,11 @@ int submit_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, 
   FI_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_a[slot], 0));
   MatchParams mp{};
   fill_match_params(h, mp, chain, nb, d_offsets, d_h0, nullptr, R, d_out, true);
-  set_work_slot(h, mp, 16 + (int)slot);
+  mp.work_counter = h->d_work + 8 + slot;
   mp.max_ctas_per_sm = h->pipe_match_ctas;
   {
     LaunchScope ls(h, h->s_main, K_MATCH);
     FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
-    h->stats.kernel_launches++;  // (chain_probe + match_pick)
   }
   FI_CUDA(cudaEventRecord(h->ev_b[slot], h->s_main));
   FI_CUDA(cudaEventRecord(h->ev_pick, h->s_main));
@@ -1455,8 +1439,6 @@ void fi_epp_destroy(fi_epp* h) {
   if (h->h_xerr) cudaFreeHost((void*)h->h_xerr);
   cudaFree(h->d_probed);
   cudaFree(h->d_work);
-  cudaFree(h->d_probe);
-  cudaFree(h->d_bins);
   cudaFree(h->d_ctr);
   cudaFree(h->d_eps);
   cudaFree(h->d_sc);
@@ -1598,11 +1580,8 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaMalloc(&h->d_picks, R * h->P * sizeof(fi_pick)));
   FI_TRY(cudaMalloc(&h->d_probed, 8 * sizeof(unsigned long long)));
   FI_TRY(cudaMemset(h->d_probed, 0, 8 * sizeof(unsigned long long)));
-  FI_TRY(cudaMalloc(&h->d_work, fi_epp::kWorkSlots * sizeof(uint32_t)));
-  FI_TRY(cudaMemset(h->d_work, 0, fi_epp::kWorkSlots * sizeof(uint32_t)));
-  FI_TRY(cudaMalloc(&h->d_probe, (size_t)fi_epp::kWorkSlots * kProbeBins * R * sizeof(ProbeRec)));
-  FI_TRY(cudaMalloc(&h->d_bins, (size_t)fi_epp::kWorkSlots * 32 * sizeof(uint32_t)));
-  FI_TRY(cudaMemset(h->d_bins, 0, (size_t)fi_epp::kWorkSlots * 32 * sizeof(uint32_t)));
+  FI_TRY(cudaMalloc(&h->d_work, 16 * sizeof(uint32_t)));
+  FI_TRY(cudaMemset(h->d_work, 0, 16 * sizeof(uint32_t)));
   FI_TRY(cudaMallocHost(&h->h_picks, R * h->P * sizeof(fi_pick)));
   FI_TRY(cudaMallocHost(&h->h_offsets, (R + 1) * sizeof(uint64_t)));
   FI_TRY(cudaMallocHost(&h->h_h0, R * sizeof(uint64_t)));

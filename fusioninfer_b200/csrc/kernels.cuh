@@ -132,20 +132,6 @@ struct PeerXchg {
   uint32_t* err;                // local: set to 1 if a poll timed out
 };
 
-// One request as the probe pass (chain_probe_kernel) hands it to match_pick: where its cached prefix sits in the
-// index.  The records are written into cost bins (by prefix length) so that the match kernel's dynamic queue can
-// take the long requests first.
-struct ProbeRec {     // 32 bytes
-  uint32_t r;         // request
-  uint32_t node0;     // node of block 0 (SLOT_MISS: the index does not hold it)
-  uint16_t m;         // blocks [0, m) have the consecutive nodes node0 + i
-  uint16_t n;         // blocks of the request
-  uint32_t complete;  // 1: block m is a confirmed miss (or m == n): nothing left to resolve
-  uint64_t h_first;   // first chain hash (seed of the tie rotation)
-  uint64_t pad;
-};
-constexpr uint32_t kProbeBins = 17;  // bin b: ceil(16 m / MP) — 0: no cached prefix ... 16: (almost) the whole prompt
-
 struct MatchParams {
   const uint64_t* chain;
   const uint32_t* nblocks;
@@ -166,9 +152,6 @@ struct MatchParams {
   double pd_threshold;
   fi_pick* out;                       // [R][P]
   unsigned long long* probed_blocks;  // optional Σ N_probe
-  ProbeRec* recs;                     // [kProbeBins][rec_pitch] probe records by cost bin (scratch of the launch)
-  uint32_t* bin_count;                // [32] records per bin (zeroed by the launcher)
-  uint32_t rec_pitch;
   uint32_t* work_counter;             // dynamic request queue of the launch
   uint32_t zero_work_counter;         // launcher zeroes it first (0: the caller already did)
   uint32_t max_ctas_per_sm;           // 0: as many as fit; else a cap (pipelined API: leave room for hash_blocks)

@@ -156,12 +156,14 @@ __device__ __forceinline__ void load_row_words(const uint32_t* __restrict__ p, b
   }
 }
 
-// Nodes of the blocks of a request whose cached prefix is NOT one consecutive run of nodes (an index built out of
-// chain order; the probe pass found block `pos` present but not at the expected node).  After a table lookup for
-// block `pos` every later block i checks "my node = that node + (i - pos)" — coalesced reads of klog, all chunks
-// of the request in flight at once — and the table is probed again where that fails; after kSpecTries such rounds
-// the remaining blocks probe the table in parallel, 64 at a time, as a plain hash index would.
-// Returns m = number of leading blocks the index holds (the first miss, or n); s_node[pos .. m) = their nodes.
+// Nodes of ALL blocks of a request, before any row is read.  A cached prefix was inserted in chain order, so its
+// nodes are consecutive (index_device.cuh): after ONE table lookup for block `pos` every later block i checks
+// "my node = that node + (i - pos)" — coalesced reads of klog, all chunks of the request in flight at once.  The
+// table is probed again only where that fails: normally at the first block the index does not hold, which ends
+// the walk (both match modes stop at the first block no pod holds).  A prefix whose nodes are scattered (an index
+// built out of chain order) gets kSpecTries such rounds, then its remaining blocks probe the table in parallel,
+// 64 at a time, as a plain hash index would.
+// Returns m = number of leading blocks the index holds (the first miss, or n); s_node[0 .. m) = their nodes.
 //
 // (Round 1 resolved chunk c+1 while chunk c's rows were in flight: a request's serial chain was two dependent
 // memory round trips per 32 blocks, ~5 800 cycles per chunk and 23 us for a fully cached 256-block prompt — a
@@ -171,14 +173,18 @@ constexpr int kSpecTries = 4;
 constexpr int kSpecChunks = 8;  // chunks of 32 blocks verified per round (256 blocks; longer chains loop)
 
 __device__ __forceinline__ uint32_t resolve_request_nodes(const IndexView& ix, const uint64_t* __restrict__ s_chain,
-                                                          uint32_t* __restrict__ s_node, uint32_t n, int lane, uint32_t pos,
-                                                          int tries) {
-  // blocks [0, pos) are resolved and present (the probe pass's consecutive run)
-  for (; pos < n; ++tries) {
+                                                          uint32_t* __restrict__ s_node, uint32_t n, int lane, bool have_first,
+                                                          uint32_t first_node) {
+  uint32_t pos = 0;  // blocks [0, pos) are resolved and present
+  for (int tries = 0; pos < n; ++tries) {
     if (tries < kSpecTries) {
       uint32_t nf = SLOT_MISS;
-      if (lane == 0) nf = index_find(ix, s_chain[pos]);
-      nf = __shfl_sync(FULL, nf, 0);
+      if (tries == 0 && have_first) {
+        nf = first_node;  // block 0's table lookup was issued during the previous request (warp-uniform)
+      } else {
+        if (lane == 0) nf = index_find(ix, s_chain[pos]);
+        nf = __shfl_sync(FULL, nf, 0);
+      }
       if (nf == SLOT_MISS) return pos;  // first miss of the request
       if (lane == 0) s_node[pos] = nf;
       uint32_t fail = n;  // first block after pos whose node is not nf + distance
@@ -229,85 +235,6 @@ __device__ __forceinline__ uint32_t resolve_request_nodes(const IndexView& ix, c
   return n;
 }
 
-// Probe pass, one warp per request: where does the request's cached prefix sit in the index, and how long is it?
-// A cached prefix was inserted in chain order, so its nodes are consecutive (index_device.cuh): one table lookup
-// for block 0, then every later block i checks "klog[node0 + i] is my hash" — coalesced reads, all chunks of the
-// request in flight at once — and one more lookup tells whether the block that ends the run is really absent
-// (normally: the walk ends there, both match modes stop at the first block no pod holds) or merely stored
-// elsewhere (complete = 0: match_pick resolves the rest).  Three dependent round trips per request at full
-// occupancy (a light kernel: 64 warps per SM), instead of on the critical path of match_pick's 24 warps per SM.
-// The record goes into a cost bin by run length so that match_pick's queue hands out the long requests first:
-// a fully cached 256-block prompt costs ten times a cold one, and whichever warp drew one last used to hold
-// the whole kernel (round 1: SM sub-partitions idle 36 % of match_pick's duration).
-__global__ void __launch_bounds__(256) chain_probe_kernel(const MatchParams p) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= p.R) return;
-  const IndexView ix = p.ix;
-  const uint32_t n = p.nblocks[r];
-  const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
-  uint64_t h_first = 0;
-  uint32_t node0 = SLOT_MISS, m = 0, complete = 1;
-  if (n) {
-    h_first = __ldg(crow);
-    if (lane == 0) node0 = index_find(ix, h_first);
-    node0 = __shfl_sync(FULL, node0, 0);
-  }
-  if (node0 != SLOT_MISS) {
-    m = 1;
-    if (node0 < ix.C) {  // (the hashes 0 / ~0 own fixed nodes: nothing to speculate from)
-      uint32_t fail = n;
-      for (uint32_t i0 = 1; i0 < n && fail == n; i0 += 32 * kSpecChunks) {
-        uint64_t hk[kSpecChunks], kk[kSpecChunks];
-#pragma unroll
-        for (int c = 0; c < kSpecChunks; ++c) {
-          const uint32_t idx = i0 + 32 * c + lane;
-          hk[c] = 0;
-          kk[c] = 1;  // (!= hk: a lane without a block never verifies)
-          if (idx < n) {
-            hk[c] = __ldg(crow + idx);
-            const uint64_t cand = (uint64_t)node0 + idx;
-            if (cand < ix.C) kk[c] = __ldg(ix.klog + cand);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < kSpecChunks; ++c) {
-          const uint32_t idx = i0 + 32 * c + lane;
-          if (fail != n || i0 + 32 * c >= n) break;  // warp-uniform
-          const bool ok = idx < n && kk[c] == hk[c] && !key_is_special(hk[c]);
-          const unsigned bad = __ballot_sync(FULL, idx < n && !ok);
-          if (bad) fail = i0 + 32 * c + (uint32_t)(__ffs(bad) - 1);
-        }
-      }
-      m = fail;
-    }
-    if (m < n) {  // is the block that ended the run absent, or only somewhere else?
-      uint32_t nf = SLOT_MISS;
-      if (lane == 0) nf = index_find(ix, __ldg(crow + m));
-      nf = __shfl_sync(FULL, nf, 0);
-      complete = nf == SLOT_MISS ? 1u : 0u;
-    }
-  }
-  if (lane == 0) {
-    // cost bin: run length in sixteenths of the longest chain; unresolved requests count as the most expensive
-    uint32_t b = complete ? ((uint32_t)m * 16u + p.MP - 1u) / p.MP : kProbeBins - 1u;
-    if (b >= kProbeBins) b = kProbeBins - 1u;
-    const uint32_t at = atomicAdd(p.bin_count + b, 1u);
-    ProbeRec rec;
-    rec.r = r;
-    rec.node0 = node0;
-    rec.m = (uint16_t)m;
-    rec.n = (uint16_t)n;
-    rec.complete = complete;
-    rec.h_first = h_first;
-    rec.pad = 0;
-    uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)b * p.rec_pitch + at);
-    const uint4* src = reinterpret_cast<const uint4*>(&rec);
-    dst[0] = src[0];
-    dst[1] = src[1];
-  }
-}
-
 // next request of the launch's dynamic queue.  Plain PTX on purpose: for `if (lane == 0) atomicAdd(..)` the
 // compiler emits its warp-aggregated form — ATOMG followed at once by a SHFL of the result — which makes every
 // request wait out the atomic's round trip (15 % of the kernel's stall samples in round 1).  Here the result
@@ -336,56 +263,62 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
   const int lane = threadIdx.x & 31;
   const int t = lane % LPR;  // position within the row
   const int g = lane / LPR;  // row group
-  // per warp: the chain and the node list of a request whose prefix is scattered (the rare case; a consecutive run
-  // needs neither)
-  uint64_t* const s_chain = s_mem + (size_t)warp * p.MP;
-  uint32_t* s_node = reinterpret_cast<uint32_t*>(s_mem + (size_t)kWarps * p.MP) + (size_t)warp * p.MP;
+  // per warp: two chain buffers (the next request's chain is staged while this one is matched) and the nodes
+  uint64_t* const s_chain_base = s_mem + (size_t)(2 * warp) * p.MP;  // buffer b at s_chain_base + b * MP
+  uint32_t* s_node = reinterpret_cast<uint32_t*>(s_mem + (size_t)2 * kWarps * p.MP) + (size_t)warp * p.MP;  // node of every block
   const IndexView ix = p.ix;
   const uint32_t P = p.st.n_profiles;
   const char* row_base = reinterpret_cast<const char*>(ix.rows + t * VEC);
   const uint32_t row_bytes = 4u << ix.logW;
   const uint32_t zero_slot = (uint32_t)(ix.C + 2);  // never written: all-zero row
 
-  // Dynamic work queue over the probe pass's records, most expensive bin first (longest-processing-time-first:
-  // the requests left for the end are the cheap ones, so no warp holds the kernel with a long request it drew
-  // late).  Lane b keeps the size of the b-th most expensive bin and the number of records before it.
-  uint32_t bin_n = 0, bin_before = 0;
-  {
-    if ((uint32_t)lane < kProbeBins) bin_n = __ldg(p.bin_count + (kProbeBins - 1 - lane));
-    uint32_t inc = bin_n;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(FULL, inc, d);
-      if (lane >= d) inc += o;
-    }
-    bin_before = inc - bin_n;
-  }
-  // record of ticket tk (tk < R): two 16-byte loads, the same addresses in every lane
-  auto fetch = [&](uint32_t tk, uint4& lo, uint4& hi) {
-    const unsigned in = __ballot_sync(FULL, (uint32_t)lane < kProbeBins && tk < bin_before + bin_n);
-    const int bl = __ffs(in) - 1;  // first bin (in cost order) whose range covers the ticket
-    const uint32_t before = __shfl_sync(FULL, bin_before, bl);
-    const uint4* src = reinterpret_cast<const uint4*>(p.recs + (size_t)(kProbeBins - 1 - bl) * p.rec_pitch + (tk - before));
-    lo = __ldg(src);
-    hi = __ldg(src + 1);
+  // Dynamic work queue (requests differ a lot in how many rows they touch), software-pipelined across requests:
+  // while request r is matched, the ticket of the request after next is in flight, the chain of the next one is
+  // being staged into the other buffer, and the home bucket of its first block is being fetched (lanes 0-3:
+  // one key + node each) — a request starts with its chain and its first node already there instead of waiting
+  // out three dependent round trips (ticket -> chain -> table), a third of a request's time in round 1.
+  const uint32_t row_units = p.MP / 2;  // 16-byte units of a chain row (rows are zero-padded to MP by the walker)
+  auto stage = [&](uint32_t rr, uint64_t* dst) {
+    const uint64_t* crow = p.chain + (uint64_t)rr * p.MP;
+    for (uint32_t u = lane; u < row_units; u += 32) cp_async16(dst + 2 * u, crow + 2 * u);
   };
-  // the record of the next request is fetched while the current one is matched: the ticket atomic and the record
-  // read are off the critical path
-  uint32_t tk = 0;
-  if (lane == 0) tk = take_ticket(p.work_counter, threadIdx.x & p.lane_zero);
-  tk = __shfl_sync(FULL, tk, 0);
-  uint4 rlo = make_uint4(0, 0, 0, 0), rhi = rlo;
-  if (tk < p.R) fetch(tk, rlo, rhi);
+  uint32_t r_next = 0;
+  if (lane == 0) r_next = take_ticket(p.work_counter, threadIdx.x & p.lane_zero);
+  r_next = __shfl_sync(FULL, r_next, 0);
+  int buf = 0;
+  if (r_next < p.R) stage(r_next, s_chain_base);
+  // prefetched home bucket of the current request's first block (valid when pf_ok)
+  bool pf_ok = false;
+  uint64_t pf_h = 0, pf_key = 0;
+  uint32_t pf_node = 0;
   for (;;) {
-    if (tk >= p.R) break;
-    uint32_t tk_next = 0;
-    if (lane == 0) tk_next = take_ticket(p.work_counter, threadIdx.x & p.lane_zero);
-    const uint32_t r = rlo.x, node0 = rlo.y, n = rlo.z >> 16, m_run = rlo.z & 0xFFFFu;
-    const bool complete = rlo.w != 0;
-    const uint64_t h_first = (uint64_t)rhi.x | ((uint64_t)rhi.y << 32);
+    const uint32_t r = r_next;
+    if (r >= p.R) break;
+    if (lane == 0) r_next = take_ticket(p.work_counter, threadIdx.x & p.lane_zero);
+    const uint32_t n = p.nblocks[r];
+    uint64_t* s_chain = s_chain_base + (size_t)buf * p.MP;
 #ifdef FI_MATCH_TIMING
     const long long tm0 = clock64();
-    const long long tm1 = tm0;
+#endif
+    // ---- 1. the chain was staged during the previous request (or just above)
+    cp_async_wait_all();
+    __syncwarp();
+    // first block's node from the prefetched bucket
+    bool have_first = false;
+    uint32_t first_node = SLOT_MISS;
+    if (pf_ok && n) {
+      const unsigned hit = __ballot_sync(FULL, lane < BUCKET_KEYS && pf_key == pf_h);
+      const unsigned emp = __ballot_sync(FULL, lane < BUCKET_KEYS && pf_key == KEY_EMPTY);
+      if (hit) {
+        first_node = __shfl_sync(FULL, pf_node, __ffs(hit) - 1);
+        have_first = true;
+      } else if (emp) {
+        have_first = true;  // definite miss
+      }  // else: home bucket full without a match — resolve_request_nodes probes on
+    }
+
+#ifdef FI_MATCH_TIMING
+    const long long tm1 = clock64();
 #endif
     BitCounter cnt[VEC];
     uint32_t alive[VEC];
@@ -397,40 +330,32 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
     uint32_t matched_rows = 0;
     bool real_miss = false;
 
-    // ---- 2. nodes: the probe pass's run, or (scattered prefix) the rest resolved here ------------
-    uint32_t m_rows = m_run;  // blocks [0, m_rows) are present
-    if (!complete) {
-      const uint64_t* crow = p.chain + (uint64_t)r * p.MP;
-      for (uint32_t u = lane; 2 * u < n; u += 32) cp_async16(s_chain + 2 * u, crow + 2 * u);
-      for (uint32_t j = lane; j < m_run; j += 32) s_node[j] = node0 + j;
-      cp_async_wait_all();
-      __syncwarp();
-      m_rows = resolve_request_nodes(ix, s_chain, s_node, n, lane, m_run, 1);
-      __syncwarp();  // s_node is written by some lanes and read by others
-    }
+    // ---- 2. the index node of every block up to the first one no endpoint holds ---------------
+    const uint32_t m_rows = resolve_request_nodes(ix, s_chain, s_node, n, lane, have_first, first_node);
     real_miss = m_rows < n;
+    __syncwarp();  // s_node is written by some lanes and read by others
+    // ---- the next request: its ticket has long arrived; stage its chain and read its first hash
+    r_next = __shfl_sync(FULL, r_next, 0);
+    pf_ok = false;
+    if (r_next < p.R) {
+      stage(r_next, s_chain_base + (size_t)(buf ^ 1) * p.MP);
+      pf_h = __ldg(p.chain + (uint64_t)r_next * p.MP);
+    }
 #ifdef FI_MATCH_TIMING
     const long long tm2 = clock64();
 #endif
     // ---- 3. the rows of those blocks: independent loads, BATCH instructions (BATCH * G rows) in flight --
-    bool fetched_next = false;
 #pragma unroll 1
     for (uint32_t b0 = 0; b0 < m_rows; b0 += BATCH * G) {
       uint32_t w[VEC][BATCH];
 #pragma unroll
       for (int qi = 0; qi < BATCH; ++qi) {
         const uint32_t j = b0 + qi * G + g;  // row this lane helps read; rows past the end read the permanently
-        // zero row instead of being predicated off
-        const uint32_t sn = j < m_rows ? (complete ? node0 + j : s_node[j]) : zero_slot;
+        const uint32_t sn = j < m_rows ? s_node[j] : zero_slot;  // zero row instead of being predicated off
         uint32_t tmp[VEC];
         load_row_words<VEC>(reinterpret_cast<const uint32_t*>(row_base + (uint64_t)sn * row_bytes), true, tmp);
 #pragma unroll
         for (int x = 0; x < VEC; ++x) w[x][qi] = tmp[x];
-      }
-      if (!fetched_next) {  // the next ticket has arrived: read its record under this request's rows
-        fetched_next = true;
-        tk = __shfl_sync(FULL, tk_next, 0);
-        if (tk < p.R) fetch(tk, rlo, rhi);
       }
       if (LPM) {
 #pragma unroll
@@ -471,11 +396,15 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
         if (!__ballot_sync(FULL, any)) break;
       }
     }
-    if (!fetched_next) {  // (no rows)
-      tk = __shfl_sync(FULL, tk_next, 0);
-      if (tk < p.R) fetch(tk, rlo, rhi);
-    }
 
+    if (r_next < p.R && !key_is_special(pf_h)) {  // pf_h has arrived by now: fetch its home bucket, used next iteration
+      pf_ok = true;
+      if (lane < BUCKET_KEYS) {
+        const uint64_t slot0 = (pf_h & ix.bmask) * BUCKET_KEYS + lane;
+        pf_key = __ldg(ix.keys + slot0);
+        pf_node = __ldg(ix.node_of + slot0);
+      }
+    }
 #ifdef FI_MATCH_TIMING
     const long long tm3 = clock64();
 #endif
@@ -498,7 +427,7 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
     TieRot tr;
     tr.E = p.E_global;
     tr.ep_begin = p.ep_begin;
-    tr.start = tie_start(tie_seed(n, n ? h_first : 0ull, n ? 0ull : p.h0[r], p.r_base + r), p.E_global);
+    tr.start = tie_start(tie_seed(n, n ? s_chain[0] : 0ull, n ? 0ull : p.h0[r], p.r_base + r), p.E_global);
     uint32_t dec_e = FI_NO_ENDPOINT, dec_m = 0;
 #pragma unroll
     for (int pi = 0; pi < (int)FI_EPP_MAX_PROFILES; ++pi) {
@@ -641,6 +570,7 @@ __global__ void __launch_bounds__(kWarps * 32, (VEC >= 4 ? FI_MATCH_MIN_BLOCKS :
       }
 #endif
     }
+    buf ^= 1;
     __syncwarp();  // this request's s_chain / s_node reads are done before the buffers are written again
   }
 }
@@ -818,7 +748,7 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const EndpointD
 
 template <int LPR, int VEC>
 cudaError_t launch_match_t(const MatchParams& p, int sm_count, cudaStream_t s) {
-  const size_t smem = (size_t)kWarps * p.MP * (sizeof(uint64_t) + sizeof(uint32_t));  // chain + nodes of a scattered request
+  const size_t smem = (size_t)kWarps * p.MP * (2 * sizeof(uint64_t) + sizeof(uint32_t));  // 2 chain buffers + nodes
   auto go = [&](auto kern) -> cudaError_t {
     // occupancy is a property of (kernel, smem): query once per distinct smem size
     static size_t cached_smem_dev[64];
@@ -850,11 +780,6 @@ cudaError_t launch_match_t(const MatchParams& p, int sm_count, cudaStream_t s) {
       e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
       if (e != cudaSuccess) return e;
     }
-    e = cudaMemsetAsync(p.bin_count, 0, 32 * sizeof(uint32_t), s);
-    if (e != cudaSuccess) return e;
-    chain_probe_kernel<<<(p.R + 7) / 8, 256, 0, s>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
     kern<<<grid, kWarps * 32, smem, s>>>(p);
     return cudaGetLastError();
   };
