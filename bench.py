@@ -389,7 +389,7 @@ class Scenario:
         if R_override:
             self.wl.R = R_override
         self.nb = batches or max(1, args.batches)
-        self.split_hash = True
+        self.split_hash = False  # sharded pools: every rank hashes every prompt (the library default); True = split + all-gather
 
     # -- sampled requests whose picks the oracle re-derives (known BEFORE the index is built, so that every rank
     # can keep just the index entries those requests can touch: for them that is equivalent to the full index)
@@ -705,7 +705,7 @@ def main():
 
     # ---- main scenario (untimed set-up) ------------------------------------------------------------
     sc = Scenario(args, cfg_id, mode, rank, world, local, order=args.index_order, R_override=wl.R if args.scale != 1.0 else None)
-    sc.split_hash = os.environ.get("FI_EPP_SHARD_HASH", "split") != "replicated"
+    sc.split_hash = os.environ.get("FI_EPP_SHARD_HASH", "replicated") == "split"
     sc.build()
     picker, R, P = sc.picker, sc.wl.R, sc.P
     wl = sc.wl
@@ -831,14 +831,12 @@ def main():
         others = {}
         for cid in (2, 5):
             x = Scenario(args, cid, "replicas", rank, world, local, batches=2 if cid == 2 else 1).build(sample=512)
-            x.split_hash = True
             others[f"cfg{cid}"] = sub_record(x, args.extra_steps, 3, peak)
             x.close()
         roofline["configs"] = others
         order = {"chain": {"decisions_per_s": value, "ms_per_step": ms_step, "match_pick_ms": avg_ms["match_pick"]}}
         for od in ("shuffled", "churned"):
             x = Scenario(args, 3, "replicas", rank, world, local, order=od, batches=1).build()
-            x.split_hash = True
             ms, _ = x.time_steps(args.extra_steps, 3)
             av, _ = x.kernel_split(8)
             order[od] = {"decisions_per_s": R / (ms * 1e-3), "ms_per_step": ms, "match_pick_ms": av["match_pick"], "index": x.index_stats}
@@ -851,15 +849,16 @@ def main():
         sharded = {}
         for cid in (4, 5):
             x = Scenario(args, cid, "sharded", rank, world, local, batches=1)
-            x.split_hash = True
             x.build(sample=512)
             rec = sub_record(x, args.extra_steps, 3, peak)
             variants = {}
-            for name, opts in (("nccl_exchange", {"exchange": 2}), ("replicated_hash", {"shard_hash": 0})):
+            # variants: the NCCL all-gather of the picks instead of the peer-memory exchange; split hashing (every rank
+            # hashes R/world prompts and the chains are all-gathered) instead of every rank hashing every prompt
+            for name, opts in (("nccl_exchange", {"exchange": 2}), ("split_hash", {"shard_hash": 1})):
                 try:
                     for k, v in opts.items():
                         x.picker.set_option(k, v)
-                    x.split_hash = "shard_hash" not in opts
+                    x.split_hash = "shard_hash" in opts
                     ms, _ = x.time_steps(args.extra_steps, 3)
                     av, _ = x.kernel_split(8)
                     variants[name] = {"decisions_per_s": x.wl.R / (ms * 1e-3), "ms_per_step": ms, "kernel_ms": av}
@@ -868,7 +867,8 @@ def main():
                 finally:
                     try:
                         x.picker.set_option("exchange", 1 if x.exchange == "peer" else 2)
-                        x.picker.set_option("shard_hash", 1)
+                        x.picker.set_option("shard_hash", 0)
+                        x.split_hash = False
                     except Exception:  # noqa: BLE001
                         pass
             rec["variants"] = variants

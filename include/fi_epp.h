@@ -351,8 +351,9 @@ int fi_epp_comm_init(fi_epp* h, const uint8_t id[FI_EPP_UNIQUE_ID_BYTES], uint32
  * (score, endpoint) picks: FI_EXCHANGE_NONE (one rank), FI_EXCHANGE_PEER (default: the match kernel stores its
  * pick into every rank's buffer over NVLink peer memory / CUDA IPC and the merge kernel polls tagged words —
  * no collective call for the reduction) or FI_EXCHANGE_NCCL (one ncclAllGather: env FI_EPP_EXCHANGE=nccl,
- * more than 16 ranks, or a rank that cannot map a peer's buffer).  Hashing is split over the ranks and the
- * chains all-gathered (env FI_EPP_SHARD_HASH=replicated: every rank hashes every prompt instead). */
+ * more than 16 ranks, or a rank that cannot map a peer's buffer).  Every rank hashes every prompt (env
+ * FI_EPP_SHARD_HASH=split: hashing split over the ranks and the chains all-gathered instead — slower on NVLink-
+ * connected B200s: 16 KiB from local HBM cost less than 2 KiB over the link). */
 #define FI_EXCHANGE_NONE 0
 #define FI_EXCHANGE_PEER 1
 #define FI_EXCHANGE_NCCL 2
@@ -360,7 +361,9 @@ int fi_epp_comm_exchange(fi_epp* h);
 
 /* Runtime knobs (measurement and tuning; every one has a working default).  Names:
  *   "exchange"     sharded pick reduction: FI_EXCHANGE_PEER | FI_EXCHANGE_NCCL (PEER only if the peers were mapped)
- *   "shard_hash"   sharded hashing: 1 = split over the ranks + all-gather of the chains (default), 0 = replicated
+ *   "shard_hash"   sharded hashing: 0 = every rank hashes every prompt (default), 1 = split over the ranks + all-gather of the chains
+ *   "device_lru"   1 = per-endpoint LRUs resident in HBM (default on a single-rank handle), 0 = host LRU; before the first Add
+ *   "lru_table_slots"  slots per endpoint table of the device LRU (0 = sized by free HBM, 4..32 x lru_capacity)
  *   "feed_slices"  slices of a host-buffer pick's prompt copy, 1..16 (default 8)
  *   "lru_threads"  host worker threads of fi_epp_index_add_chains (takes effect at the next call)
  *   "pipe_hash_ctas", "pipe_match_ctas"  CTAs per SM of the two kernels the pipelined path runs side by side
