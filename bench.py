@@ -719,6 +719,7 @@ def main():
     units = R * (world if mode == "replicas" else 1)
     value = units / (ms_step * 1e-3)
     stream_ordered = None
+    pinfo = picker.pipeline_info() if pipelined else None
     if pipelined:  # the same K steps through the stream-ordered call, for reference
         ms_so, _ = sc.time_steps(min(args.steps, 50), 3, False)
         stream_ordered = {"decisions_per_s": units / (ms_so * 1e-3), "ms_per_step": ms_so,
@@ -885,8 +886,12 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": dict(workload_config(wl, cfg_id, f"{mode}{world}"), exchange=sc.exchange,
-                           pipeline=("fi_epp_pick_submit/pick_wait: 2 batches in flight, batch k+1 hashed while batch k "
-                                     "is matched; all K batches complete inside the timed region") if pipelined
+                           pipeline=((f"fi_epp_pick_submit/pick_wait on a partitioned GPU (green contexts): batch k matched and "
+                                      f"batch k+2 hashed on {pinfo['main_sms']} SMs while batch k+1's chains are walked on "
+                                      f"{pinfo['walk_sms']} SMs, 3 batches in flight; all K batches complete inside the timed region")
+                                     if pinfo and pinfo["partitioned"] else
+                                     ("fi_epp_pick_submit/pick_wait: 2 batches in flight, batch k+1 hashed while batch k "
+                                      "is matched; all K batches complete inside the timed region")) if pipelined
                            else "stream-ordered fi_epp_pick_batch_device calls"),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": int(launches),
             "parity": parity,

@@ -217,6 +217,7 @@ SYMBOLS = [
     ("fi_epp_index_add_chains_device", C.c_int, [_P, _P, _P, C.c_uint32, _P, C.c_uint32, _P]),
     ("fi_epp_lru_dump", C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _P]),
     ("fi_epp_lru_counters", C.c_int, [_P, _P]),
+    ("fi_epp_pipeline_info", C.c_int, [_P, _P]),
     ("fi_epp_set_option", C.c_int, [_P, C.c_char_p, C.c_int64]),
     ("fi_epp_index_sync", C.c_int, [_P]),
     ("fi_epp_index_contains", C.c_int, [_P, _P, C.c_uint64, _P]),

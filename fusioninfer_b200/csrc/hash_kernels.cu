@@ -189,8 +189,10 @@ __global__ void __launch_bounds__(256) hash_blocks_any_kernel(const uint8_t* __r
 //   * the loop is unrolled by two groups with the register roles swapped, so no buffer is ever copied;
 //   * the buffers are padded to whole groups (MP % 8 == 0): no per-unit predicates.
 // Entries [n, MP) of every row are zeroed.
-constexpr int kRing = 4;   // ring slots
-constexpr int kAhead = 3;  // prefetch distance in groups (= kRing - 1)
+// kRing ring slots, prefetch distance kRing - 1 groups.  Two shapes: RING = 4 with the whole register file (one warp
+// per scheduler on 128 SMs: nothing else hides the pre-state loads), and RING = 3 capped at 64 registers / 24 KB so
+// that ALL 128 CTAs fit on the 16 SMs of the pipelined path's walker partition (eight warps per scheduler hide each
+// other's latency there).
 
 __device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -214,10 +216,12 @@ __device__ __forceinline__ ulonglong2 lds16(const ulonglong2* p) {
 // Four warps (128 requests) per CTA, one per SM sub-partition.
 constexpr int kChainWarps = 4;
 
-__global__ void __launch_bounds__(kChainWarps * 32) chain_finalize_kernel(const uint64_t* __restrict__ pre,
+template <int kRing, int MINB>
+__global__ void __launch_bounds__(kChainWarps * 32, MINB) chain_finalize_kernel(const uint64_t* __restrict__ pre,
                                                                           const uint32_t* __restrict__ nblocks,
                                                                           const uint64_t* __restrict__ h0, uint32_t R,
                                                                           uint32_t MP, uint64_t* __restrict__ chain) {
+  constexpr int kAhead = kRing - 1;
   __shared__ __align__(16) ulonglong2 s_ring[kChainWarps][kRing][4][32];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t grp = blockIdx.x * kChainWarps + warp;
@@ -382,10 +386,12 @@ cudaError_t launch_hash_blocks(const uint8_t* prompts, const uint64_t* offsets, 
 }
 
 cudaError_t launch_chain_finalize(const uint64_t* pre, const uint32_t* nblocks, const uint64_t* h0, uint32_t R,
-                                  uint32_t MP, uint64_t* chain, cudaStream_t s) {
+                                  uint32_t MP, uint64_t* chain, bool compact, cudaStream_t s) {
   if (R == 0) return cudaSuccess;
   const uint32_t groups = (R + 31) / 32;
-  chain_finalize_kernel<<<(groups + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, s>>>(pre, nblocks, h0, R, MP, chain);
+  const uint32_t grid = (groups + kChainWarps - 1) / kChainWarps;
+  if (compact) chain_finalize_kernel<3, 8><<<grid, kChainWarps * 32, 0, s>>>(pre, nblocks, h0, R, MP, chain);
+  else chain_finalize_kernel<4, 1><<<grid, kChainWarps * 32, 0, s>>>(pre, nblocks, h0, R, MP, chain);
   return cudaGetLastError();
 }
 

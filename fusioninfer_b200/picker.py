@@ -199,6 +199,12 @@ class EndpointPicker:
         self._check(self._lib.fi_epp_lru_dump(self._h, endpoint, _ptr(out), cap, C.byref(n)), "fi_epp_lru_dump")
         return out[: n.value].copy()
 
+    def pipeline_info(self) -> dict:
+        """How pick_submit runs: partitioned GPU (three batches in flight) or not (two)."""
+        out = (C.c_int32 * 3)()
+        self._check(self._lib.fi_epp_pipeline_info(self._h, out), "fi_epp_pipeline_info")
+        return {"partitioned": bool(out[0]), "walk_sms": int(out[1]), "main_sms": int(out[2])}
+
     def lru_counters(self) -> dict:
         """Totals of the device-resident LRU since create (diagnostics)."""
         out = (C.c_uint64 * 6)()

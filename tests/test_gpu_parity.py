@@ -501,8 +501,10 @@ def test_pick_parity_after_churn_and_rebuild():
     gpu.close()
 
 
-def test_pipelined_submit_equals_oracle_with_index_updates_in_between():
-    """fi_epp_pick_submit keeps two batches in flight (batch k+1 is hashed while batch k is matched).  Seven
+@pytest.mark.parametrize("partition", [None, 0, 16])
+def test_pipelined_submit_equals_oracle_with_index_updates_in_between(partition):
+    """fi_epp_pick_submit keeps two batches in flight (batch k+1 is hashed while batch k is matched) — three on a
+    partitioned GPU (the default where green contexts exist: chain walk on its own SMs; 0 = unpartitioned).  Seven
     different batches of different sizes are submitted back to back, index updates and a pod-state refresh
     are interleaved (each batch must see the index and the pod states as of ITS submit call), stream-ordered
     picks are mixed in; after one fi_epp_pick_wait every output equals the oracle's."""
@@ -513,6 +515,8 @@ def test_pipelined_submit_equals_oracle_with_index_updates_in_between():
     pd = dict(pd, threshold=900.0)
     cfg = H.config_for(wl, profiles=profiles, pd=pd)
     gpu, cpu = _pair(cfg)
+    if partition is not None:
+        gpu.set_option("pipe_partition", partition)
     st = wl.endpoint_states()
     gpu.update_endpoints(st)
     cpu.update_endpoints(st)
@@ -829,4 +833,50 @@ def test_device_lru_from_device_chains():
         gpu.index_add_chains_device(got[:, 0]["endpoint"], d_ch.data_ptr(), wl.max_blocks, got[:, 0]["n_blocks"], stream=stream)
         cpu.index_add_chains(want[:, 0]["endpoint"], wch, want[:, 0]["n_blocks"])
     assert gpu.index_stats().tombstones > 0
+    gpu.close()
+
+
+@pytest.mark.parametrize("partition", [None, 0])
+def test_pipelined_back_to_back_batches(partition):
+    """Twelve batches of different sizes submitted back to back with nothing in between (so that the pipeline really
+    has its two — partitioned GPU: three — batches in flight and reuses every slot buffer several times), one wait
+    at the end, every output equal to the oracle's; then the same again after a stream-ordered pick."""
+    import torch
+
+    wl = H.small_workload(E=200, R=512, T=2048, max_blocks=128)
+    cfg = H.config_for(wl, profiles=WEIGHTED)
+    gpu, cpu = _pair(cfg)
+    if partition is not None:
+        gpu.set_option("pipe_partition", partition)
+    _load(wl, gpu, cpu)
+    s = torch.cuda.current_stream().cuda_stream
+    sizes = [512, 37, 512, 1, 300, 512, 512, 64, 511, 512, 200, 512]
+    for rnd in range(2):
+        keep, wants, outs = [], [], []
+        for k, R in enumerate(sizes):
+            tok, offs = wl.prompts(batch=k + 20 * rnd)
+            tok = np.ascontiguousarray(tok[:R])
+            offs = offs[: R + 1].copy()
+            d_tok = torch.from_numpy(tok.view(np.int32)).cuda()
+            d_off = torch.from_numpy(offs.view(np.int64)).cuda()
+            d_h0 = torch.full((R,), np.uint64(wl.h0).astype(np.int64), dtype=torch.int64, device="cuda")
+            d_out = torch.zeros(R * 16, dtype=torch.uint8, device="cuda")
+            keep.append((d_tok, d_off, d_h0))
+            wants.append(cpu.pick_batch(tok, offs, wl.h0))
+            outs.append(d_out)
+        torch.cuda.synchronize()
+        for k, R in enumerate(sizes):
+            d_tok, d_off, d_h0 = keep[k]
+            gpu.pick_submit(d_tok.data_ptr(), d_off.data_ptr(), d_h0.data_ptr(), R, int(d_tok.numel()) * 4, outs[k].data_ptr(), s)
+        gpu.pick_wait(s)
+        torch.cuda.synchronize()
+        for k, R in enumerate(sizes):
+            got = outs[k].cpu().numpy().view(H.PICK_DTYPE).reshape(R, 1)
+            assert H.picks_equal(got, wants[k]), f"round {rnd} batch {k}\n" + H.describe_diff(got, wants[k])
+        if rnd == 0:  # a stream-ordered pick between the two pipelined rounds
+            tok, offs = wl.prompts(batch=99)
+            assert H.picks_equal(gpu.pick_batch(tok, offs, wl.h0), cpu.pick_batch(tok, offs, wl.h0))
+    info = gpu.pipeline_info()
+    if partition == 0:
+        assert not info["partitioned"]
     gpu.close()
