@@ -838,7 +838,7 @@ def main():
         order = {"chain": {"decisions_per_s": value, "ms_per_step": ms_step, "match_pick_ms": avg_ms["match_pick"]}}
         for od in ("shuffled", "churned"):
             x = Scenario(args, 3, "replicas", rank, world, local, order=od, batches=1).build()
-            ms, _ = x.time_steps(args.extra_steps, 3)
+            ms, _ = x.time_steps(args.extra_steps, 3, pipelined)  # the same API as the headline
             av, _ = x.kernel_split(8)
             order[od] = {"decisions_per_s": R / (ms * 1e-3), "ms_per_step": ms, "match_pick_ms": av["match_pick"], "index": x.index_stats}
             x.close()

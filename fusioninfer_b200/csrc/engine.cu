@@ -2530,7 +2530,12 @@ int fi_epp_set_option(fi_epp* h, const char* name, int64_t value) {
   if (n == "pipe_partition") {
     if (value < 0 || value > 64) return fail(h, FI_ERR_INVALID, "pipe_partition: 0 (off) or the walker partition's SM count");
     if (h->part_state == 1 && value == 0) {
-      h->part_state = -1;  // back to the unpartitioned pipeline (contexts are released with the handle)
+      // back to the unpartitioned pipeline (contexts are released with the handle); nothing of the partitioned
+      // one may still be in flight: the two share the pre-state / chain buffers
+      cudaSetDevice(h->cfg.device);
+      for (cudaStream_t st : {h->s_pa, h->s_pw, h->s_pb})
+        if (st) cudaStreamSynchronize(st);
+      h->part_state = -1;
       h->part_active = false;
     } else if (h->part_state != 1) {
       h->part_want = (int)value;
