@@ -618,9 +618,8 @@ int choose_lru_mode(fi_epp* h) {
   if (want < 0) {
     if (const char* e = std::getenv("FI_EPP_DEVICE_LRU")) want = std::strtol(e, nullptr, 10) != 0;
   }
-  const bool possible = h->world <= 1 && h->cfg.lru_capacity >= h->cfg.max_blocks && h->cfg.lru_capacity <= (1u << 28);
-  if (want == 1 && !possible)
-    return fail(h, FI_ERR_STATE, "device_lru needs a single-rank handle and lru_capacity >= max_blocks");
+  const bool possible = h->cfg.lru_capacity >= h->cfg.max_blocks && h->cfg.lru_capacity <= (1u << 28);
+  if (want == 1 && !possible) return fail(h, FI_ERR_STATE, "device_lru needs lru_capacity >= max_blocks");
   h->lru_mode = (want < 0 ? possible : want == 1) ? 1 : 0;
   return FI_OK;
 }
@@ -714,10 +713,20 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
   if (rc != FI_OK) return rc;
   const auto t0 = std::chrono::steady_clock::now();
   LruPlan& pl = h->lru_plan;
-  lru_plan_batch(endpoints, nblocks, R, lo, EL, conservative ? h->cfg.lru_capacity : 0xFFFFFFFFu, h->lru_touch_cap, h->cfg.max_batch,
-                 &pl);
-  if (pl.subs.empty()) return FI_OK;
+  // sharded pool: a sub-batch's APPEAR / VANISH transitions must fit the gossip log of one round (at most one SET per
+  // touch; CLEARs: evictions <= keys added, plus doomed entries <= touches)
+  const bool sharded = h->world > 1;
+  const uint64_t cap_touches = sharded ? std::min<uint64_t>(h->lru_touch_cap, kOpChunk / 2) : h->lru_touch_cap;
+  lru_plan_batch(endpoints, nblocks, R, lo, EL, conservative ? h->cfg.lru_capacity : 0xFFFFFFFFu, cap_touches, h->cfg.max_batch, &pl);
+  if (pl.subs.empty() && !sharded) return FI_OK;
   const size_t K = pl.req_id.size(), nsub = pl.subs.size();
+  // collective on a sharded pool: the ranks' sub-batch counts differ, every one is a gossip round for all
+  uint64_t rounds = nsub;
+  if (sharded) {
+    rc = agree_rounds(h, nsub, &rounds);
+    if (rc != FI_OK) return rc;
+  }
+  const GossipLog glog = gossip_log(h);
   // staging: req_id | req_ep | req_n | req_off | ep_list | ep_start[nsub][EL+1] | inc[nsub][EL]
   const size_t words = 5 * K + nsub * ((size_t)2 * EL + 1);
   FI_CUDA(cudaEventSynchronize(h->ev_lru));  // the previous call's staging (and chain copy) has been consumed
@@ -733,6 +742,7 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
     h->lru_plan_cap = cap;
   }
   uint32_t* hp = h->h_lru_plan;
+  if (words) {
   std::memcpy(hp, pl.req_id.data(), K * 4);
   std::memcpy(hp + K, pl.req_ep.data(), K * 4);
   std::memcpy(hp + 2 * K, pl.req_n.data(), K * 4);
@@ -740,13 +750,14 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
   std::memcpy(hp + 4 * K, pl.ep_list.data(), K * 4);
   std::memcpy(hp + 5 * K, pl.ep_start.data(), pl.ep_start.size() * 4);
   std::memcpy(hp + 5 * K + nsub * ((size_t)EL + 1), pl.inc.data(), pl.inc.size() * 4);
+  }
   // the LRU kernels run on the index stream; like every index update they are ordered behind the picks
   // submitted so far (a pick sees the index as of its call)
   FI_CUDA(cudaStreamWaitEvent(h->s_index, h->ev_pick, 0));
-  FI_CUDA(cudaMemcpyAsync(h->d_lru_plan, hp, words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_index));
+  if (words) FI_CUDA(cudaMemcpyAsync(h->d_lru_plan, hp, words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_index));
   h->stats.h2d_bytes += words * sizeof(uint32_t);
   const uint64_t* d_chains = chains;
-  if (!on_device) {
+  if (!on_device && K) {
     const size_t cw = (size_t)R * pitch;
     if (cw > h->lru_chains_cap) {
       cudaFree(h->d_lru_chains);
@@ -774,7 +785,12 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
   std::vector<uint8_t> deferred;  // per request of this call: its endpoint overflowed in the optimistic pass
   std::vector<uint32_t> ovf_host;
   size_t n_deferred = 0;
-  for (size_t sb = 0; sb < nsub; ++sb) {
+  for (size_t sb = 0; sb < rounds; ++sb) {
+    if (sb >= nsub) {  // (sharded) this rank is done: it only takes part in the others' gossip rounds
+      rc = gossip_round(h);
+      if (rc != FI_OK) return rc;
+      continue;
+    }
     if (sb) {  // the index counters of the previous sub-batch decide about a rebuild before more keys arrive
       rc = check_counters(h);
       if (rc != FI_OK) return rc;
@@ -840,7 +856,7 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
     }
     {
       LaunchScope ls(h, h->s_index, K_INDEX);
-      FI_CUDA(launch_index_set(h->ix, h->d_ctr, h->d_lru_sets, sbt.touches, lo, EL, h->rank, GossipLog{}, h->s_index));
+      FI_CUDA(launch_index_set(h->ix, h->d_ctr, h->d_lru_sets, sbt.touches, lo, EL, h->rank, glog, h->s_index));
     }
     {
       LaunchScope ls(h, h->s_index, K_INDEX);
@@ -850,13 +866,17 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
       // CLEARs of a sub-batch: at most one per entry that was in the LRUs before it and per key it added
       const uint64_t cap = std::min<uint64_t>(h->lru_touch_cap, sbt.touches + (uint64_t)EL * h->cfg.lru_capacity);
       LaunchScope ls(h, h->s_index, K_INDEX);
-      FI_CUDA(launch_index_clear_counted(h->ix, h->d_ctr, h->d_lru_clears, cap, h->d_lru_ctr + 2, lo, EL, h->rank, GossipLog{},
+      FI_CUDA(launch_index_clear_counted(h->ix, h->d_ctr, h->d_lru_clears, cap, h->d_lru_ctr + 2, lo, EL, h->rank, glog,
                                          h->s_index));
     }
     if (any_ovf) FI_CUDA(cudaMemsetAsync(h->dlru.ovf, 0, ((size_t)EL + 1) * sizeof(uint32_t), h->s_index));  // ovf[] and any_ovf
     FI_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(IndexCounters), cudaMemcpyDeviceToHost, h->s_index));
     FI_CUDA(cudaEventRecord(h->ev_ctr, h->s_index));
     h->ctr_pending = true;
+    if (sharded) {  // the other ranks replay this sub-batch's transitions into their directories (and we theirs)
+      rc = gossip_round(h);
+      if (rc != FI_OK) return rc;
+    }
   }
   rc = lru_refresh_stat(h);
   if (rc != FI_OK) return rc;
@@ -870,9 +890,9 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
                  std::chrono::duration<double, std::milli>(t1 - t0).count());
   }
   h->lru_deferred += n_deferred;
-  if (n_deferred) {
+  if (n_deferred || (sharded && !conservative)) {  // (sharded: every rank enters the second pass, most with nothing to do)
     std::vector<uint32_t> ep2(R);
-    for (uint32_t r = 0; r < R; ++r) ep2[r] = deferred[r] ? endpoints[r] : FI_NO_ENDPOINT;
+    for (uint32_t r = 0; r < R; ++r) ep2[r] = (n_deferred && deferred[r]) ? endpoints[r] : FI_NO_ENDPOINT;
     return lru_device_add(h, ep2.data(), d_chains, true, pitch, nblocks, R, true);
   }
   return FI_OK;
@@ -1939,7 +1959,7 @@ int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes,
   std::lock_guard<std::mutex> lk(h->mu);
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
   if (!h->cfg.lru_capacity) return fail(h, FI_ERR_STATE, "lru_capacity is 0: the host LRU is disabled");
-  if (h->world > 1) return fail(h, FI_ERR_STATE, "sharded pool: use the collective fi_epp_index_add_chains");
+  if (h->world > 1) return fail(h, FI_ERR_STATE, "sharded pool: use the collective fi_epp_index_add_chains");  // (device LRU too)
   if (endpoint >= h->cfg.num_endpoints) return fail(h, FI_ERR_INVALID, "endpoint out of range");
   const uint32_t e = endpoint - h->cfg.endpoint_begin;
   if (e >= h->cfg.endpoint_count) return FI_OK;  // another rank's shard
