@@ -171,6 +171,11 @@ struct fi_epp {
                                 // not fit (fewer than 24 SMs); FI_EPP_WALK_COMPACT=0/1 forces it
   int part_state = 0;           // 0: not tried, 1: active, -1: unavailable (fallback to the unpartitioned pipeline)
   bool part_active = false;     // the partitioned pipeline has batches in flight / owns the slot events
+  // how often ev_index / ev_plain / ev_lru have been re-recorded, and the values the partitioned pipeline's streams
+  // already waited for: a submit makes ~16 runtime calls instead of ~23 (eight processes on a 16-core host are
+  // launch-bound otherwise)
+  uint64_t gen_index = 0, gen_plain = 0, gen_lru = 0;
+  uint64_t seen_index = ~0ull, seen_plain = ~0ull, seen_lru = ~0ull;
   uint64_t part_seq = 0;        // batches submitted to it since it last became active
   int part_walk_sms = 0, part_main_sms = 0;
   CUgreenCtx gctx_walk = nullptr, gctx_main = nullptr;
@@ -476,6 +481,7 @@ int check_counters(fi_epp* h) {
     int rc = rebuild_index(h);
     if (rc != FI_OK) return rc;
     FI_CUDA(cudaEventRecord(h->ev_index, h->s_index));
+  h->gen_index++;
   }
   return FI_OK;
 }
@@ -523,6 +529,7 @@ int flush_ops(fi_epp* h) {
   FI_CUDA(cudaEventRecord(h->ev_ctr, h->s_index));
   h->ctr_pending = true;
   FI_CUDA(cudaEventRecord(h->ev_index, h->s_index));
+  h->gen_index++;
   h->n_sets = h->n_clears = 0;
   h->cleared.clear();
   h->cur_buf ^= 1;
@@ -574,6 +581,7 @@ int gossip_round(fi_epp* h) {
     h->ctr_pending = true;
   }
   FI_CUDA(cudaEventRecord(h->ev_index, h->s_index));
+  h->gen_index++;
   return FI_OK;
 }
 
@@ -650,7 +658,7 @@ int ensure_dev_lru(fi_epp* h) {
   d.insert_limit = (uint32_t)((uint64_t)d.TS * 85 / 100);
   const size_t slot_bytes = (size_t)EL * (d.TS + 2) * sizeof(LruSlot), log_bytes = (size_t)EL * d.L * sizeof(uint64_t);
   h->lru_touch_cap = std::max<uint64_t>((uint64_t)h->cfg.max_batch * h->MP, 1u << 16);
-  const size_t scratch = (size_t)h->lru_touch_cap * (sizeof(uint32_t) + 2 * sizeof(fi_index_op));
+  const size_t scratch = (size_t)h->lru_touch_cap * (sizeof(uint32_t) + 3 * sizeof(fi_index_op));
   if (slot_bytes + log_bytes + scratch + (256u << 20) > free_b)
     return fail(h, FI_ERR_NOMEM, "device LRU does not fit in free HBM (option device_lru = 0 selects the host LRU)");
   const size_t state_words = (size_t)7 * EL + 2;
@@ -662,7 +670,7 @@ int ensure_dev_lru(fi_epp* h) {
   std::memset(h->h_lru_stat, 0, sizeof(fi_epp::LruHostStat));
   FI_CUDA(cudaMalloc(&h->d_lru_slot_of, h->lru_touch_cap * sizeof(uint32_t)));
   FI_CUDA(cudaMalloc(&h->d_lru_sets, h->lru_touch_cap * sizeof(fi_index_op)));
-  FI_CUDA(cudaMalloc(&h->d_lru_clears, h->lru_touch_cap * sizeof(fi_index_op)));
+  FI_CUDA(cudaMalloc(&h->d_lru_clears, 2 * h->lru_touch_cap * sizeof(fi_index_op)));  // doomed keys + evictions
   FI_CUDA(cudaMalloc(&h->d_lru_wcount, (size_t)h->cfg.max_batch * sizeof(uint32_t)));
   FI_CUDA(cudaMalloc(&h->d_lru_base, (size_t)h->cfg.max_batch * sizeof(uint32_t)));
   FI_CUDA(cudaEventCreateWithFlags(&h->ev_lru, cudaEventDisableTiming));
@@ -671,6 +679,7 @@ int ensure_dev_lru(fi_epp* h) {
   FI_CUDA(cudaMemsetAsync(h->d_lru_state, 0, state_words * sizeof(uint32_t), h->s_index));
   FI_CUDA(cudaMemsetAsync(h->d_lru_ctr, 0, 8 * sizeof(unsigned long long), h->s_index));
   FI_CUDA(cudaEventRecord(h->ev_lru, h->s_index));
+  h->gen_lru++;
   d.head = h->d_lru_state;
   d.tail = d.head + EL;
   d.count = d.tail + EL;
@@ -852,7 +861,7 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
     }
     {
       LaunchScope ls(h, h->s_index, K_INDEX);
-      FI_CUDA(launch_lru_append(h->dlru, b, h->d_lru_clears, h->d_lru_ctr + 2, h->lru_touch_cap, lo, h->s_index));
+      FI_CUDA(launch_lru_append(h->dlru, b, h->d_lru_clears, h->d_lru_ctr + 2, 2 * h->lru_touch_cap, lo, h->s_index));
     }
     {
       LaunchScope ls(h, h->s_index, K_INDEX);
@@ -860,11 +869,11 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
     }
     {
       LaunchScope ls(h, h->s_index, K_INDEX);
-      FI_CUDA(launch_lru_evict(h->dlru, h->d_lru_clears, h->d_lru_ctr + 2, h->lru_touch_cap, lo, h->s_index));
+      FI_CUDA(launch_lru_evict(h->dlru, h->d_lru_clears, h->d_lru_ctr + 2, 2 * h->lru_touch_cap, lo, h->s_index));
     }
     {
-      // CLEARs of a sub-batch: at most one per entry that was in the LRUs before it and per key it added
-      const uint64_t cap = std::min<uint64_t>(h->lru_touch_cap, sbt.touches + (uint64_t)EL * h->cfg.lru_capacity);
+      // CLEARs of a sub-batch: at most one per doomed key (<= touches) and one per eviction (<= keys it added)
+      const uint64_t cap = std::min<uint64_t>(2 * h->lru_touch_cap, 2 * sbt.touches);
       LaunchScope ls(h, h->s_index, K_INDEX);
       FI_CUDA(launch_index_clear_counted(h->ix, h->d_ctr, h->d_lru_clears, cap, h->d_lru_ctr + 2, lo, EL, h->rank, glog,
                                          h->s_index));
@@ -882,7 +891,9 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
   if (rc != FI_OK) return rc;
   FI_CUDA(cudaEventRecord(h->ev_ctr, h->s_index));  // covers the status copy too
   FI_CUDA(cudaEventRecord(h->ev_lru, h->s_index));
+  h->gen_lru++;
   FI_CUDA(cudaEventRecord(h->ev_index, h->s_index));
+  h->gen_index++;
   if (h->verbose) {
     const auto t1 = std::chrono::steady_clock::now();
     std::fprintf(stderr, "[fi_epp] device LRU%s: %u requests (%zu kept), %zu sub-batch(es), %zu deferred, host side %.3f ms\n",
@@ -1268,6 +1279,7 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
   if (rc != FI_OK) return rc;
   FI_CUDA(cudaEventRecord(h->ev_pick, h->s_main));  // index updates submitted later wait for this pick
   FI_CUDA(cudaEventRecord(h->ev_plain, h->s_main));
+  h->gen_plain++;
   h->last_plain_R = R;
   return FI_OK;
 }
@@ -1372,8 +1384,14 @@ int submit_pick_partitioned(fi_epp* h, const uint8_t* d_prompts, const uint64_t*
   // match(k-3) has; d_pre / d_chain are shared with stream-ordered picks and with the device LRU's reads
   FI_CUDA(cudaEventRecord(h->ev_in, us));
   FI_CUDA(cudaStreamWaitEvent(h->s_pa, h->ev_in, 0));
-  FI_CUDA(cudaStreamWaitEvent(h->s_pa, h->ev_plain, 0));
-  if (h->ev_lru) FI_CUDA(cudaStreamWaitEvent(h->s_pa, h->ev_lru, 0));
+  if (h->seen_plain != h->gen_plain) {
+    FI_CUDA(cudaStreamWaitEvent(h->s_pa, h->ev_plain, 0));
+    h->seen_plain = h->gen_plain;
+  }
+  if (h->ev_lru && h->seen_lru != h->gen_lru) {
+    FI_CUDA(cudaStreamWaitEvent(h->s_pa, h->ev_lru, 0));
+    h->seen_lru = h->gen_lru;
+  }
   if (h->part_seq >= 2) FI_CUDA(cudaStreamWaitEvent(h->s_pa, h->ev_a[s2], 0));
   if (h->part_seq >= 3) FI_CUDA(cudaStreamWaitEvent(h->s_pa, h->ev_b3[s3], 0));
   {
@@ -1391,13 +1409,18 @@ int submit_pick_partitioned(fi_epp* h, const uint8_t* d_prompts, const uint64_t*
   }
   FI_CUDA(cudaEventRecord(h->ev_a[s2], h->s_pw));
   // ---- match(k): every submitted index op and pod-state update is visible
-  int rc = upload_endpoints(h);  // (on s_main)
-  if (rc != FI_OK) return rc;
-  rc = upload_lora(h);
-  if (rc != FI_OK) return rc;
-  FI_CUDA(cudaEventRecord(h->ev_up, h->s_main));
-  FI_CUDA(cudaStreamWaitEvent(h->s_pb, h->ev_up, 0));
-  FI_CUDA(cudaStreamWaitEvent(h->s_pb, h->ev_index, 0));
+  if (h->eps_dirty || h->lora_dirty) {
+    int rc = upload_endpoints(h);  // (on s_main)
+    if (rc != FI_OK) return rc;
+    rc = upload_lora(h);
+    if (rc != FI_OK) return rc;
+    FI_CUDA(cudaEventRecord(h->ev_up, h->s_main));
+    FI_CUDA(cudaStreamWaitEvent(h->s_pb, h->ev_up, 0));
+  }
+  if (h->seen_index != h->gen_index) {
+    FI_CUDA(cudaStreamWaitEvent(h->s_pb, h->ev_index, 0));
+    h->seen_index = h->gen_index;
+  }
   FI_CUDA(cudaStreamWaitEvent(h->s_pb, h->ev_a[s2], 0));
   MatchParams mp{};
   fill_match_params(h, mp, chain, nb, d_offsets, d_h0, nullptr, R, d_out, true);
@@ -1435,6 +1458,7 @@ int submit_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, 
       FI_CUDA(cudaStreamWaitEvent(h->s_pw, h->ev_pick, 0));
       h->part_active = true;
       h->part_seq = 0;
+      h->seen_index = h->seen_plain = h->seen_lru = ~0ull;
     }
     return submit_pick_partitioned(h, d_prompts, d_offsets, d_h0, R, d_out, us);
   }

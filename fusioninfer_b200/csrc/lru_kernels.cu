@@ -11,9 +11,10 @@
 // on the way.  So the state after a batch of touches depends only on every key's LAST touch: per endpoint, the
 // keys touched in the batch, ordered by their last touch (the WINNERS), go behind everything older, and the
 // content is cut to the newest C.  A winner followed by C or more other winners is gone again by the end of the
-// batch (DOOMED: it never reaches the index, or is CLEARed if it was there before); the index gets SET for the
-// surviving winners that were new to the endpoint and CLEAR for the entries that fell off — the same membership
-// as R sequential Adds, whatever those inserted and evicted in between.
+// batch (DOOMED: CLEARed — sequential Adds would have SET and evicted it, so the pair ends up absent whatever put
+// it into the index before); the index gets SET for the surviving winners that were new to the endpoint and CLEAR
+// for the entries that fell off — the same membership as R sequential Adds, whatever those inserted and evicted
+// in between.
 //
 // Capacity.  A table takes the batch's distinct keys on top of its C entries; it holds 0.85 TS, with TS between
 // 4 C and 32 C slots depending on how much HBM is free (engine.cu: a B200 gives 1 024 endpoints 1 Mi slots each).
@@ -269,14 +270,14 @@ __global__ void __launch_bounds__(256) lru_append_kernel(DevLru lru, LruBatch b,
       const uint64_t key = chain[j];
       const bool was_entry = tab[slot].posp1 != 0;
       if (rank < doomed_below) {
-        // touched, but C or more distinct keys were touched after it: not in the LRU at the end of the batch
+        // touched, but C or more distinct keys were touched after it: not in the LRU at the end of the batch.
+        // Sequential Adds would have SET it and evicted (CLEARed) it again, so the pair must end up absent from
+        // the index even if something else put it there (fi_epp_index_apply bypasses the LRU): always CLEAR
         lru_retire(tab, lru.TS, slot);
         ++doomed;
-        if (was_entry) {
-          ++lost;
-          const unsigned long long c = atomicAdd(n_clears, 1ull);
-          if (c < clears_cap) clears[c] = fi_index_op{key, ep_begin + e, FI_OP_CLEAR};
-        }
+        if (was_entry) ++lost;
+        const unsigned long long c = atomicAdd(n_clears, 1ull);
+        if (c < clears_cap) clears[c] = fi_index_op{key, ep_begin + e, FI_OP_CLEAR};
       } else {
         const uint32_t p = hold + (rank - doomed_below);
         if (p < lru.L) log[p] = key;
@@ -312,11 +313,11 @@ __global__ void __launch_bounds__(256) lru_append_kernel(DevLru lru, LruBatch b,
       atomicAdd(lru.count + e, s_fresh);
       atomicAdd(lru.n_sets, (unsigned long long)s_fresh);
     }
-    if (s_lost) {
-      atomicSub(lru.count + e, s_lost);
-      atomicAdd(lru.n_clears, (unsigned long long)s_lost);
+    if (s_lost) atomicSub(lru.count + e, s_lost);
+    if (s_doomed) {
+      atomicAdd(lru.n_doomed, (unsigned long long)s_doomed);
+      atomicAdd(lru.n_clears, (unsigned long long)s_doomed);
     }
-    if (s_doomed) atomicAdd(lru.n_doomed, (unsigned long long)s_doomed);
   }
 }
 
