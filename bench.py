@@ -507,8 +507,10 @@ class Scenario:
 
     def run_steps(self, k, pipelined=False):
         if pipelined:
+            t0 = time.perf_counter()
             for i in range(k):
                 self.submit(i)
+            self.submit_us = (time.perf_counter() - t0) * 1e6 / max(k, 1)  # host time per submit (launch-bound if ~ the step)
             self.picker.pick_wait(self.stream)
         else:
             for i in range(k):
@@ -720,6 +722,8 @@ def main():
     value = units / (ms_step * 1e-3)
     stream_ordered = None
     pinfo = picker.pipeline_info() if pipelined else None
+    if pinfo is not None:
+        pinfo["host_us_per_submit"] = round(getattr(sc, "submit_us", 0.0), 1)
     if pipelined:  # the same K steps through the stream-ordered call, for reference
         ms_so, _ = sc.time_steps(min(args.steps, 50), 3, False)
         stream_ordered = {"decisions_per_s": units / (ms_so * 1e-3), "ms_per_step": ms_so,
@@ -888,7 +892,8 @@ def main():
             "config": dict(workload_config(wl, cfg_id, f"{mode}{world}"), exchange=sc.exchange,
                            pipeline=((f"fi_epp_pick_submit/pick_wait on a partitioned GPU (green contexts): batch k matched and "
                                       f"batch k+2 hashed on {pinfo['main_sms']} SMs while batch k+1's chains are walked on "
-                                      f"{pinfo['walk_sms']} SMs, 3 batches in flight; all K batches complete inside the timed region")
+                                      f"{pinfo['walk_sms']} SMs, 3 batches in flight; all K batches complete inside the timed region; "
+                                      f"host time per submit {pinfo['host_us_per_submit']} us on this rank")
                                      if pinfo and pinfo["partitioned"] else
                                      ("fi_epp_pick_submit/pick_wait: 2 batches in flight, batch k+1 hashed while batch k "
                                       "is matched; all K batches complete inside the timed region")) if pipelined

@@ -153,7 +153,9 @@ struct fi_epp {
   uint64_t* d_chain2 = nullptr;
   uint32_t* d_nblocks2 = nullptr;
   cudaEvent_t ev_in = nullptr, ev_a[2] = {}, ev_b[2] = {};
-  cudaEvent_t ev_pick = nullptr;   // completion of the most recent pick of any kind on s_main
+  cudaEvent_t ev_pick = nullptr;   // completion of the most recent pick of any kind: ev_pick_own, or (partitioned
+                                   // pipeline) the slot event of the batch submitted last — a handle, not a second record
+  cudaEvent_t ev_pick_own = nullptr;
   cudaEvent_t ev_plain = nullptr;  // completion of the most recent stream-ordered (not pipelined) pick
   uint64_t pipe_seq = 0;          // batches submitted
   uint32_t pipe_hash_ctas = 0;    // per-SM caps of the pipelined path's two co-running kernels (0 = uncapped);
@@ -1277,6 +1279,7 @@ int run_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, con
              const uint64_t* d_adapters, uint32_t R, fi_pick* d_out, const HostFeed* feed = nullptr) {
   int rc = run_pick_impl(h, d_prompts, d_offsets, d_h0, d_adapters, R, d_out, feed);
   if (rc != FI_OK) return rc;
+  h->ev_pick = h->ev_pick_own;
   FI_CUDA(cudaEventRecord(h->ev_pick, h->s_main));  // index updates submitted later wait for this pick
   FI_CUDA(cudaEventRecord(h->ev_plain, h->s_main));
   h->gen_plain++;
@@ -1396,7 +1399,9 @@ int submit_pick_partitioned(fi_epp* h, const uint8_t* d_prompts, const uint64_t*
   if (h->part_seq >= 3) FI_CUDA(cudaStreamWaitEvent(h->s_pa, h->ev_b3[s3], 0));
   {
     LaunchScope ls(h, h->s_pa, K_HASH);
-    FI_CUDA(launch_hash_blocks(d_prompts, d_offsets, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, pre, nb, 0, h->s_pa));
+    // (the kernel also zeroes the request-queue counter of this batch's match_pick: one runtime call less per batch)
+    FI_CUDA(launch_hash_blocks(d_prompts, d_offsets, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, pre, nb, 0, h->s_pa,
+                               h->d_work + 8 + s3));
   }
   FI_CUDA(cudaEventRecord(h->ev_h[s2], h->s_pa));
   // ---- chain(k) on its own SMs: chain[s2] free once match(k-2) has read it
@@ -1425,12 +1430,13 @@ int submit_pick_partitioned(fi_epp* h, const uint8_t* d_prompts, const uint64_t*
   MatchParams mp{};
   fill_match_params(h, mp, chain, nb, d_offsets, d_h0, nullptr, R, d_out, true);
   mp.work_counter = h->d_work + 8 + s3;
+  mp.zero_work_counter = 0;  // hash_blocks of this batch did
   {
     LaunchScope ls(h, h->s_pb, K_MATCH);
     FI_CUDA(launch_match_pick(mp, h->part_main_sms, h->s_pb));
   }
   FI_CUDA(cudaEventRecord(h->ev_b3[s3], h->s_pb));
-  FI_CUDA(cudaEventRecord(h->ev_pick, h->s_pb));
+  h->ev_pick = h->ev_b3[s3];
   h->pipe_seq++;
   h->part_seq++;
   h->stats.pick_calls++;
@@ -1519,6 +1525,7 @@ int submit_pick(fi_epp* h, const uint8_t* d_prompts, const uint64_t* d_offsets, 
     FI_CUDA(launch_match_pick(mp, h->sm_count, h->s_main));
   }
   FI_CUDA(cudaEventRecord(h->ev_b[slot], h->s_main));
+  h->ev_pick = h->ev_pick_own;
   FI_CUDA(cudaEventRecord(h->ev_pick, h->s_main));
   h->pipe_seq++;
   h->stats.pick_calls++;
@@ -1707,7 +1714,7 @@ void fi_epp_destroy(fi_epp* h) {
     if (e) cudaEventDestroy(e);
   for (int k = 0; k < fi_epp::kMaxFeedSlices; ++k)
     if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);
-  for (cudaEvent_t e : {h->ev_in, h->ev_a[0], h->ev_a[1], h->ev_b[0], h->ev_b[1], h->ev_pick, h->ev_plain})
+  for (cudaEvent_t e : {h->ev_in, h->ev_a[0], h->ev_a[1], h->ev_b[0], h->ev_b[1], h->ev_pick_own, h->ev_plain})
     if (e) cudaEventDestroy(e);
   cudaFree(h->d_chain2);
   cudaFree(h->d_nblocks2);
@@ -1769,7 +1776,16 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   h->fast_hash = (cfg->block_bytes % 32) == 0;
   if (const char* e = std::getenv("FI_EPP_TRACE")) h->trace_call = std::strtol(e, nullptr, 10);
   h->verbose = std::getenv("FI_EPP_VERBOSE") != nullptr;
-  if (const char* e = std::getenv("FI_EPP_PIPE_PARTITION")) h->part_want = (int)std::strtol(e, nullptr, 10);
+  if (const char* e = std::getenv("FI_EPP_PIPE_PARTITION")) {
+    h->part_want = (int)std::strtol(e, nullptr, 10);
+  } else if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) {
+    // Measured: 1, 2 and 4 ranks per host run the partitioned pipeline at 116-117 us per batch; 8 ranks on a host
+    // whose cgroup grants 16 cores at 138.5 us, slower than unpartitioned (133.4 us) — the hand-offs between the
+    // partitions' streams go through the driver's host side, which starves at two cores per rank.  Keep the
+    // partition where a rank has at least three cores to itself.
+    const long ranks = std::strtol(lw, nullptr, 10);
+    if (ranks > 1 && usable_cores() < 3u * (unsigned)ranks) h->part_want = 0;
+  }
   if (const char* e = std::getenv("FI_EPP_WALK_COMPACT")) h->part_compact = std::strtol(e, nullptr, 10) != 0 ? 1 : 0;
   if (const char* e = std::getenv("FI_EPP_PIPE_HASH_CTAS")) h->pipe_hash_ctas = (uint32_t)std::strtol(e, nullptr, 10);
   if (const char* e = std::getenv("FI_EPP_PIPE_MATCH_CTAS")) h->pipe_match_ctas = (uint32_t)std::strtol(e, nullptr, 10);
@@ -1787,8 +1803,9 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   FI_TRY(cudaStreamCreateWithFlags(&h->s_index, cudaStreamNonBlocking));
   FI_TRY(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
   FI_TRY(cudaStreamCreateWithFlags(&h->s_a, cudaStreamNonBlocking));
-  for (cudaEvent_t* e : {&h->ev_in, &h->ev_a[0], &h->ev_a[1], &h->ev_b[0], &h->ev_b[1], &h->ev_pick, &h->ev_plain})
+  for (cudaEvent_t* e : {&h->ev_in, &h->ev_a[0], &h->ev_a[1], &h->ev_b[0], &h->ev_b[1], &h->ev_pick_own, &h->ev_plain})
     FI_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  h->ev_pick = h->ev_pick_own;
   for (int k = 0; k < fi_epp::kMaxFeedSlices; ++k) FI_TRY(cudaEventCreateWithFlags(&h->ev_copy[k], cudaEventDisableTiming));
   if (const char* e = std::getenv("FI_EPP_FEED_SLICES")) {
     const long v = std::strtol(e, nullptr, 10);

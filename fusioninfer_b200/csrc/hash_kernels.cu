@@ -69,10 +69,11 @@ template <int STRIPES>
 __global__ void __launch_bounds__(256, STRIPES <= 2 ? 8 : 5) hash_blocks_kernel(const uint8_t* __restrict__ prompts,
                                                           const uint64_t* __restrict__ offsets, uint32_t R, uint32_t M,
                                                           uint32_t MP, uint64_t* __restrict__ pre,
-                                                          uint32_t* __restrict__ nblocks) {
+                                                          uint32_t* __restrict__ nblocks, uint32_t* __restrict__ zero_word) {
   constexpr uint32_t B = STRIPES * 32;
   const uint32_t MP2 = MP / 2;
   const uint64_t pol = make_evict_first_policy();
+  if (zero_word && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0;
   // one request per CTA pass; the grid is R CTAs, or capped when the kernel has to share the SMs with the
   // previous batch's match_pick (pipelined API)
   for (uint32_t r = blockIdx.x; r < R; r += gridDim.x) {
@@ -369,19 +370,22 @@ __global__ void __launch_bounds__(128) hash_generic_kernel(const uint8_t* __rest
 }  // namespace
 
 cudaError_t launch_hash_blocks(const uint8_t* prompts, const uint64_t* offsets, uint32_t R, uint32_t B, uint32_t M,
-                               uint32_t MP, uint64_t* pre, uint32_t* nblocks, uint32_t grid_cap, cudaStream_t s) {
+                               uint32_t MP, uint64_t* pre, uint32_t* nblocks, uint32_t grid_cap, cudaStream_t s,
+                               uint32_t* zero_word) {
   if (R == 0) return cudaSuccess;
   uint32_t threads = (M + 31) / 32 * 32;
   if (threads > 256) threads = 256;
   const uint32_t grid = (grid_cap && grid_cap < R) ? grid_cap : R;
   if (B == 64)
-    hash_blocks_kernel<2><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks);
+    hash_blocks_kernel<2><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks, zero_word);
   else if (B == 32)
-    hash_blocks_kernel<1><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks);
+    hash_blocks_kernel<1><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks, zero_word);
   else if (B == 128)
-    hash_blocks_kernel<4><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks);
-  else
+    hash_blocks_kernel<4><<<grid, threads, 0, s>>>(prompts, offsets, R, M, MP, pre, nblocks, zero_word);
+  else {
     hash_blocks_any_kernel<<<R, threads, 0, s>>>(prompts, offsets, B, M, MP, pre, nblocks);
+    if (zero_word) cudaMemsetAsync(zero_word, 0, sizeof(uint32_t), s);
+  }
   return cudaGetLastError();
 }
 

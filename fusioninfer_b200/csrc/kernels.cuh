@@ -175,9 +175,10 @@ struct MergeParams {
 
 // ---- launchers (each returns the cudaGetLastError() of its launch) -----------
 // grid_cap: 0 = one CTA per request; else at most that many CTAs (the pipelined API shares the SMs with match_pick)
+// zero_word: optional device word the kernel clears (the pipelined path's request-queue counter of the batch)
 cudaError_t launch_hash_blocks(const uint8_t* prompts, const uint64_t* offsets, uint32_t R, uint32_t B,
                                uint32_t M, uint32_t MP, uint64_t* pre, uint32_t* nblocks, uint32_t grid_cap,
-                               cudaStream_t s);
+                               cudaStream_t s, uint32_t* zero_word = nullptr);
 // compact: the 64-register / 24 KB shape whose 128 CTAs all fit on a 16-SM partition (pipelined path)
 cudaError_t launch_chain_finalize(const uint64_t* pre, const uint32_t* nblocks, const uint64_t* h0,
                                   uint32_t R, uint32_t MP, uint64_t* chain, bool compact, cudaStream_t s);
