@@ -134,7 +134,7 @@ typedef struct fi_epp_config {
   int32_t device;       /* CUDA ordinal */
   uint32_t block_bytes; /* blockSize | hashBlockSize (strategy.go:57,147); 64 = 16 u32 tokens */
   uint32_t max_blocks;  /* maxPrefixBlocksToMatch (strategy.go:58,148) */
-  uint32_t lru_capacity; /* lruCapacityPerServer (strategy.go:59,149); 0 disables the host LRU */
+  uint32_t lru_capacity; /* lruCapacityPerServer (strategy.go:59,149); 0: no LRU (fi_epp_index_add_chain* fail) */
   uint32_t num_endpoints;  /* global pool size E */
   uint32_t endpoint_begin; /* this handle's shard [begin, begin+count) of the pool */
   uint32_t endpoint_count;
@@ -202,7 +202,7 @@ typedef struct fi_index_stats {
   uint64_t tombstones; /* keys whose row became empty */
   uint64_t rebuilds;
   uint64_t ops_applied;
-  uint64_t lru_entries; /* host LRU: sum over endpoints */
+  uint64_t lru_entries; /* entries of the per-endpoint LRUs (device-resident or host), summed */
 } fi_index_stats;
 
 typedef struct fi_epp_stats {
@@ -267,17 +267,18 @@ int fi_epp_index_add_chain(fi_epp* h, uint32_t endpoint, const uint64_t* hashes,
 
 /* The same for a whole batch of routing decisions — upstream's PreRequest step after a pick batch:
  * indexer.Add(chains[r*pitch_blocks .. +nblocks[r]), endpoints[r]) for r = 0..R-1 (FI_NO_ENDPOINT and
- * endpoints of other shards are skipped).  Equal to R fi_epp_index_add_chain calls in request order; the
- * endpoints' LRUs are walked in parallel on host worker threads (FI_EPP_LRU_THREADS, default = usable
- * cores, at most 128).  `chains` / `nblocks` are what fi_epp_pick_batch returned (chains_out, picks'
- * n_blocks).  Collective on a sharded pool. */
+ * endpoints of other shards are skipped).  Equal to R fi_epp_index_add_chain calls in request order.  With the
+ * device-resident LRU (the default, see below) the chains are copied to the GPU and the whole batch is applied
+ * by a handful of kernels; with the host LRU the endpoints' LRUs are walked in parallel on host worker threads
+ * (FI_EPP_LRU_THREADS, default = usable cores, at most 128).  `chains` / `nblocks` are what fi_epp_pick_batch
+ * returned (chains_out, picks' n_blocks).  Collective on a sharded pool. */
 int fi_epp_index_add_chains(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains, uint32_t pitch_blocks,
                             const uint32_t* nblocks, uint32_t R);
 
 /* The same with the chains already in device memory — the chains_out of fi_epp_pick_batch_device, written on
  * `stream` — so that only the two small host arrays cross PCIe.  Served by the device-resident LRU
- * (fusioninfer_b200/csrc/lru_kernels.cu), which is also what fi_epp_index_add_chain(s) use on a single-rank
- * handle with lru_capacity >= max_blocks unless fi_epp_set_option(h, "device_lru", 0) / FI_EPP_DEVICE_LRU=0
+ * (fusioninfer_b200/csrc/lru_kernels.cu), which is also what fi_epp_index_add_chain(s) use on a handle with
+ * lru_capacity >= max_blocks (sharded pools included) unless fi_epp_set_option(h, "device_lru", 0) / FI_EPP_DEVICE_LRU=0
  * selected the host LRU before the first Add; FI_ERR_STATE when the handle runs the host LRU.
  * d_chains == NULL: the chains of this handle's most recent fi_epp_pick_batch / fi_epp_pick_batch_device call,
  * read from the handle's own buffer (pitch_blocks ignored; R <= that call's R) — the PreRequest step right after
@@ -367,7 +368,7 @@ int fi_epp_comm_exchange(fi_epp* h);
 /* Runtime knobs (measurement and tuning; every one has a working default).  Names:
  *   "exchange"     sharded pick reduction: FI_EXCHANGE_PEER | FI_EXCHANGE_NCCL (PEER only if the peers were mapped)
  *   "shard_hash"   sharded hashing: 0 = every rank hashes every prompt (default), 1 = split over the ranks + all-gather of the chains
- *   "device_lru"   1 = per-endpoint LRUs resident in HBM (default on a single-rank handle), 0 = host LRU; before the first Add
+ *   "device_lru"   1 = per-endpoint LRUs resident in HBM (default when lru_capacity >= max_blocks), 0 = host LRU; before the first Add
  *   "lru_table_slots"  slots per endpoint table of the device LRU (0 = sized by free HBM, 4..32 x lru_capacity)
  *   "feed_slices"  slices of a host-buffer pick's prompt copy, 1..16 (default 8)
  *   "lru_threads"  host worker threads of fi_epp_index_add_chains (takes effect at the next call)
