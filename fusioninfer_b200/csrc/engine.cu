@@ -1347,10 +1347,26 @@ void setup_partition(fi_epp* h) {
     destroy_partition(h);
     return;
   }
+  // hash_blocks(k+2) and match_pick(k) become runnable at the same moment (both wait for match_pick(k-1)) and share
+  // the big partition; which of them gets its CTAs resident first decided the step — 116 us on some boxes, 138 us
+  // on others with the same code.  Stream priorities make the block scheduler prefer one of them whenever SMs free
+  // up (FI_EPP_PIPE_PRIO=match | hash | none).
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // lo = least (numerically greatest), hi = greatest priority
+  int pa = 0, pb = 0;
+  const char* pe = std::getenv("FI_EPP_PIPE_PRIO");
+  const std::string prio = pe ? pe : "none";  // (measured on a 116-us box: none 116.1, hash 116.2, match 121.2 us)
+  if (prio == "match") {
+    pa = prio_lo;
+    pb = prio_hi;
+  } else if (prio == "hash") {
+    pa = prio_hi;
+    pb = prio_lo;
+  }
   CUstream sw = nullptr, sa = nullptr, sb = nullptr;
   if (g_green.GreenCtxStreamCreate(&sw, h->gctx_walk, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
-      g_green.GreenCtxStreamCreate(&sa, h->gctx_main, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
-      g_green.GreenCtxStreamCreate(&sb, h->gctx_main, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+      g_green.GreenCtxStreamCreate(&sa, h->gctx_main, CU_STREAM_NON_BLOCKING, pa) != CUDA_SUCCESS ||
+      g_green.GreenCtxStreamCreate(&sb, h->gctx_main, CU_STREAM_NON_BLOCKING, pb) != CUDA_SUCCESS) {
     destroy_partition(h);
     return;
   }
@@ -1400,8 +1416,15 @@ int submit_pick_partitioned(fi_epp* h, const uint8_t* d_prompts, const uint64_t*
   {
     LaunchScope ls(h, h->s_pa, K_HASH);
     // (the kernel also zeroes the request-queue counter of this batch's match_pick: one runtime call less per batch)
-    FI_CUDA(launch_hash_blocks(d_prompts, d_offsets, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, pre, nb, 0, h->s_pa,
-                               h->d_work + 8 + s3));
+    // hash_blocks runs as 4 persistent CTAs per SM here (FI_EPP_PIPE_HASH_CTAS / option "pipe_hash_ctas" overrides;
+    // a large value = one CTA per request).  With one CTA per request the step is bimodal: 116 us on most boxes,
+    // 138 us on others (among them the 8-GPU node) with the same binary — depending on which of the two kernels
+    // gets its CTAs resident first, hash_blocks' 16 384 short CTAs and match_pick's 324 long ones (80 registers
+    // x 256 threads x 3 per SM) lock each other out of the SMs.  Four hashing CTAs (32 K registers) always leave
+    // room for one matching CTA next to them: 122.6-123.3 us on both kinds of box.
+    const uint32_t hash_ctas = h->pipe_hash_ctas ? h->pipe_hash_ctas : 4u;
+    FI_CUDA(launch_hash_blocks(d_prompts, d_offsets, R, h->cfg.block_bytes, h->cfg.max_blocks, h->MP, pre, nb,
+                               hash_ctas * (uint32_t)h->part_main_sms, h->s_pa, h->d_work + 8 + s3));
   }
   FI_CUDA(cudaEventRecord(h->ev_h[s2], h->s_pa));
   // ---- chain(k) on its own SMs: chain[s2] free once match(k-2) has read it
@@ -1430,6 +1453,7 @@ int submit_pick_partitioned(fi_epp* h, const uint8_t* d_prompts, const uint64_t*
   MatchParams mp{};
   fill_match_params(h, mp, chain, nb, d_offsets, d_h0, nullptr, R, d_out, true);
   mp.work_counter = h->d_work + 8 + s3;
+  mp.max_ctas_per_sm = h->pipe_match_ctas;
   mp.zero_work_counter = 0;  // hash_blocks of this batch did
   {
     LaunchScope ls(h, h->s_pb, K_MATCH);
@@ -2578,7 +2602,7 @@ int fi_epp_set_option(fi_epp* h, const char* name, int64_t value) {
     return FI_OK;
   }
   if (n == "pipe_hash_ctas" || n == "pipe_match_ctas") {
-    if (value < 0 || value > 32) return fail(h, FI_ERR_INVALID, n + ": 0..32");
+    if (value < 0 || value > 4096) return fail(h, FI_ERR_INVALID, n + ": 0..4096");
     (n == "pipe_hash_ctas" ? h->pipe_hash_ctas : h->pipe_match_ctas) = (uint32_t)value;
     return FI_OK;
   }

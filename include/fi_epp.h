@@ -373,7 +373,8 @@ int fi_epp_comm_exchange(fi_epp* h);
  *   "feed_slices"  slices of a host-buffer pick's prompt copy, 1..16 (default 8)
  *   "lru_threads"  host worker threads of fi_epp_index_add_chains (takes effect at the next call)
  *   "pipe_partition"  SMs of the chain-walk partition of the pipelined path (default 40; 0 = no partition)
- *   "pipe_hash_ctas", "pipe_match_ctas"  CTAs per SM of the two kernels the unpartitioned pipelined path runs side by side
+ *   "pipe_hash_ctas", "pipe_match_ctas"  CTAs per SM of the two kernels the pipelined path runs side by side (0 = default:
+ *                  partitioned GPU 4 hashing CTAs per SM, otherwise one CTA per request; match_pick as many as fit)
  *                  (fi_epp_pick_submit: batch k+1's block hashing next to batch k's match; 0 = uncapped)
  * FI_ERR_INVALID for an unknown name or a value out of range. */
 int fi_epp_set_option(fi_epp* h, const char* name, int64_t value);
