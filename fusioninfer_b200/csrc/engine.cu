@@ -1802,14 +1802,11 @@ int fi_epp_create(const fi_epp_config* cfg, fi_epp** out) {
   h->verbose = std::getenv("FI_EPP_VERBOSE") != nullptr;
   if (const char* e = std::getenv("FI_EPP_PIPE_PARTITION")) {
     h->part_want = (int)std::strtol(e, nullptr, 10);
-  } else if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) {
-    // Measured: 1, 2 and 4 ranks per host run the partitioned pipeline at 116-117 us per batch; 8 ranks on a host
-    // whose cgroup grants 16 cores at 138.5 us, slower than unpartitioned (133.4 us) — the hand-offs between the
-    // partitions' streams go through the driver's host side, which starves at two cores per rank.  Keep the
-    // partition where a rank has at least three cores to itself.
-    const long ranks = std::strtol(lw, nullptr, 10);
-    if (ranks > 1 && usable_cores() < 3u * (unsigned)ranks) h->part_want = 0;
   }
+  // (8 ranks on the 8-GPU node ran the partitioned pipeline at 138.5 us per batch with one hashing CTA per request,
+  // slower than unpartitioned (133.4 us).  That was first taken for host starvation — 16 cgroup cores for 8 ranks —
+  // and the partition switched off there; a single-GPU box then showed the same 138 us with one rank: it is the
+  // bimodal co-scheduling that the 4-CTA hashing default removes, so the partition stays on at any rank count.)
   if (const char* e = std::getenv("FI_EPP_WALK_COMPACT")) h->part_compact = std::strtol(e, nullptr, 10) != 0 ? 1 : 0;
   if (const char* e = std::getenv("FI_EPP_PIPE_HASH_CTAS")) h->pipe_hash_ctas = (uint32_t)std::strtol(e, nullptr, 10);
   if (const char* e = std::getenv("FI_EPP_PIPE_MATCH_CTAS")) h->pipe_match_ctas = (uint32_t)std::strtol(e, nullptr, 10);
