@@ -249,13 +249,14 @@ struct fi_epp {
   // the two are never mixed on one handle.
   int lru_mode = -1;  // -1: not chosen yet, 0: host LRU, 1: device LRU
   int lru_want = -1;  // option / environment override (-1: automatic)
+  bool dlru_ready = false;  // the device LRU's buffers are all there
   uint32_t lru_table_slots = 0;  // option "lru_table_slots": slots per endpoint table of the device LRU (0: sized by free HBM)
   DevLru dlru{};
   uint32_t* d_lru_state = nullptr;           // head | tail | count | used | error
   unsigned long long* d_lru_ctr = nullptr;   // [0] SETs emitted, [1] endpoints maintained, [2] CLEARs of the running sub-batch,
                                              // [3] CLEARs total, [4] doomed winners
   struct LruHostStat {
-    uint32_t error, pad;
+    uint32_t error, any_ovf;  // (any_ovf: the touch kernel's overflow flag of the running sub-batch)
     unsigned long long n_sets, n_maintained, n_clears_cur, n_clears, n_doomed;
   };
   uint64_t lru_deferred = 0, lru_sub_batches = 0;  // host-side totals
@@ -634,8 +635,46 @@ int choose_lru_mode(fi_epp* h) {
   return FI_OK;
 }
 
+void free_dev_lru(fi_epp* h) {
+  cudaFree(h->dlru.slots);
+  cudaFree(h->dlru.log);
+  cudaFree(h->d_lru_state);
+  cudaFree(h->d_lru_ctr);
+  if (h->h_lru_stat) cudaFreeHost(h->h_lru_stat);
+  cudaFree(h->d_lru_slot_of);
+  cudaFree(h->d_lru_wcount);
+  cudaFree(h->d_lru_base);
+  cudaFree(h->d_lru_sets);
+  cudaFree(h->d_lru_clears);
+  if (h->ev_lru) cudaEventDestroy(h->ev_lru);
+  if (h->ev_lru_ovf) cudaEventDestroy(h->ev_lru_ovf);
+  h->dlru = DevLru{};
+  h->d_lru_state = nullptr;
+  h->d_lru_ctr = nullptr;
+  h->h_lru_stat = nullptr;
+  h->d_lru_slot_of = h->d_lru_wcount = h->d_lru_base = nullptr;
+  h->d_lru_sets = h->d_lru_clears = nullptr;
+  h->ev_lru = h->ev_lru_ovf = nullptr;
+  h->dlru_ready = false;
+}
+
+int alloc_dev_lru(fi_epp* h);
+
 int ensure_dev_lru(fi_epp* h) {
-  if (h->dlru.slots) return FI_OK;
+  if (h->dlru_ready) return FI_OK;
+  const int rc = alloc_dev_lru(h);
+  if (rc != FI_OK) {  // nothing of a partial allocation survives (a later call may succeed, e.g. with the host LRU freed)
+    const std::string why = h->err;
+    cudaGetLastError();
+    free_dev_lru(h);
+    h->err = why;
+    return rc;
+  }
+  h->dlru_ready = true;
+  return FI_OK;
+}
+
+int alloc_dev_lru(fi_epp* h) {
   const uint32_t EL = h->cfg.endpoint_count, C = h->cfg.lru_capacity;
   DevLru& d = h->dlru;
   d.EL = EL;
@@ -832,10 +871,10 @@ int lru_device_add(fi_epp* h, const uint32_t* endpoints, const uint64_t* chains,
     }
     // did some endpoint's table refuse keys?  (one host round trip per sub-batch; everything after it is queued
     // without waiting)
-    FI_CUDA(cudaMemcpyAsync(&h->h_lru_stat->pad, h->dlru.any_ovf, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_index));
+    FI_CUDA(cudaMemcpyAsync(&h->h_lru_stat->any_ovf, h->dlru.any_ovf, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_index));
     FI_CUDA(cudaEventRecord(h->ev_lru_ovf, h->s_index));
     FI_CUDA(cudaEventSynchronize(h->ev_lru_ovf));
-    const bool any_ovf = h->h_lru_stat->pad != 0;
+    const bool any_ovf = h->h_lru_stat->any_ovf != 0;
     if (any_ovf) {
       if (conservative) return fail(h, FI_ERR_STATE, "device LRU: overflow in a conservative sub-batch");
       {
@@ -1705,21 +1744,10 @@ void fi_epp_destroy(fi_epp* h) {
   h->pool.reset();
   h->lrus.clear();
   h->lru_arena.release();
-  cudaFree(h->dlru.slots);
-  cudaFree(h->dlru.log);
-  cudaFree(h->d_lru_state);
-  cudaFree(h->d_lru_ctr);
-  if (h->h_lru_stat) cudaFreeHost(h->h_lru_stat);
+  free_dev_lru(h);
   cudaFree(h->d_lru_plan);
   if (h->h_lru_plan) cudaFreeHost(h->h_lru_plan);
-  cudaFree(h->d_lru_slot_of);
-  cudaFree(h->d_lru_wcount);
-  cudaFree(h->d_lru_base);
-  cudaFree(h->d_lru_sets);
-  cudaFree(h->d_lru_clears);
   cudaFree(h->d_lru_chains);
-  if (h->ev_lru) cudaEventDestroy(h->ev_lru);
-  if (h->ev_lru_ovf) cudaEventDestroy(h->ev_lru_ovf);
   free_index(h->ix);
   free_index(h->ix_spare);
   for (int b = 0; b < 2; ++b) {
@@ -2236,7 +2264,7 @@ int fi_epp_lru_dump(fi_epp* h, uint32_t endpoint, uint64_t* out, uint32_t cap, u
   *n_out = 0;
   const uint32_t e = endpoint - h->cfg.endpoint_begin;
   if (e >= h->cfg.endpoint_count) return fail(h, FI_ERR_INVALID, "endpoint outside this handle's shard");
-  if (h->lru_mode != 1 || !h->dlru.slots) return h->lru_mode == 0 ? fail(h, FI_ERR_STATE, "the handle runs the host LRU") : FI_OK;
+  if (h->lru_mode != 1 || !h->dlru_ready) return h->lru_mode == 0 ? fail(h, FI_ERR_STATE, "the handle runs the host LRU") : FI_OK;
   uint64_t* d_out = nullptr;
   uint32_t* d_n = nullptr;
   FI_CUDA(cudaMalloc(&d_out, ((size_t)h->dlru.capacity + 1) * sizeof(uint64_t)));
@@ -2263,7 +2291,7 @@ int fi_epp_lru_counters(fi_epp* h, uint64_t out[6]) {
   std::lock_guard<std::mutex> lk(h->mu);
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, FI_ERR_CUDA, "cudaSetDevice failed");
   for (int i = 0; i < 6; ++i) out[i] = 0;
-  if (h->lru_mode != 1 || !h->dlru.slots) return FI_OK;
+  if (h->lru_mode != 1 || !h->dlru_ready) return FI_OK;
   FI_CUDA(cudaStreamSynchronize(h->s_index));
   out[0] = h->h_lru_stat->n_sets;
   out[1] = h->h_lru_stat->n_clears;
@@ -2299,7 +2327,7 @@ int fi_epp_index_stats(fi_epp* h, fi_index_stats* out) {
   out->rebuilds = h->rebuilds;
   out->ops_applied = h->ops_applied;
   uint64_t l = 0;
-  if (h->lru_mode == 1 && h->dlru.slots) {
+  if (h->lru_mode == 1 && h->dlru_ready) {
     std::vector<uint32_t> cnt(h->dlru.EL);
     FI_CUDA(cudaMemcpy(cnt.data(), h->dlru.count, cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for (uint32_t c2 : cnt) l += c2;
@@ -2627,7 +2655,7 @@ int fi_epp_set_option(fi_epp* h, const char* name, int64_t value) {
   }
   if (n == "lru_table_slots") {
     if (value < 0 || value > (1ll << 30)) return fail(h, FI_ERR_INVALID, "lru_table_slots: 0 .. 2^30");
-    if (h->dlru.slots) return fail(h, FI_ERR_STATE, "lru_table_slots: the device LRU is already allocated");
+    if (h->dlru_ready) return fail(h, FI_ERR_STATE, "lru_table_slots: the device LRU is already allocated");
     h->lru_table_slots = (uint32_t)value;
     return FI_OK;
   }
